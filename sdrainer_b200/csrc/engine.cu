@@ -1,0 +1,876 @@
+// engine.cu -- libsdrgpu.so: engine, stream state, batching and the C ABI of include/sdrgpu.h.
+//
+// The engine is the device-side half of rx.Receiver.run (rx/receiver.go:336-464): it owns, per
+// stream, what the reference keeps in run()'s locals -- the float32 cumulation vector and its
+// counter (:340,:347) and the two 60-block rolling means (:343-344) -- and executes the frame
+// iteration (:364-461) for whole batches of queued frames with two kernels:
+//   K1 k1_spectral_kernel  FFT + |X|^2 + dB + noise floor + listener taps + cumulation
+//   K2 k2_post_kernel      rolling means/thresholds + key states + FindPeaks at flushes
+// Three CUDA streams (H2D, compute, D2H) with events give copy/compute overlap across in-flight
+// slots; kernels of successive batches stay ordered on the compute stream, which is what keeps
+// the per-stream state sequential.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/sdrgpu.h"
+#include "k1_spectral.cuh"
+#include "k2_post.cuh"
+#include "k3_goertzel.cuh"
+
+using namespace sdr;
+
+namespace {
+
+std::string g_create_error;
+
+struct StreamInfo {
+    bool open = false;
+    int sample_rate = 0;
+    int cum_count = 0;  // cumulationCount (rx/receiver.go:347)
+};
+
+struct Slot {
+    bool busy = false;
+    bool collected = false;
+    sdr_ticket ticket = 0;
+    int flags = 0;
+    // descriptors: one pinned staging block + one device block
+    unsigned char *h_desc = nullptr, *d_desc = nullptr;
+    size_t desc_bytes = 0;
+    // device results
+    float *d_psd_floor = nullptr;
+    double *d_variance = nullptr;
+    float *d_thresholds = nullptr;
+    float *d_taps = nullptr;
+    uint8_t *d_keys = nullptr;
+    int *d_flush_block = nullptr, *d_flush_n_peaks = nullptr;
+    sdr_peak *d_flush_peaks = nullptr;
+    float *d_flush_cum = nullptr;
+    float *d_spectrum = nullptr, *d_psd = nullptr;  // lazy (SDR_WANT_SPECTRUM)
+    float *d_iq = nullptr;                          // lazy (host inputs)
+    // pinned host mirrors
+    float *h_psd_floor = nullptr;
+    double *h_variance = nullptr;
+    float *h_thresholds = nullptr;
+    float *h_taps = nullptr;
+    uint8_t *h_keys = nullptr;
+    int *h_flush_block = nullptr, *h_flush_n_peaks = nullptr;
+    sdr_peak *h_flush_peaks = nullptr;
+    float *h_flush_cum = nullptr;
+    float *h_spectrum = nullptr, *h_psd = nullptr;  // lazy
+    std::vector<int> work_block_offset, work_flush_offset;
+    int n_works = 0, n_blocks = 0, n_flushes = 0, launches = 0;
+    cudaEvent_t ev_h2d = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
+};
+
+}  // namespace
+
+struct sdr_engine {
+    sdr_engine_config cfg{};
+    int N = 0;
+    int tap_stride = 4;
+    int max_segs = 0, max_flushes = 0;
+    int sm_count = 148;
+    std::string err;
+    cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    bool own_streams = true;
+    float2 *d_tw1 = nullptr, *d_tw2 = nullptr;
+    float *d_window = nullptr;
+    float *d_cum_state = nullptr;
+    RollingState *d_rolling = nullptr;
+    std::vector<StreamInfo> streams;
+    std::vector<Slot> slots;
+    sdr_ticket next_ticket = 1;
+    int64_t launches = 0;
+    int k1_grid_cap = 0;  // resident CTAs of K1 on this device
+    // scratch for the dsp single calls
+    float *d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+};
+
+namespace {
+
+#define CK(e, call)                                                                                  \
+    do {                                                                                             \
+        cudaError_t _st = (call);                                                                    \
+        if (_st != cudaSuccess) {                                                                    \
+            (e)->err = std::string(#call) + ": " + cudaGetErrorString(_st);                          \
+            return SDR_ECUDA;                                                                        \
+        }                                                                                            \
+    } while (0)
+
+bool supported_fused_n(int n) { return n == 512 || n == 1024 || n == 2048 || n == 4096; }
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// descriptor block layout (same on host and device)
+struct DescLayout {
+    size_t segs, works, post, lbins, total;
+};
+DescLayout desc_layout(const sdr_engine *e) {
+    DescLayout l;
+    size_t off = 0;
+    l.segs = off;
+    off = align_up(off + sizeof(Segment) * (size_t)e->max_segs, 256);
+    l.works = off;
+    off = align_up(off + sizeof(WorkParams) * (size_t)e->cfg.max_streams, 256);
+    l.post = off;
+    off = align_up(off + sizeof(PostWork) * (size_t)e->cfg.max_streams, 256);
+    l.lbins = off;
+    off = align_up(off + sizeof(int) * (size_t)e->cfg.max_streams * (size_t)(e->cfg.max_listeners > 0 ? e->cfg.max_listeners : 1), 256);
+    l.total = off;
+    return l;
+}
+
+template <int N>
+int k1_occupancy(bool dbg, bool win) {
+    using Gm = K1Geom<N>;
+    int occ = 0;
+    const void *fn;
+    if (dbg)
+        fn = win ? (const void *)k1_spectral_kernel<N, true, true> : (const void *)k1_spectral_kernel<N, true, false>;
+    else
+        fn = win ? (const void *)k1_spectral_kernel<N, false, true> : (const void *)k1_spectral_kernel<N, false, false>;
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, Gm::SMEM_BYTES);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, Gm::CTA_THREADS, Gm::SMEM_BYTES);
+    return occ;
+}
+
+template <int N>
+cudaError_t launch_k1_n(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st) {
+    using Gm = K1Geom<N>;
+    const bool win = a.window != nullptr;
+    int need = (a.n_segs + Gm::G - 1) / Gm::G;
+    int grid = need < e->k1_grid_cap ? need : e->k1_grid_cap;
+    if (grid < 1) grid = 1;
+    if (dbg) {
+        if (win)
+            k1_spectral_kernel<N, true, true><<<grid, Gm::CTA_THREADS, Gm::SMEM_BYTES, st>>>(a);
+        else
+            k1_spectral_kernel<N, true, false><<<grid, Gm::CTA_THREADS, Gm::SMEM_BYTES, st>>>(a);
+    } else {
+        if (win)
+            k1_spectral_kernel<N, false, true><<<grid, Gm::CTA_THREADS, Gm::SMEM_BYTES, st>>>(a);
+        else
+            k1_spectral_kernel<N, false, false><<<grid, Gm::CTA_THREADS, Gm::SMEM_BYTES, st>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_k1(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st) {
+    switch (e->N) {
+        case 512: return launch_k1_n<512>(e, a, dbg, st);
+        case 1024: return launch_k1_n<1024>(e, a, dbg, st);
+        case 2048: return launch_k1_n<2048>(e, a, dbg, st);
+        case 4096: return launch_k1_n<4096>(e, a, dbg, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+int k1_grid_cap_for(int n, bool win, int sm_count) {
+    int occ = 0;
+    switch (n) {
+        case 512: occ = std::max(k1_occupancy<512>(false, win), 0); k1_occupancy<512>(true, win); break;
+        case 1024: occ = k1_occupancy<1024>(false, win); k1_occupancy<1024>(true, win); break;
+        case 2048: occ = k1_occupancy<2048>(false, win); k1_occupancy<2048>(true, win); break;
+        case 4096: occ = k1_occupancy<4096>(false, win); k1_occupancy<4096>(true, win); break;
+    }
+    if (occ < 1) occ = 1;
+    return occ * sm_count;
+}
+
+void build_twiddles(int n, std::vector<float2> &tw1, std::vector<float2> &tw2) {
+    const int M = n / 16, R3 = n / 256;
+    tw1.resize((size_t)15 * M);
+    tw2.resize((size_t)15 * R3);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int k = 1; k < 16; k++)
+        for (int j = 0; j < M; j++) {
+            const double ang = -two_pi * (double)((long long)j * k % n) / (double)n;
+            tw1[(size_t)(k - 1) * M + j] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+    for (int k = 1; k < 16; k++)
+        for (int n3 = 0; n3 < R3; n3++) {
+            const double ang = -two_pi * (double)((n3 * k) % M) / (double)M;
+            tw2[(size_t)(k - 1) * R3 + n3] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+}
+
+void free_slot(Slot &s) {
+    cudaFreeHost(s.h_desc);
+    cudaFree(s.d_desc);
+    cudaFree(s.d_psd_floor);
+    cudaFree(s.d_variance);
+    cudaFree(s.d_thresholds);
+    cudaFree(s.d_taps);
+    cudaFree(s.d_keys);
+    cudaFree(s.d_flush_block);
+    cudaFree(s.d_flush_n_peaks);
+    cudaFree(s.d_flush_peaks);
+    cudaFree(s.d_flush_cum);
+    cudaFree(s.d_spectrum);
+    cudaFree(s.d_psd);
+    cudaFree(s.d_iq);
+    cudaFreeHost(s.h_psd_floor);
+    cudaFreeHost(s.h_variance);
+    cudaFreeHost(s.h_thresholds);
+    cudaFreeHost(s.h_taps);
+    cudaFreeHost(s.h_keys);
+    cudaFreeHost(s.h_flush_block);
+    cudaFreeHost(s.h_flush_n_peaks);
+    cudaFreeHost(s.h_flush_peaks);
+    cudaFreeHost(s.h_flush_cum);
+    cudaFreeHost(s.h_spectrum);
+    cudaFreeHost(s.h_psd);
+    if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+    if (s.ev_k0) cudaEventDestroy(s.ev_k0);
+    if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+    if (s.ev_done) cudaEventDestroy(s.ev_done);
+    s = Slot();
+}
+
+int alloc_slot(sdr_engine *e, Slot &s) {
+    const size_t MB = (size_t)e->cfg.max_blocks_per_batch, MF = (size_t)e->max_flushes, MP = (size_t)e->cfg.max_peaks_per_flush;
+    const size_t N = (size_t)e->N, TS = (size_t)e->tap_stride;
+    const DescLayout dl = desc_layout(e);
+    s.desc_bytes = dl.total;
+    CK(e, cudaMallocHost((void **)&s.h_desc, dl.total));
+    CK(e, cudaMalloc((void **)&s.d_desc, dl.total));
+    CK(e, cudaMalloc((void **)&s.d_psd_floor, MB * sizeof(float)));
+    CK(e, cudaMalloc((void **)&s.d_variance, MB * sizeof(double)));
+    CK(e, cudaMalloc((void **)&s.d_thresholds, MB * 4 * sizeof(float)));
+    CK(e, cudaMalloc((void **)&s.d_taps, MB * TS * sizeof(float)));
+    CK(e, cudaMalloc((void **)&s.d_keys, MB * TS));
+    CK(e, cudaMalloc((void **)&s.d_flush_block, MF * sizeof(int)));
+    CK(e, cudaMalloc((void **)&s.d_flush_n_peaks, MF * sizeof(int)));
+    CK(e, cudaMalloc((void **)&s.d_flush_peaks, MF * MP * sizeof(sdr_peak)));
+    CK(e, cudaMalloc((void **)&s.d_flush_cum, MF * N * sizeof(float)));
+    CK(e, cudaMallocHost((void **)&s.h_psd_floor, MB * sizeof(float)));
+    CK(e, cudaMallocHost((void **)&s.h_variance, MB * sizeof(double)));
+    CK(e, cudaMallocHost((void **)&s.h_thresholds, MB * 4 * sizeof(float)));
+    CK(e, cudaMallocHost((void **)&s.h_taps, MB * TS * sizeof(float)));
+    CK(e, cudaMallocHost((void **)&s.h_keys, MB * TS));
+    CK(e, cudaMallocHost((void **)&s.h_flush_block, MF * sizeof(int)));
+    CK(e, cudaMallocHost((void **)&s.h_flush_n_peaks, MF * sizeof(int)));
+    CK(e, cudaMallocHost((void **)&s.h_flush_peaks, MF * MP * sizeof(sdr_peak)));
+    CK(e, cudaMallocHost((void **)&s.h_flush_cum, MF * N * sizeof(float)));
+    CK(e, cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+    CK(e, cudaEventCreate(&s.ev_k0));
+    CK(e, cudaEventCreate(&s.ev_k1));
+    CK(e, cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    return SDR_OK;
+}
+
+Slot *find_slot(sdr_engine *e, sdr_ticket t) {
+    for (auto &s : e->slots)
+        if (s.busy && s.ticket == t) return &s;
+    return nullptr;
+}
+
+__global__ void __launch_bounds__(128) noise_floor_kernel(const float *psd, int n, int e, float *out_min, double *out_var) {
+    __shared__ double wsum[16];
+    const int ws = nf_window_size(n, e);
+    const int n_win = nf_window_count(n, e);
+    nf_window_sums<128>(psd, wsum, e, ws, n_win, threadIdx.x);
+    __syncthreads();
+    if (threadIdx.x < 32) nf_select_variance(psd, wsum, e, ws, n_win, threadIdx.x, out_min, out_var);
+}
+
+int ensure_scratch(sdr_engine *e, size_t bytes) {
+    if (e->scratch_bytes >= bytes) return SDR_OK;
+    if (e->d_scratch) cudaFree(e->d_scratch);
+    e->d_scratch = nullptr;
+    e->scratch_bytes = 0;
+    CK(e, cudaMalloc((void **)&e->d_scratch, bytes));
+    e->scratch_bytes = bytes;
+    return SDR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *sdr_version(void) { return "sdrgpu 0.1 (sm_100a)"; }
+
+int sdr_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char *sdr_last_error(const sdr_engine *e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
+    if (!cfg || !out) return SDR_EINVAL;
+    *out = nullptr;
+    if (!supported_fused_n(cfg->block_size)) {
+        g_create_error = "block_size must be 512, 1024, 2048 or 4096 for the fused path";
+        return SDR_EINVAL;
+    }
+    if (cfg->max_streams < 1 || cfg->max_blocks_per_batch < 1 || cfg->n_slots < 1 || cfg->max_listeners < 0 ||
+        cfg->max_listeners > K1Geom<2048>::LMAX || cfg->max_peaks_per_flush < 1) {
+        g_create_error = "bad engine configuration (max_listeners <= 256, everything else >= 1)";
+        return SDR_EINVAL;
+    }
+    sdr_engine *e = new (std::nothrow) sdr_engine();
+    if (!e) return SDR_ENOMEM;
+    e->cfg = *cfg;
+    e->N = cfg->block_size;
+    e->tap_stride = ((cfg->max_listeners > 0 ? cfg->max_listeners : 1) + 3) / 4 * 4;
+    e->max_segs = cfg->max_blocks_per_batch / SDR_CUMULATION_SIZE + 2 * cfg->max_streams + 2;
+    e->max_flushes = cfg->max_blocks_per_batch / SDR_CUMULATION_SIZE + cfg->max_streams + 1;
+    auto fail = [&](int code) {
+        g_create_error = e->err;
+        sdr_engine_destroy(e);
+        return code;
+    };
+#define CKC(call)                                                                      \
+    do {                                                                               \
+        cudaError_t _st = (call);                                                      \
+        if (_st != cudaSuccess) {                                                      \
+            e->err = std::string(#call) + ": " + cudaGetErrorString(_st);              \
+            return fail(SDR_ECUDA);                                                    \
+        }                                                                              \
+    } while (0)
+    CKC(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CKC(cudaGetDeviceProperties(&prop, cfg->device));
+    e->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        e->err = "libsdrgpu requires an sm_100a device (B200); found compute capability " + std::to_string(prop.major) + "." +
+                 std::to_string(prop.minor);
+        return fail(SDR_ECUDA);
+    }
+    if (cfg->cuda_stream) {
+        e->own_streams = false;
+        e->s_compute = e->s_h2d = e->s_d2h = (cudaStream_t)cfg->cuda_stream;
+    } else {
+        CKC(cudaStreamCreateWithFlags(&e->s_compute, cudaStreamNonBlocking));
+        CKC(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
+        CKC(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
+    }
+    std::vector<float2> tw1, tw2;
+    build_twiddles(e->N, tw1, tw2);
+    CKC(cudaMalloc((void **)&e->d_tw1, tw1.size() * sizeof(float2)));
+    CKC(cudaMalloc((void **)&e->d_tw2, tw2.size() * sizeof(float2)));
+    CKC(cudaMemcpy(e->d_tw1, tw1.data(), tw1.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    CKC(cudaMemcpy(e->d_tw2, tw2.data(), tw2.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    if (cfg->window) {
+        CKC(cudaMalloc((void **)&e->d_window, (size_t)e->N * sizeof(float)));
+        CKC(cudaMemcpy(e->d_window, cfg->window, (size_t)e->N * sizeof(float), cudaMemcpyHostToDevice));
+        e->cfg.window = nullptr;  // never retain the caller's pointer (cgo rule)
+    }
+    CKC(cudaMalloc((void **)&e->d_cum_state, (size_t)cfg->max_streams * e->N * sizeof(float)));
+    CKC(cudaMemset(e->d_cum_state, 0, (size_t)cfg->max_streams * e->N * sizeof(float)));
+    CKC(cudaMalloc((void **)&e->d_rolling, (size_t)cfg->max_streams * sizeof(RollingState)));
+    CKC(cudaMemset(e->d_rolling, 0, (size_t)cfg->max_streams * sizeof(RollingState)));
+    e->streams.resize(cfg->max_streams);
+    e->k1_grid_cap = k1_grid_cap_for(e->N, e->d_window != nullptr, e->sm_count);
+    CKC(cudaGetLastError());
+    e->slots.resize(cfg->n_slots);
+    for (auto &s : e->slots) {
+        int rc = alloc_slot(e, s);
+        if (rc != SDR_OK) return fail(rc);
+    }
+    CKC(cudaDeviceSynchronize());
+#undef CKC
+    *out = e;
+    return SDR_OK;
+}
+
+void sdr_engine_destroy(sdr_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    cudaDeviceSynchronize();
+    for (auto &s : e->slots) free_slot(s);
+    cudaFree(e->d_tw1);
+    cudaFree(e->d_tw2);
+    cudaFree(e->d_window);
+    cudaFree(e->d_cum_state);
+    cudaFree(e->d_rolling);
+    cudaFree(e->d_scratch);
+    if (e->own_streams) {
+        if (e->s_compute) cudaStreamDestroy(e->s_compute);
+        if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
+        if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
+    }
+    delete e;
+}
+
+int sdr_alloc_pinned(sdr_engine *e, size_t bytes, void **out) {
+    if (!e || !out) return SDR_EINVAL;
+    CK(e, cudaSetDevice(e->cfg.device));
+    CK(e, cudaMallocHost(out, bytes));
+    return SDR_OK;
+}
+
+int sdr_free_pinned(sdr_engine *e, void *p) {
+    if (!e) return SDR_EINVAL;
+    CK(e, cudaFreeHost(p));
+    return SDR_OK;
+}
+
+int sdr_stream_open(sdr_engine *e, int sample_rate, int *out_stream) {
+    if (!e || !out_stream || sample_rate <= 0) return SDR_EINVAL;
+    for (size_t i = 0; i < e->streams.size(); i++) {
+        if (!e->streams[i].open) {
+            e->streams[i].open = true;
+            e->streams[i].sample_rate = sample_rate;
+            *out_stream = (int)i;
+            return sdr_stream_reset(e, (int)i);
+        }
+    }
+    e->err = "no free stream slot (max_streams reached)";
+    return SDR_EBUSY;
+}
+
+int sdr_stream_close(sdr_engine *e, int stream) {
+    if (!e || stream < 0 || stream >= (int)e->streams.size() || !e->streams[stream].open) return SDR_EINVAL;
+    e->streams[stream].open = false;
+    return SDR_OK;
+}
+
+int sdr_stream_reset(sdr_engine *e, int stream) {
+    if (!e || stream < 0 || stream >= (int)e->streams.size() || !e->streams[stream].open) return SDR_EINVAL;
+    CK(e, cudaSetDevice(e->cfg.device));
+    e->streams[stream].cum_count = 0;
+    CK(e, cudaMemsetAsync(e->d_rolling + stream, 0, sizeof(RollingState), e->s_compute));
+    CK(e, cudaMemsetAsync(e->d_cum_state + (size_t)stream * e->N, 0, (size_t)e->N * sizeof(float), e->s_compute));
+    return SDR_OK;
+}
+
+int sdr_stream_cumulation_count(sdr_engine *e, int stream, int *out) {
+    if (!e || !out || stream < 0 || stream >= (int)e->streams.size() || !e->streams[stream].open) return SDR_EINVAL;
+    *out = e->streams[stream].cum_count;
+    return SDR_OK;
+}
+
+int64_t sdr_engine_launch_count(const sdr_engine *e) { return e ? e->launches : 0; }
+
+int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr_ticket *out) {
+    if (!e || !works || !out || n_works < 1) return SDR_EINVAL;
+    if (n_works > e->cfg.max_streams) {
+        e->err = "more works than max_streams";
+        return SDR_EINVAL;
+    }
+    CK(e, cudaSetDevice(e->cfg.device));
+    const int N = e->N;
+    // ---- validate (programmer errors: the Go reference panics or logs-and-drops) ----
+    long long total_blocks = 0;
+    bool any_host = false;
+    {
+        std::vector<char> seen(e->streams.size(), 0);
+        for (int w = 0; w < n_works; w++) {
+            const sdr_work &wk = works[w];
+            if (wk.stream < 0 || wk.stream >= (int)e->streams.size() || !e->streams[wk.stream].open) {
+                e->err = "work " + std::to_string(w) + ": stream not open";
+                return SDR_EINVAL;
+            }
+            if (seen[wk.stream]) {
+                e->err = "work " + std::to_string(w) + ": a stream may appear only once per submit";
+                return SDR_EINVAL;
+            }
+            seen[wk.stream] = 1;
+            if (wk.n_blocks < 1 || !wk.iq) {
+                e->err = "work " + std::to_string(w) + ": empty";
+                return SDR_EINVAL;
+            }
+            if (wk.n_listeners < 0 || wk.n_listeners > e->cfg.max_listeners || (wk.n_listeners > 0 && !wk.listener_bins)) {
+                e->err = "work " + std::to_string(w) + ": bad listener count";
+                return SDR_EINVAL;
+            }
+            for (int l = 0; l < wk.n_listeners; l++)
+                if (wk.listener_bins[l] < 0 || wk.listener_bins[l] >= N) {
+                    e->err = "work " + std::to_string(w) + ": listener bin out of range";
+                    return SDR_EINVAL;
+                }
+            if (wk.edge_width < 0 || nf_window_size(N, wk.edge_width) < 1) {
+                e->err = "work " + std::to_string(w) + ": edge_width leaves no noise window ((N-2e)/10 < 1)";
+                return SDR_EINVAL;
+            }
+            if (wk.mem == SDR_MEM_DEVICE && ((uintptr_t)wk.iq & 15)) {
+                e->err = "work " + std::to_string(w) + ": device iq must be 16-byte aligned";
+                return SDR_EINVAL;
+            }
+            if (wk.mem != SDR_MEM_DEVICE) any_host = true;
+            total_blocks += wk.n_blocks;
+        }
+    }
+    if (total_blocks > e->cfg.max_blocks_per_batch) {
+        e->err = "batch exceeds max_blocks_per_batch";
+        return SDR_EINVAL;
+    }
+    Slot *sp = nullptr;
+    for (auto &s : e->slots)
+        if (!s.busy) {
+            sp = &s;
+            break;
+        }
+    if (!sp) {
+        e->err = "all in-flight slots busy";
+        return SDR_EBUSY;
+    }
+    Slot &s = *sp;
+    const bool dbg = (flags & SDR_WANT_SPECTRUM) != 0;
+    if (dbg && !s.d_spectrum) {
+        const size_t bytes = (size_t)e->cfg.max_blocks_per_batch * N * sizeof(float);
+        CK(e, cudaMalloc((void **)&s.d_spectrum, bytes));
+        CK(e, cudaMalloc((void **)&s.d_psd, bytes));
+        CK(e, cudaMallocHost((void **)&s.h_spectrum, bytes));
+        CK(e, cudaMallocHost((void **)&s.h_psd, bytes));
+    }
+    if (any_host && !s.d_iq) CK(e, cudaMalloc((void **)&s.d_iq, (size_t)e->cfg.max_blocks_per_batch * 2 * N * sizeof(float)));
+
+    // ---- build descriptors ----
+    const DescLayout dl = desc_layout(e);
+    Segment *segs = reinterpret_cast<Segment *>(s.h_desc + dl.segs);
+    WorkParams *wps = reinterpret_cast<WorkParams *>(s.h_desc + dl.works);
+    PostWork *pws = reinterpret_cast<PostWork *>(s.h_desc + dl.post);
+    int *lbins = reinterpret_cast<int *>(s.h_desc + dl.lbins);
+    s.work_block_offset.assign(n_works + 1, 0);
+    s.work_flush_offset.assign(n_works + 1, 0);
+    int n_segs = 0, n_flushes = 0, block_off = 0, lb_off = 0;
+    size_t iq_off = 0;  // floats into d_iq
+    for (int w = 0; w < n_works; w++) {
+        const sdr_work &wk = works[w];
+        StreamInfo &si = e->streams[wk.stream];
+        const float *dev_iq = wk.iq;
+        if (wk.mem != SDR_MEM_DEVICE) {
+            dev_iq = s.d_iq + iq_off;
+            CK(e, cudaMemcpyAsync(s.d_iq + iq_off, wk.iq, (size_t)wk.n_blocks * 2 * N * sizeof(float), cudaMemcpyHostToDevice, e->s_h2d));
+            iq_off += (size_t)wk.n_blocks * 2 * N;
+        }
+        wps[w].edge_width = wk.edge_width;
+        wps[w].n_listeners = wk.n_listeners;
+        wps[w].listener_off = lb_off;
+        wps[w].pad = 0;
+        for (int l = 0; l < wk.n_listeners; l++) lbins[lb_off + l] = wk.listener_bins[l];
+        lb_off += wk.n_listeners;
+        PostWork &pw = pws[w];
+        pw.stream = wk.stream;
+        pw.block_out = block_off;
+        pw.n_blocks = wk.n_blocks;
+        pw.flush_out = n_flushes;
+        pw.n_flushes = 0;
+        pw.first_flush_block = SDR_CUMULATION_SIZE - si.cum_count - 1;
+        pw.peak_threshold = wk.peak_threshold;
+        pw.n_listeners = wk.n_listeners;
+        pw.do_peaks = (flags & SDR_NO_PEAKS) ? 0 : 1;
+        pw.pad = 0;
+        s.work_block_offset[w] = block_off;
+        s.work_flush_offset[w] = n_flushes;
+        int c = si.cum_count, pos = 0, rem = wk.n_blocks;
+        while (rem > 0) {
+            const int take = rem < SDR_CUMULATION_SIZE - c ? rem : SDR_CUMULATION_SIZE - c;
+            if (n_segs >= e->max_segs || n_flushes >= e->max_flushes) {
+                e->err = "internal: descriptor capacity exceeded";
+                return SDR_ESTATE;
+            }
+            Segment &sg = segs[n_segs++];
+            sg.iq = dev_iq + (size_t)pos * 2 * N;
+            sg.n_blocks = take;
+            sg.stream = wk.stream;
+            sg.work = w;
+            sg.block_out = block_off + pos;
+            sg.load_state = c > 0 ? 1 : 0;
+            sg.flush_idx = (c + take == SDR_CUMULATION_SIZE) ? n_flushes++ : -1;
+            sg.pad = 0;
+            if (sg.flush_idx >= 0) pw.n_flushes++;
+            c = (c + take) % SDR_CUMULATION_SIZE;
+            pos += take;
+            rem -= take;
+        }
+        si.cum_count = c;
+        block_off += wk.n_blocks;
+    }
+    s.work_block_offset[n_works] = block_off;
+    s.work_flush_offset[n_works] = n_flushes;
+    s.n_works = n_works;
+    s.n_blocks = block_off;
+    s.n_flushes = n_flushes;
+    s.flags = flags;
+    s.launches = 0;
+
+    // ---- H2D: descriptors (+ IQ queued above) ----
+    CK(e, cudaMemcpyAsync(s.d_desc, s.h_desc, dl.total, cudaMemcpyHostToDevice, e->s_h2d));
+    CK(e, cudaEventRecord(s.ev_h2d, e->s_h2d));
+    CK(e, cudaStreamWaitEvent(e->s_compute, s.ev_h2d, 0));
+
+    // ---- kernels ----
+    K1Args a1;
+    a1.segs = reinterpret_cast<const Segment *>(s.d_desc + dl.segs);
+    a1.n_segs = n_segs;
+    a1.works = reinterpret_cast<const WorkParams *>(s.d_desc + dl.works);
+    a1.listener_bins = reinterpret_cast<const int *>(s.d_desc + dl.lbins);
+    a1.tw1 = e->d_tw1;
+    a1.tw2 = e->d_tw2;
+    a1.window = e->d_window;
+    a1.cum_state = e->d_cum_state;
+    a1.psd_floor = s.d_psd_floor;
+    a1.variance = s.d_variance;
+    a1.taps = s.d_taps;
+    a1.tap_stride = e->tap_stride;
+    a1.flush_cum = s.d_flush_cum;
+    a1.dbg_spectrum = s.d_spectrum;
+    a1.dbg_psd = s.d_psd;
+    CK(e, cudaEventRecord(s.ev_k0, e->s_compute));
+    CK(e, launch_k1(e, a1, dbg, e->s_compute));
+    K2Args a2;
+    a2.works = reinterpret_cast<const PostWork *>(s.d_desc + dl.post);
+    a2.rolling = e->d_rolling;
+    a2.psd_floor = s.d_psd_floor;
+    a2.variance = s.d_variance;
+    a2.thresholds = s.d_thresholds;
+    a2.taps = s.d_taps;
+    a2.keys = s.d_keys;
+    a2.tap_stride = e->tap_stride;
+    a2.flush_cum = s.d_flush_cum;
+    a2.flush_block = s.d_flush_block;
+    a2.flush_n_peaks = s.d_flush_n_peaks;
+    a2.flush_peaks = s.d_flush_peaks;
+    a2.max_peaks = e->cfg.max_peaks_per_flush;
+    a2.n = N;
+    k2_post_kernel<<<n_works, K2_THREADS, 0, e->s_compute>>>(a2);
+    CK(e, cudaGetLastError());
+    CK(e, cudaEventRecord(s.ev_k1, e->s_compute));
+    s.launches = 2;
+    e->launches += 2;
+
+    // ---- D2H ----
+    if (!(flags & SDR_NO_D2H)) {
+        CK(e, cudaStreamWaitEvent(e->s_d2h, s.ev_k1, 0));
+        const size_t nb = (size_t)block_off, TS = (size_t)e->tap_stride;
+        CK(e, cudaMemcpyAsync(s.h_psd_floor, s.d_psd_floor, nb * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
+        CK(e, cudaMemcpyAsync(s.h_variance, s.d_variance, nb * sizeof(double), cudaMemcpyDeviceToHost, e->s_d2h));
+        CK(e, cudaMemcpyAsync(s.h_thresholds, s.d_thresholds, nb * 4 * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
+        CK(e, cudaMemcpyAsync(s.h_taps, s.d_taps, nb * TS * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
+        CK(e, cudaMemcpyAsync(s.h_keys, s.d_keys, nb * TS, cudaMemcpyDeviceToHost, e->s_d2h));
+        if (n_flushes > 0) {
+            const size_t nf = (size_t)n_flushes;
+            CK(e, cudaMemcpyAsync(s.h_flush_block, s.d_flush_block, nf * sizeof(int), cudaMemcpyDeviceToHost, e->s_d2h));
+            CK(e, cudaMemcpyAsync(s.h_flush_n_peaks, s.d_flush_n_peaks, nf * sizeof(int), cudaMemcpyDeviceToHost, e->s_d2h));
+            CK(e, cudaMemcpyAsync(s.h_flush_peaks, s.d_flush_peaks, nf * e->cfg.max_peaks_per_flush * sizeof(sdr_peak),
+                                  cudaMemcpyDeviceToHost, e->s_d2h));
+            if (flags & SDR_WANT_FLUSH_CUM)
+                CK(e, cudaMemcpyAsync(s.h_flush_cum, s.d_flush_cum, nf * N * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
+        }
+        if (dbg) {
+            CK(e, cudaMemcpyAsync(s.h_spectrum, s.d_spectrum, nb * N * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
+            CK(e, cudaMemcpyAsync(s.h_psd, s.d_psd, nb * N * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
+        }
+        CK(e, cudaEventRecord(s.ev_done, e->s_d2h));
+    } else {
+        CK(e, cudaEventRecord(s.ev_done, e->s_compute));
+    }
+    s.busy = true;
+    s.collected = false;
+    s.ticket = e->next_ticket++;
+    *out = s.ticket;
+    return SDR_OK;
+}
+
+int sdr_collect(sdr_engine *e, sdr_ticket t, int blocking, sdr_result *out) {
+    if (!e || !out) return SDR_EINVAL;
+    Slot *sp = find_slot(e, t);
+    if (!sp) {
+        e->err = "unknown ticket";
+        return SDR_EINVAL;
+    }
+    Slot &s = *sp;
+    if (blocking) {
+        CK(e, cudaEventSynchronize(s.ev_done));
+    } else {
+        cudaError_t st = cudaEventQuery(s.ev_done);
+        if (st == cudaErrorNotReady) return SDR_ENOTREADY;
+        CK(e, st);
+    }
+    s.collected = true;
+    memset(out, 0, sizeof(*out));
+    out->n_works = s.n_works;
+    out->n_blocks = s.n_blocks;
+    out->n_flushes = s.n_flushes;
+    out->tap_stride = e->tap_stride;
+    out->block_size = e->N;
+    out->max_peaks_per_flush = e->cfg.max_peaks_per_flush;
+    out->work_block_offset = s.work_block_offset.data();
+    out->work_flush_offset = s.work_flush_offset.data();
+    if (!(s.flags & SDR_NO_D2H)) {
+        out->psd_noise_floor = s.h_psd_floor;
+        out->noise_variance = s.h_variance;
+        out->thresholds = s.h_thresholds;
+        out->taps = s.h_taps;
+        out->keys = s.h_keys;
+        out->flush_block = s.h_flush_block;
+        out->flush_n_peaks = s.h_flush_n_peaks;
+        out->flush_peaks = s.h_flush_peaks;
+        out->flush_cum = (s.flags & SDR_WANT_FLUSH_CUM) ? s.h_flush_cum : nullptr;
+        out->spectrum = (s.flags & SDR_WANT_SPECTRUM) ? s.h_spectrum : nullptr;
+        out->psd = (s.flags & SDR_WANT_SPECTRUM) ? s.h_psd : nullptr;
+    }
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1) == cudaSuccess) out->gpu_ms = ms;
+    out->gpu_launches = s.launches;
+    return SDR_OK;
+}
+
+int sdr_release(sdr_engine *e, sdr_ticket t) {
+    if (!e) return SDR_EINVAL;
+    Slot *sp = find_slot(e, t);
+    if (!sp) {
+        e->err = "unknown ticket";
+        return SDR_EINVAL;
+    }
+    if (!sp->collected) CK(e, cudaEventSynchronize(sp->ev_done));
+    sp->busy = false;
+    return SDR_OK;
+}
+
+int sdr_ticket_device_ptrs(sdr_engine *e, sdr_ticket t, void **psd_noise_floor, void **noise_variance, void **thresholds,
+                           void **taps, void **keys) {
+    if (!e) return SDR_EINVAL;
+    Slot *sp = find_slot(e, t);
+    if (!sp) {
+        e->err = "unknown ticket";
+        return SDR_EINVAL;
+    }
+    if (psd_noise_floor) *psd_noise_floor = sp->d_psd_floor;
+    if (noise_variance) *noise_variance = sp->d_variance;
+    if (thresholds) *thresholds = sp->d_thresholds;
+    if (taps) *taps = sp->d_taps;
+    if (keys) *keys = sp->d_keys;
+    return SDR_OK;
+}
+
+// ---- dsp-signature-compatible single calls ---------------------------------------------------
+
+int sdr_dsp_iq_to_spectrum_and_psd(sdr_engine *e, const float *iq, int n_blocks, float *spectrum, float *psd) {
+    if (!e || !iq || !spectrum || !psd || n_blocks < 1) return SDR_EINVAL;
+    CK(e, cudaSetDevice(e->cfg.device));
+    const int N = e->N;
+    // every block is its own segment so the calls stay independent of any stream state
+    const size_t iq_bytes = (size_t)n_blocks * 2 * N * sizeof(float);
+    const size_t out_bytes = (size_t)n_blocks * N * sizeof(float);
+    const size_t seg_bytes = align_up(sizeof(Segment) * (size_t)n_blocks, 256);
+    const size_t misc = 4096;
+    size_t need = align_up(iq_bytes, 256) + 2 * align_up(out_bytes, 256) + seg_bytes + misc +
+                  align_up((size_t)n_blocks * 16, 256) * 2 + align_up((size_t)N * sizeof(float), 256);
+    int rc = ensure_scratch(e, need);
+    if (rc != SDR_OK) return rc;
+    unsigned char *p = reinterpret_cast<unsigned char *>(e->d_scratch);
+    float *d_iq = reinterpret_cast<float *>(p);
+    p += align_up(iq_bytes, 256);
+    float *d_spec = reinterpret_cast<float *>(p);
+    p += align_up(out_bytes, 256);
+    float *d_psd = reinterpret_cast<float *>(p);
+    p += align_up(out_bytes, 256);
+    Segment *d_segs = reinterpret_cast<Segment *>(p);
+    p += seg_bytes;
+    WorkParams *d_work = reinterpret_cast<WorkParams *>(p);
+    p += 256;
+    float *d_floor = reinterpret_cast<float *>(p);
+    p += align_up((size_t)n_blocks * 16, 256);
+    double *d_var = reinterpret_cast<double *>(p);
+    p += align_up((size_t)n_blocks * 16, 256);
+    float *d_taps = reinterpret_cast<float *>(p);
+    p += 256;
+    float *d_cum = reinterpret_cast<float *>(p);
+    std::vector<Segment> segs(n_blocks);
+    for (int b = 0; b < n_blocks; b++) {
+        Segment &sg = segs[b];
+        sg.iq = d_iq + (size_t)b * 2 * N;
+        sg.n_blocks = 1;
+        sg.stream = 0;
+        sg.work = 0;
+        sg.block_out = b;
+        sg.flush_idx = 0;  // cumulation goes to the throw-away row
+        sg.load_state = 0;
+        sg.pad = 0;
+    }
+    WorkParams wp;
+    wp.edge_width = 0;
+    wp.n_listeners = 0;
+    wp.listener_off = 0;
+    wp.pad = 0;
+    CK(e, cudaMemcpyAsync(d_iq, iq, iq_bytes, cudaMemcpyHostToDevice, e->s_compute));
+    CK(e, cudaMemcpyAsync(d_segs, segs.data(), sizeof(Segment) * (size_t)n_blocks, cudaMemcpyHostToDevice, e->s_compute));
+    CK(e, cudaMemcpyAsync(d_work, &wp, sizeof(wp), cudaMemcpyHostToDevice, e->s_compute));
+    K1Args a;
+    a.segs = d_segs;
+    a.n_segs = n_blocks;
+    a.works = d_work;
+    a.listener_bins = nullptr;
+    a.tw1 = e->d_tw1;
+    a.tw2 = e->d_tw2;
+    a.window = e->d_window;
+    a.cum_state = d_cum;
+    a.psd_floor = d_floor;
+    a.variance = d_var;
+    a.taps = d_taps;
+    a.tap_stride = 0;
+    a.flush_cum = d_cum;
+    a.dbg_spectrum = d_spec;
+    a.dbg_psd = d_psd;
+    CK(e, launch_k1(e, a, true, e->s_compute));
+    e->launches += 1;
+    CK(e, cudaMemcpyAsync(spectrum, d_spec, out_bytes, cudaMemcpyDeviceToHost, e->s_compute));
+    CK(e, cudaMemcpyAsync(psd, d_psd, out_bytes, cudaMemcpyDeviceToHost, e->s_compute));
+    CK(e, cudaStreamSynchronize(e->s_compute));
+    return SDR_OK;
+}
+
+int sdr_dsp_find_noise_floor(sdr_engine *e, const float *psd, int edge_width, float *min_value, double *variance) {
+    if (!e || !psd || !min_value || !variance) return SDR_EINVAL;
+    const int N = e->N;
+    if (edge_width < 0 || nf_window_size(N, edge_width) < 1) {
+        e->err = "edge_width leaves no noise window ((N-2e)/10 < 1)";
+        return SDR_EINVAL;
+    }
+    CK(e, cudaSetDevice(e->cfg.device));
+    int rc = ensure_scratch(e, (size_t)N * sizeof(float) + 256);
+    if (rc != SDR_OK) return rc;
+    unsigned char *p = reinterpret_cast<unsigned char *>(e->d_scratch);
+    double *d_var = reinterpret_cast<double *>(p);
+    float *d_min = reinterpret_cast<float *>(p + 8);
+    float *d_psd = reinterpret_cast<float *>(p + 256);
+    CK(e, cudaMemcpyAsync(d_psd, psd, (size_t)N * sizeof(float), cudaMemcpyHostToDevice, e->s_compute));
+    noise_floor_kernel<<<1, 128, 0, e->s_compute>>>(d_psd, N, edge_width, d_min, d_var);
+    CK(e, cudaGetLastError());
+    e->launches += 1;
+    CK(e, cudaMemcpyAsync(min_value, d_min, sizeof(float), cudaMemcpyDeviceToHost, e->s_compute));
+    CK(e, cudaMemcpyAsync(variance, d_var, sizeof(double), cudaMemcpyDeviceToHost, e->s_compute));
+    CK(e, cudaStreamSynchronize(e->s_compute));
+    return SDR_OK;
+}
+
+int sdr_dsp_find_peaks(sdr_engine *e, const float *cumulation, int cumulation_size, float threshold, sdr_peak *peaks,
+                       int max_peaks, int *n_peaks) {
+    if (!e || !cumulation || !peaks || !n_peaks || max_peaks < 1 || cumulation_size < 1) return SDR_EINVAL;
+    const int N = e->N;
+    CK(e, cudaSetDevice(e->cfg.device));
+    int rc = ensure_scratch(e, (size_t)N * sizeof(float) + 256 + (size_t)max_peaks * sizeof(sdr_peak));
+    if (rc != SDR_OK) return rc;
+    unsigned char *p = reinterpret_cast<unsigned char *>(e->d_scratch);
+    int *d_n = reinterpret_cast<int *>(p);
+    float *d_cum = reinterpret_cast<float *>(p + 256);
+    sdr_peak *d_peaks = reinterpret_cast<sdr_peak *>(p + 256 + (size_t)N * sizeof(float));
+    CK(e, cudaMemcpyAsync(d_cum, cumulation, (size_t)N * sizeof(float), cudaMemcpyHostToDevice, e->s_compute));
+    find_peaks_kernel<<<1, K2_THREADS, 0, e->s_compute>>>(d_cum, N, (float)cumulation_size, threshold, d_peaks, max_peaks, d_n);
+    CK(e, cudaGetLastError());
+    e->launches += 1;
+    int n = 0;
+    CK(e, cudaMemcpyAsync(&n, d_n, sizeof(int), cudaMemcpyDeviceToHost, e->s_compute));
+    CK(e, cudaStreamSynchronize(e->s_compute));
+    *n_peaks = n;
+    const int ncopy = n < max_peaks ? n : max_peaks;
+    if (ncopy > 0) CK(e, cudaMemcpy(peaks, d_peaks, (size_t)ncopy * sizeof(sdr_peak), cudaMemcpyDeviceToHost));
+    return SDR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,387 @@
+// k1_spectral.cuh -- K1: fused spectral front end, one pass over the IQ in HBM.
+//
+// Replaces, for every block of N complex samples (rx/receiver.go:379-407):
+//   dsp.FFT.IQToSpectrumAndPSD   dsp/fft.go:23-37   (FFT, fftshift, |X|^2, dB + 120)
+//   dsp.FindNoiseFloor           dsp/fft.go:215-252 (10 window means, min, variance)
+//   listener taps                rx/receiver.go:393 (spectrum[l.SignalBin()])
+//   cumulation                   rx/receiver.go:404-407 (float32, block order), flushed every 100
+//
+// Data movement: each IQ block (8N bytes) is read from HBM exactly once, by a TMA bulk copy
+// (cp.async.bulk -> UBLKCP) into a shared-memory ring guarded by mbarriers; spectrum and PSD never
+// go to HBM (unless DEBUG_STORE).  Per block only 4L+12 bytes are written; 4N bytes per flush.
+//
+// Work decomposition: a *segment* is a run of <=100 consecutive blocks of one stream inside one
+// cumulation window.  A thread *group* of T = N/16 threads owns a segment: each thread keeps 16
+// points in registers, does radix-16 / radix-16 / radix-(N/256) passes with two shared-memory
+// exchanges, and keeps its 16 cumulation bins in registers for the whole segment (sequential
+// float32 adds in block order, exactly like the reference).  Groups are independent; a CTA holds
+// G groups so that it always has 128..256 threads.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fft_radix.cuh"
+
+namespace sdr {
+
+struct Segment {
+    const float *iq;      // first block of the segment (device, 16-byte aligned)
+    int n_blocks;         // 1..100
+    int stream;           // stream slot (cumulation state row)
+    int work;             // index into WorkParams
+    int block_out;        // index of the first block in the per-block output arrays
+    int flush_idx;        // >=0: this segment closes a window -> write cumulation there; -1: store to state
+    int load_state;       // 1: start from the stream's saved partial cumulation
+    int pad;
+};
+
+struct WorkParams {
+    int edge_width;
+    int n_listeners;
+    int listener_off;  // offset into the listener bin array
+    int pad;
+};
+
+struct K1Args {
+    const Segment *segs;
+    int n_segs;
+    const WorkParams *works;
+    const int *listener_bins;
+    const float2 *tw1;      // [15][M]  W_N^(j*k1)
+    const float2 *tw2;      // [15][R3] W_M^(n3*k2)
+    const float *window;    // [N] or nullptr
+    float *cum_state;       // [max_streams][N]
+    float *psd_floor;       // [blocks]
+    double *variance;       // [blocks]
+    float *taps;            // [blocks][tap_stride]
+    int tap_stride;
+    float *flush_cum;       // [flushes][N]
+    float *dbg_spectrum;    // [blocks][N] (DEBUG_STORE)
+    float *dbg_psd;         // [blocks][N]
+};
+
+// ---- PTX helpers: mbarrier + TMA bulk copy -------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 1-D bulk async copy global -> shared, completion on mbarrier (TMA engine; SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+template <int N>
+struct K1Geom {
+    static constexpr int M = N / 16;       // points per pass-1 column set == threads per group
+    static constexpr int R3 = N / 256;     // last radix
+    static constexpr int T = N / 16;       // threads per group
+    static constexpr int PAIRS = 16 / R3;  // (k1,k2) pairs per thread in pass 3
+    static constexpr int S1 = M + R3;      // E1 row stride (complex), bank-conflict free
+    static constexpr int S2 = 256 + 16 / R3;  // E2 row stride (complex)
+    static constexpr int E1_BYTES = 16 * S1 * 8;
+    static constexpr int E2_BYTES = R3 * S2 * 8;
+    static constexpr int STAGE_BYTES = ((E2_BYTES > 8 * N ? E2_BYTES : 8 * N) + 127) / 128 * 128;
+    static constexpr int NSTAGE = 2;
+    static constexpr int LMAX = 256;       // listener bins cached in smem per group
+    static constexpr int TW2_BYTES = 15 * R3 * 8;
+    static constexpr int MISC_BYTES = 16 * 8 /*wsum*/ + LMAX * 4 + NSTAGE * 8 /*mbar*/ + 64;
+    static constexpr int GROUP_BYTES = ((NSTAGE * STAGE_BYTES + E1_BYTES + TW2_BYTES + MISC_BYTES) + 127) / 128 * 128;
+    static constexpr int G = (T >= 128) ? 1 : 128 / T;  // groups per CTA
+    static constexpr int CTA_THREADS = G * T;
+    static constexpr int SMEM_BYTES = G * GROUP_BYTES;
+    static_assert(R3 == 2 || R3 == 4 || R3 == 8 || R3 == 16, "fused path covers N = 512..4096");
+    static_assert(E1_BYTES >= 4 * N, "PSD aliases E1");
+};
+
+template <int T, int G>
+__device__ __forceinline__ void group_sync(int g) {
+    if (T == 32) {
+        __syncwarp();
+    } else if (G == 1) {
+        __syncthreads();
+    } else {
+        asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(T) : "memory");
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// dB projection of rx/receiver.go:376-378: float32(10*log10(20*psd/N^2)) + float32(120)
+template <int N>
+__device__ __forceinline__ float psd_to_db(float psd) {
+    // 10*log10(20*p/N^2) = A*log2(p) + B
+    constexpr float A = 3.01029995663981195f;  // 10*log10(2)
+    constexpr double LOG2N = (N == 512) ? 9.0 : (N == 1024) ? 10.0 : (N == 2048) ? 11.0 : (N == 4096) ? 12.0 : 0.0;
+    constexpr float B = (float)(13.0102999566398120 - 20.0 * LOG2N * 0.30102999566398120);  // 10*log10(20) - 20*log10(N)
+    float t = fmaf(A, __log2f(psd), B);
+    return __fadd_rn(t, 120.0f);
+}
+
+// ---- dsp.FindNoiseFloor (dsp/fft.go:215-252), parallel form --------------------------------
+// Window w covers bins [e + w*ws, e + (w+1)*ws); its mean is only evaluated when the loop reaches
+// the next bin, so the 10th window is skipped when 10*ws == N - 2e (n_win = 9).  float64 sums of
+// float32 values as in the reference (summation order differs: tree instead of sequential, a
+// relative 1e-16 effect).
+__host__ __device__ __forceinline__ int nf_window_size(int n, int e) { return (n - 2 * e) / 10; }
+__host__ __device__ __forceinline__ int nf_window_count(int n, int e) {
+    const int ws = nf_window_size(n, e);
+    return (10 * ws < n - 2 * e) ? 10 : 9;
+}
+
+// all T threads of a group (T % 32 == 0); result WSUM[0..n_win) valid after the next group barrier
+template <int T>
+__device__ __forceinline__ void nf_window_sums(const float *PSD, double *WSUM, int e, int ws, int n_win, int t) {
+    const int warp = t / 32, lane = t % 32;
+    constexpr int NW = T / 32;
+    for (int w = warp; w < n_win; w += NW) {
+        const int from = e + w * ws;
+        double acc = 0.0;
+        for (int i = lane; i < ws; i += 32) acc += (double)PSD[from + i];
+        acc = warp_sum(acc);
+        if (lane == 0) WSUM[w] = acc;
+    }
+}
+
+// one full warp; the sequential min selection runs identically on every lane (dsp/fft.go:217-236),
+// the variance over [from..to] INCLUSIVE (ws+1 terms, :244-248) is a warp reduction.
+__device__ __forceinline__ void nf_select_variance(const float *PSD, const double *WSUM, int e, int ws, int n_win,
+                                                   int lane, float *out_min, double *out_var) {
+    double min_value = (double)PSD[0];
+    bool first = true;
+    double result_mean = 0.0;
+    int result_from = 0, result_to = 0;
+    for (int w = 0; w < n_win; w++) {
+        const double mean = WSUM[w] / (double)ws;
+        if (mean < min_value || first) {
+            min_value = mean;
+            first = false;
+            result_mean = mean;
+            result_from = e + w * ws;
+            result_to = e + (w + 1) * ws;  // first bin of the next window
+        }
+    }
+    double acc = 0.0;
+    for (int i = result_from + lane; i <= result_to; i += 32) {
+        const double d = (double)PSD[i] - result_mean;
+        acc += d * d;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        *out_min = (float)min_value;
+        *out_var = acc / (double)ws;
+    }
+}
+
+template <int N, bool DEBUG_STORE, bool HAS_WINDOW>
+__global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS) k1_spectral_kernel(const K1Args a) {
+    using Gm = K1Geom<N>;
+    constexpr int M = Gm::M, R3 = Gm::R3, T = Gm::T, PAIRS = Gm::PAIRS, S1 = Gm::S1, S2 = Gm::S2;
+    constexpr int NSTAGE = Gm::NSTAGE, G = Gm::G;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int g = threadIdx.x / T;  // group within CTA
+    const int t = threadIdx.x % T;  // thread within group
+    unsigned char *base = smem_raw + (size_t)g * Gm::GROUP_BYTES;
+    unsigned char *stage_base = base;
+    float2 *E1 = reinterpret_cast<float2 *>(base + NSTAGE * Gm::STAGE_BYTES);
+    float *PSD = reinterpret_cast<float *>(E1);  // aliases E1 (E1 is dead after pass 2 loads)
+    float2 *TW2 = reinterpret_cast<float2 *>(base + NSTAGE * Gm::STAGE_BYTES + Gm::E1_BYTES);
+    double *WSUM = reinterpret_cast<double *>(base + NSTAGE * Gm::STAGE_BYTES + Gm::E1_BYTES + Gm::TW2_BYTES);
+    int *LB = reinterpret_cast<int *>(WSUM + 16);
+    uint64_t *FULL = reinterpret_cast<uint64_t *>(LB + Gm::LMAX);
+
+    const int group_id = blockIdx.x * G + g;
+    const int group_stride = gridDim.x * G;
+
+    // ---- one-time setup ----
+    if (t == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; s++) mbar_init(&FULL[s], 1);
+        fence_mbar_init();
+    }
+    for (int i = t; i < 15 * R3; i += T) TW2[i] = a.tw2[i];
+    float2 tw1[15];
+#pragma unroll
+    for (int k = 0; k < 15; k++) tw1[k] = __ldg(&a.tw1[k * M + t]);
+    float win[16];
+    if (HAS_WINDOW) {
+#pragma unroll
+        for (int m = 0; m < 16; m++) win[m] = __ldg(&a.window[m * M + t]);
+    }
+    group_sync<T, G>(g);
+
+    // ---- producer iterator (thread 0 of the group runs NSTAGE items ahead) ----
+    int pseg = group_id, pblk = 0, pn = 0;
+    if (pseg < a.n_segs) pn = __ldg(&a.segs[pseg].n_blocks);
+    uint32_t issued = 0;
+    auto issue_next = [&]() {
+        if (pseg >= a.n_segs) return;
+        const float *src = a.segs[pseg].iq + (size_t)pblk * 2 * N;
+        int s = issued % NSTAGE;
+        mbar_expect_tx(&FULL[s], 8 * N);
+        tma_load_1d(stage_base + (size_t)s * Gm::STAGE_BYTES, src, 8 * N, &FULL[s]);
+        issued++;
+        pblk++;
+        if (pblk == pn) {
+            pseg += group_stride;
+            pblk = 0;
+            if (pseg < a.n_segs) pn = a.segs[pseg].n_blocks;
+        }
+    };
+    if (t == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; s++) issue_next();
+    }
+
+    // pass-2 role of this thread
+    const int k1_p2 = t / R3, n3_p2 = t % R3;
+    uint32_t item = 0;
+
+    for (int seg = group_id; seg < a.n_segs; seg += group_stride) {
+        const Segment sg = a.segs[seg];
+        const WorkParams wp = a.works[sg.work];
+        const int L = wp.n_listeners;
+        for (int i = t; i < L; i += T) LB[i] = a.listener_bins[wp.listener_off + i];
+
+        // noise-floor window geometry (dsp/fft.go:216,224)
+        const int e = wp.edge_width;
+        const int ws = nf_window_size(N, e);
+        const int n_win = nf_window_count(N, e);  // the 10th window only closes if a later bin exists
+
+        // cumulation registers: bin kk(i,k3) = (c + 256*k3 + N/2) % N with c = t + i*T
+        float cum[16];
+        if (sg.load_state) {
+            const float *cs = a.cum_state + (size_t)sg.stream * N;
+#pragma unroll
+            for (int i = 0; i < PAIRS; i++)
+#pragma unroll
+                for (int k3 = 0; k3 < R3; k3++) cum[i * R3 + k3] = cs[((t + i * T) + 256 * k3 + N / 2) % N];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) cum[i] = 0.f;
+        }
+        group_sync<T, G>(g);  // LB visible
+
+        for (int blk = 0; blk < sg.n_blocks; blk++, item++) {
+            const int s = item % NSTAGE;
+            const uint32_t parity = (item / NSTAGE) & 1u;
+            float2 *IN = reinterpret_cast<float2 *>(stage_base + (size_t)s * Gm::STAGE_BYTES);
+            float2 *E2 = IN;  // aliases the stage once pass 1 has consumed it
+            const int ob = sg.block_out + blk;
+
+            mbar_wait(&FULL[s], parity);
+
+            // ---------------- pass 1: radix-16 over n1, column j = t ----------------
+            float2 v[16];
+#pragma unroll
+            for (int m = 0; m < 16; m++) {
+                v[m] = IN[m * M + t];
+                if (HAS_WINDOW) {
+                    v[m].x *= win[m];
+                    v[m].y *= win[m];
+                }
+            }
+            dft16(v);
+#pragma unroll
+            for (int p = 0; p < 16; p++) {
+                const int k1 = OutIdx<16>::of(p);
+                float2 x = v[p];
+                if (k1 > 0) x = cmul(x, tw1[k1 - 1]);
+                E1[k1 * S1 + t] = x;
+            }
+            group_sync<T, G>(g);  // B1: E1 complete, IN consumed
+
+            // ---------------- pass 2: radix-16 over n2 for (k1, n3) ----------------
+#pragma unroll
+            for (int n2 = 0; n2 < 16; n2++) v[n2] = E1[k1_p2 * S1 + n2 * R3 + n3_p2];
+            dft16(v);
+#pragma unroll
+            for (int p = 0; p < 16; p++) {
+                const int k2 = OutIdx<16>::of(p);
+                float2 x = v[p];
+                if (k2 > 0) x = cmul(x, TW2[(k2 - 1) * R3 + n3_p2]);
+                E2[n3_p2 * S2 + k1_p2 + 16 * k2] = x;
+            }
+            group_sync<T, G>(g);  // B2: E2 complete, E1 dead
+
+            // ---------------- pass 3: radix-R3 over n3 for pairs c = t + i*T ----------------
+#pragma unroll
+            for (int i = 0; i < PAIRS; i++) {
+                const int c = t + i * T;
+                float2 u[R3];
+#pragma unroll
+                for (int n3 = 0; n3 < R3; n3++) u[n3] = E2[n3 * S2 + c];
+                dftR<R3>(u);
+#pragma unroll
+                for (int p = 0; p < R3; p++) {
+                    const int k3 = OutIdx<R3>::of(p);
+                    const int kk = (c + 256 * k3 + N / 2) % N;  // dsp/fft.go:54-57 fftshift
+                    const float psd = fmaf(u[p].x, u[p].x, u[p].y * u[p].y);  // dsp/fft.go:71-73
+                    PSD[kk] = psd;
+                    const float db = psd_to_db<N>(psd);
+                    cum[i * R3 + k3] += db;  // rx/receiver.go:404-406
+                    if (DEBUG_STORE) {
+                        a.dbg_spectrum[(size_t)ob * N + kk] = db;
+                        a.dbg_psd[(size_t)ob * N + kk] = psd;
+                    }
+                }
+            }
+            group_sync<T, G>(g);  // B3: PSD complete, stage (E2) dead
+
+            // stage s is free again: prefetch item + NSTAGE into it
+            if (t == 0) {
+                fence_proxy_async();
+                issue_next();
+            }
+
+            // ---------------- noise floor: window sums (dsp/fft.go:224-241) ----------------
+            nf_window_sums<T>(PSD, WSUM, e, ws, n_win, t);
+            // listener taps (rx/receiver.go:393): same dB function as the owner thread
+            for (int l = t; l < L; l += T) a.taps[(size_t)ob * a.tap_stride + l] = psd_to_db<N>(PSD[LB[l]]);
+            group_sync<T, G>(g);  // B3b: WSUM complete
+
+            if (t < 32) nf_select_variance(PSD, WSUM, e, ws, n_win, t, &a.psd_floor[ob], &a.variance[ob]);
+            group_sync<T, G>(g);  // B4: PSD (=E1) may be overwritten by the next block
+        }
+
+        // ---- end of segment: flush or save the cumulation ----
+        float *dst = (sg.flush_idx >= 0) ? a.flush_cum + (size_t)sg.flush_idx * N : a.cum_state + (size_t)sg.stream * N;
+#pragma unroll
+        for (int i = 0; i < PAIRS; i++)
+#pragma unroll
+            for (int k3 = 0; k3 < R3; k3++) dst[((t + i * T) + 256 * k3 + N / 2) % N] = cum[i * R3 + k3];
+        // after a flush the state row is never read: the next segment of the stream has load_state = 0
+    }
+}
+
+}  // namespace sdr

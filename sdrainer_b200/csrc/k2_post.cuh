@@ -1,0 +1,226 @@
+// k2_post.cuh -- K2: per-stream threshold scan, key states and peak lists.
+//
+// Replaces, per stream and batch (one CTA per work):
+//   rx/receiver.go:383-385   dB conversion of the noise-floor scalars + two float32 rolling means
+//                            over 60 blocks (dsp.RollingMean.Put, dsp/dsp.go:257-268), peak and
+//                            listener thresholds
+//   cw/spectral.go:49        state := value > threshold for every (block, listener)
+//   dsp.FindPeaks            dsp/fft.go:254-285 on every flushed cumulation vector, emitted in bin
+//                            order by a block-wide prefix sum (no atomics)
+//
+// The rolling mean is a *running* float32 sum (subtract oldest, add newest) whose value depends
+// on the whole history, so the recurrence is executed sequentially by one thread, in block order,
+// with the same float32 operations as the reference; everything around it is parallel.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/sdrgpu.h"
+
+namespace sdr {
+
+struct RollingState {  // two dsp.RollingMean[float32] of size 60 advancing in lock step
+    float floor_values[SDR_NOISE_WINDOW];
+    float dev_values[SDR_NOISE_WINDOW];
+    float floor_sum, dev_sum;
+    int next;
+    int pad;
+};
+
+struct PostWork {
+    int stream;
+    int block_out;          // first block of this work in the per-block arrays
+    int n_blocks;
+    int flush_out;          // first flush slot of this work
+    int n_flushes;
+    int first_flush_block;  // index (within the work) of the block that closes the first window
+    float peak_threshold;   // rx.Receiver.peakThreshold
+    int n_listeners;
+    int do_peaks;
+    int pad;
+};
+
+struct K2Args {
+    const PostWork *works;
+    RollingState *rolling;      // [max_streams]
+    const float *psd_floor;     // [blocks]
+    const double *variance;     // [blocks]
+    float *thresholds;          // [blocks][4]
+    const float *taps;          // [blocks][tap_stride]
+    uint8_t *keys;              // [blocks][tap_stride]
+    int tap_stride;
+    const float *flush_cum;     // [flushes][N]
+    int *flush_block;           // [flushes]
+    int *flush_n_peaks;         // [flushes]
+    sdr_peak *flush_peaks;      // [flushes][max_peaks]
+    int max_peaks;
+    int n;                      // block size N
+};
+
+// dsp.PSDValueIndB (dsp/fft.go:83-85) + dBmShift as a float32 add (rx/receiver.go:383-384)
+__device__ __forceinline__ float psd_value_in_db_shifted(float psd_value, double n2) {
+    const float db = (float)(10.0 * log10(20.0 * (double)psd_value / n2));
+    return __fadd_rn(db, (float)SDR_DBM_SHIFT);
+}
+
+constexpr int K2_THREADS = 256;
+constexpr int K2_CHUNK = 1024;  // blocks staged in shared memory per sequential pass
+
+// dsp.FindPeaks on one vector `cum` of n bins; all K2_THREADS threads of the CTA participate.
+__device__ void find_peaks_block(const float *__restrict__ cum, int n, float cumulation_size, float thr,
+                                 sdr_peak *__restrict__ out, int max_peaks, int *__restrict__ n_out, int *s_scan) {
+    const int tid = threadIdx.x;
+    const int per = (n + K2_THREADS - 1) / K2_THREADS;
+    const int lo = tid * per, hi = min(n, lo + per);
+    auto val = [&](int i) { return __fdiv_rn(cum[i], cumulation_size); };  // v / T(cumulationSize)
+    // a run starts at i when value > threshold and no run is open; a run stays open until the
+    // first value <= threshold (a NaN neither opens nor closes a run, as in the Go if/else chain)
+    auto starts_at = [&](int i) -> bool {
+        if (!(val(i) > thr)) return false;
+        int j = i - 1;
+        while (j >= 0) {
+            const float p = val(j);
+            if (p > thr) return false;   // previous bin is inside an open run
+            if (p <= thr) return true;   // previous bin closed any run
+            j--;                         // NaN: look further back
+        }
+        return true;
+    };
+    int count = 0;
+    for (int i = lo; i < hi; i++) count += starts_at(i) ? 1 : 0;
+    // block-wide exclusive scan of `count`
+    s_scan[tid] = count;
+    __syncthreads();
+    for (int off = 1; off < K2_THREADS; off <<= 1) {
+        int v = (tid >= off) ? s_scan[tid - off] : 0;
+        __syncthreads();
+        s_scan[tid] += v;
+        __syncthreads();
+    }
+    int slot = s_scan[tid] - count;
+    if (tid == K2_THREADS - 1) *n_out = s_scan[tid];
+    for (int i = lo; i < hi; i++) {
+        if (!starts_at(i)) continue;
+        int from = i, bin = i;
+        float best = val(i);
+        int j = i + 1;
+        while (j < n) {
+            const float v = val(j);
+            if (v <= thr) break;
+            if (best < v) {  // strict: the first maximum wins
+                best = v;
+                bin = j;
+            }
+            j++;
+        }
+        if (slot < max_peaks) {
+            sdr_peak p;
+            p.from = from;
+            p.to = j - 1;
+            p.signal_bin = bin;
+            p.signal_value = best;
+            const bool inner = bin > 0 && bin < n - 1;
+            p.y1 = inner ? cum[bin - 1] : 0.f;
+            p.y2 = cum[bin];
+            p.y3 = inner ? cum[bin + 1] : 0.f;
+            out[slot] = p;
+        }
+        slot++;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(K2_THREADS) k2_post_kernel(const K2Args a) {
+    __shared__ float s_floor[K2_CHUNK];
+    __shared__ float s_dev[K2_CHUNK];
+    __shared__ RollingState s_roll;
+    __shared__ int s_scan[K2_THREADS];
+    const PostWork w = a.works[blockIdx.x];
+    const int tid = threadIdx.x;
+    const double n2 = (double)a.n * (double)a.n;
+
+    if (tid == 0) s_roll = a.rolling[w.stream];
+    __syncthreads();
+
+    for (int c0 = 0; c0 < w.n_blocks; c0 += K2_CHUNK) {
+        const int cn = min(K2_CHUNK, w.n_blocks - c0);
+        // phase A (parallel): inputs of the two rolling means (rx/receiver.go:383-384)
+        for (int i = tid; i < cn; i += K2_THREADS) {
+            const int b = w.block_out + c0 + i;
+            const float psd_noise_floor = a.psd_floor[b];
+            const double var = a.variance[b];
+            // T(float64(PSDValueIndB(T(math.Sqrt(var)), N) + dBmShift) * 0.25)
+            const float dev_db = psd_value_in_db_shifted((float)sqrt(var), n2);
+            s_dev[i] = (float)((double)dev_db * 0.25);
+            s_floor[i] = psd_value_in_db_shifted(psd_noise_floor, n2);
+        }
+        __syncthreads();
+        // phase B (sequential, float32, block order): dsp.RollingMean.Put (dsp/dsp.go:257-268)
+        if (tid == 0) {
+            float fs = s_roll.floor_sum, ds = s_roll.dev_sum;
+            int next = s_roll.next;
+            for (int i = 0; i < cn; i++) {
+                fs = __fsub_rn(fs, s_roll.floor_values[next]);
+                s_roll.floor_values[next] = s_floor[i];
+                fs = __fadd_rn(fs, s_floor[i]);
+                ds = __fsub_rn(ds, s_roll.dev_values[next]);
+                s_roll.dev_values[next] = s_dev[i];
+                ds = __fadd_rn(ds, s_dev[i]);
+                next = (next + 1) % SDR_NOISE_WINDOW;
+                s_floor[i] = fs;
+                s_dev[i] = ds;
+            }
+            s_roll.floor_sum = fs;
+            s_roll.dev_sum = ds;
+            s_roll.next = next;
+        }
+        __syncthreads();
+        // phase C (parallel): means, thresholds (rx/receiver.go:384-385,394)
+        for (int i = tid; i < cn; i += K2_THREADS) {
+            const int b = w.block_out + c0 + i;
+            const float noise_floor = __fdiv_rn(s_floor[i], (float)SDR_NOISE_WINDOW);
+            const float noise_dev = __fdiv_rn(s_dev[i], (float)SDR_NOISE_WINDOW);
+            float4 th;
+            th.x = noise_floor;
+            th.y = noise_dev;
+            th.z = __fadd_rn(w.peak_threshold, noise_floor);
+            th.w = __fadd_rn(noise_floor, noise_dev);
+            reinterpret_cast<float4 *>(a.thresholds)[b] = th;
+        }
+        __syncthreads();
+        // key states (cw/spectral.go:49) for this chunk
+        const int L = w.n_listeners;
+        for (int idx = tid; idx < cn * L; idx += K2_THREADS) {
+            const int i = idx / L, l = idx % L;
+            const int b = w.block_out + c0 + i;
+            const float listen = a.thresholds[(size_t)b * 4 + 3];
+            a.keys[(size_t)b * a.tap_stride + l] = a.taps[(size_t)b * a.tap_stride + l] > listen ? 1 : 0;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) a.rolling[w.stream] = s_roll;
+
+    // flushes of this work (rx/receiver.go:409-425)
+    for (int f = 0; f < w.n_flushes; f++) {
+        const int fb = w.first_flush_block + f * SDR_CUMULATION_SIZE;  // block that closed the window
+        const int slot = w.flush_out + f;
+        if (tid == 0) a.flush_block[slot] = w.block_out + fb;
+        if (w.do_peaks) {
+            const float thr = a.thresholds[(size_t)(w.block_out + fb) * 4 + 2];
+            find_peaks_block(a.flush_cum + (size_t)slot * a.n, a.n, (float)SDR_CUMULATION_SIZE, thr,
+                             a.flush_peaks + (size_t)slot * a.max_peaks, a.max_peaks, &a.flush_n_peaks[slot], s_scan);
+        } else if (tid == 0) {
+            a.flush_n_peaks[slot] = 0;
+        }
+    }
+}
+
+// ---- stand-alone kernels behind the dsp-signature-compatible calls --------------------------
+__global__ void __launch_bounds__(K2_THREADS) find_peaks_kernel(const float *cum, int n, float cumulation_size, float thr,
+                                                                sdr_peak *out, int max_peaks, int *n_out) {
+    __shared__ int s_scan[K2_THREADS];
+    find_peaks_block(cum, n, cumulation_size, thr, out, max_peaks, n_out, s_scan);
+}
+
+}  // namespace sdr
