@@ -1,0 +1,480 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the SDRainer DSP hot path on B200 (BASELINE.json metric).
+
+A *step* is one pass of the hot path (K1 fused FFT+|X|^2+dB+noise floor+taps+cumulation, K2 thresholds+
+keys+peaks) over one batch of synthetic IQ.  Workload at every N: BASELINE.json configs[1] shape --
+192 kS/s streams, 2048-point blocks, 50 CW signals / listeners per stream -- as S independent streams
+x 100 blocks (one cumulation window, 1.07 s of signal) per step, S chosen so that the batch is
+> 2 GiB (far larger than the 126 MB L2, so no flush between iterations is needed).
+
+  value  : Msamples/s with the IQ already resident in HBM (CUDA events on the launch stream).
+  e2e    : same metric through the C ABI with HOST buffers: pinned H2D + kernels + result D2H in the
+           timed region, double-buffered over the engine's three streams.
+  roofline: K1's algorithmic bytes / K1's event-timed duration vs MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline: the CPU oracle (C restatement of the Go reference; the Go toolchain is absent)
+           timed on this box's host cores on a bounded sample of the same workload.
+
+`--impl reference` times only that CPU path (rank 0; other ranks exit 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FS = 192000
+N = 2048
+LISTENERS = 50
+BLOCKS_PER_STREAM = 100
+EDGE = 70
+METRIC = "IQ Msamples/s through FFT+peak+envelope path"
+SM_COUNT = 148
+
+
+def alg_bytes_per_block(n=N, l=LISTENERS):
+    """8N (fp32 IQ read once) + 4N/100 (cumulation flush) + 4L + 16 (taps + noise scalars)"""
+    return 8 * n + 4 * n / 100.0 + 4 * l + 16
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return json.load(f)
+        except Exception:
+            return None
+    return None
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic IQ on the device (torch is plumbing: memory + RNG); same signal model as synth.py
+# ---------------------------------------------------------------------------------------------
+def make_device_iq(torch, n_streams, seed, device):
+    from sdrainer_b200 import synth
+    total = BLOCKS_PER_STREAM * N
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    iq = torch.empty((n_streams, total, 2), dtype=torch.float32, device=device)
+    bins_all = []
+    units = torch.from_numpy(synth.morse_units(synth.DEFAULT_TEXT).astype(np.float32)).to(device)
+    t = torch.arange(total, device=device, dtype=torch.float64) / FS
+    nmod = (torch.arange(total, device=device) % N).to(torch.float64)
+    rng = np.random.default_rng(seed)
+    chunk = 4
+    for s0 in range(0, n_streams, chunk):
+        s1 = min(n_streams, s0 + chunk)
+        ns = s1 - s0
+        noise = torch.randn((ns, total, 2), generator=g, device=device, dtype=torch.float32) * 1e-4
+        bins = np.empty((ns, LISTENERS), np.int64)
+        amp = np.empty((ns, LISTENERS))
+        wpm = np.empty((ns, LISTENERS))
+        start = np.empty((ns, LISTENERS))
+        phase = np.empty((ns, LISTENERS))
+        for i in range(ns):
+            tones = synth.make_tones(rng, LISTENERS, N, EDGE, wpm_range=(15.0, 30.0))
+            bins[i] = [tn.bin for tn in tones]
+            amp[i] = [tn.amplitude for tn in tones]
+            wpm[i] = [tn.wpm for tn in tones]
+            start[i] = [tn.start_s for tn in tones]
+            phase[i] = [tn.phase for tn in tones]
+            bins_all.append(bins[i].astype(np.int32).copy())
+        k = torch.from_numpy(bins - N // 2).to(device).to(torch.float64)            # [ns, L]
+        ph = (k[:, :, None] * nmod[None, None, :] / N) % 1.0                        # exact per-block periodicity
+        ang = (2 * np.pi) * ph + torch.from_numpy(phase).to(device)[:, :, None]
+        dit = torch.from_numpy(1.2 / wpm).to(device)[:, :, None]
+        idx = torch.floor((t[None, None, :] - torch.from_numpy(start).to(device)[:, :, None]) / dit).to(torch.int64)
+        env = torch.where(idx >= 0, units[idx.clamp(min=0) % units.numel()], torch.zeros((), device=device))
+        a = torch.from_numpy(amp).to(device)[:, :, None] * env
+        re = (a * torch.cos(ang)).sum(dim=1).to(torch.float32)
+        im = (a * torch.sin(ang)).sum(dim=1).to(torch.float32)
+        iq[s0:s1, :, 0] = noise[:, :, 0] + re
+        iq[s0:s1, :, 1] = noise[:, :, 1] + im
+        del noise, ph, ang, idx, env, a, re, im
+    return iq, bins_all
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.th = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.th = threading.Thread(target=self._read, daemon=True)
+        self.th.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle on host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_run(n_threads, streams_per_thread, seed=4242):
+    """every thread runs the oracle's hot loop over `streams_per_thread` streams x 100 blocks"""
+    from oracle import oracle as O
+    from sdrainer_b200 import synth
+    O.lib()
+    specs = []
+    for i in range(n_threads * streams_per_thread):
+        spec = synth.config(2, seconds=1.0, stream=seed + i)
+        spec.n_blocks = BLOCKS_PER_STREAM
+        specs.append(spec)
+    # distinct content per stream is irrelevant to CPU timing: synthesise a few and reuse them
+    base = [synth.generate(s) for s in specs[:min(4, len(specs))]]
+    bins = [[t.bin for t in s.tones] for s in specs[:len(base)]]
+    O.process_stream(base[0][:2 * N * 2], N, listener_bins=bins[0], sample_rate=FS)  # warm tables (not thread safe)
+
+    def work(tid):
+        for j in range(streams_per_thread):
+            k = (tid * streams_per_thread + j) % len(base)
+            O.process_stream(base[k], N, edge_width=EDGE, listener_bins=bins[k], sample_rate=FS)
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(n_threads)]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    dt = time.perf_counter() - t0
+    samples = n_threads * streams_per_thread * BLOCKS_PER_STREAM * N
+    return samples, dt
+
+
+def cpu_sample(target_s=12.0):
+    cores = os.cpu_count() or 1
+    s0, d0 = cpu_run(cores, 1)
+    per = max(1, int(0.25 * target_s / max(d0, 1e-3)))
+    samples, dt, rounds = 0, 0.0, 0
+    while dt < target_s and rounds < 64:
+        s, d = cpu_run(cores, per)
+        samples += s
+        dt += d
+        rounds += 1
+    return {"value": samples / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
+            "sample": f"{rounds} rounds of {cores} threads x {per} streams x {BLOCKS_PER_STREAM} blocks of N={N} with "
+                      f"{LISTENERS} listeners (C restatement of the Go reference, oracle/sdr_oracle.c; {dt:.1f} s of CPU work)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    s0, d0 = cpu_run(cores, 1)  # untimed probe to size a step at ~2 s
+    per = max(1, min(32, int(2.0 / max(d0, 1e-3))))
+    for _ in range(args.warmup):
+        cpu_run(cores, 1)
+    tot_samples, tot_t = 0, 0.0
+    for _ in range(args.steps):
+        s, d = cpu_run(cores, per)
+        tot_samples += s
+        tot_t += d
+    value = tot_samples / tot_t / 1e6
+    sample = (f"each step: {cores} threads x {per} streams x {BLOCKS_PER_STREAM} blocks (N={N}, {LISTENERS} listeners); "
+              "C restatement of the Go reference (no Go toolchain in this image)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.streams, note=f"CPU arm: each step is a bounded sample of {cores * per} streams of this workload"),
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(n_streams, note=None):
+    c = {"workload": "BASELINE configs[1]: 192 kS/s IQ streams, 2048-pt FFT blocks, 50 CW signals/listeners per stream",
+         "sample_rate": FS, "block_size": N, "listeners_per_stream": LISTENERS, "streams_per_gpu": n_streams,
+         "blocks_per_stream_per_step": BLOCKS_PER_STREAM, "edge_width": EDGE,
+         "l2_policy": "inputs_larger_than_L2 (batch > 2 GiB vs 126 MB L2; no flush needed)", "parallelism": "streams sharded by GPU, no collective"}
+    if note:
+        c["note"] = note
+    return c
+
+
+# ---------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from sdrainer_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    capi.lib()  # fail loudly if the extension is missing
+
+    n_streams = args.streams
+    n_blocks = n_streams * BLOCKS_PER_STREAM
+    samples_per_step = n_blocks * N
+    iq, bins_all = make_device_iq(torch, n_streams, seed=1234 + rank, device=device)
+    torch.cuda.synchronize()
+
+    stream = torch.cuda.current_stream()
+    eng = capi.Engine(N, max_streams=n_streams, max_listeners=LISTENERS, max_blocks_per_batch=n_blocks,
+                      max_peaks_per_flush=128, n_slots=2, device=local_rank, cuda_stream=stream.cuda_stream)
+    sids = [eng.open_stream(FS) for _ in range(n_streams)]
+    stride = BLOCKS_PER_STREAM * 2 * N * 4
+    base_ptr = iq.data_ptr()
+    works = [dict(stream=sids[i], iq=base_ptr + i * stride, n_blocks=BLOCKS_PER_STREAM, edge_width=EDGE,
+                  peak_threshold=15.0, listener_bins=bins_all[i]) for i in range(n_streams)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident ----
+    prepared = eng.prepare(works)  # the sdr_work array is built once; a step is one sdr_submit call
+
+    def step():
+        return eng.submit_prepared(prepared, capi.NO_D2H)
+
+    k1_ms = []
+    for _ in range(args.warmup):
+        t = step()
+        eng.collect_raw(t)
+        eng.release(t)
+    barrier()
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tickets = []
+    e0.record(stream)
+    for i in range(args.steps):
+        t = step()
+        # the two slots alternate; collect the older one (already finished or finishing) to free its slot
+        tickets.append(t)
+        if len(tickets) == 2:
+            r = eng.collect_raw(tickets[0])
+            k1_ms.append(r.k1_ms)
+            eng.release(tickets.pop(0))
+    e1.record(stream)
+    for t in tickets:
+        r = eng.collect_raw(t)
+        k1_ms.append(r.k1_ms)
+        eng.release(t)
+    barrier()
+    clocks = sampler.stop()
+    launches = eng.launch_count() - launches0
+    elapsed_ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([elapsed_ms], device=device, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(tt.item())
+    value = world * samples_per_step * args.steps / (elapsed_ms * 1e-3) / 1e6
+    k1_avg_ms = float(np.mean(k1_ms))
+
+    # parity spot check of the timed configuration (rank 0): a few streams against the oracle
+    parity = None
+    if rank == 0 and not args.no_check:
+        parity = spot_check(eng, capi, iq, bins_all, sids)
+
+    # ---- e2e: host buffers through the C ABI, H2D + kernels + D2H inside the timed region ----
+    eng.close()
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, capi, torch, iq, bins_all, local_rank, world, dist, device)
+
+    peaks, peak_src = measured_peaks()
+    abytes = alg_bytes_per_block() * n_blocks
+    achieved = abytes / (k1_avg_ms * 1e-3) / 1e9
+    tr = ncu_traffic()
+    roofline = {"bound": "hbm", "kernel": "k1_spectral_kernel<2048>", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "peak_source": peak_src,
+                "traffic": (tr or {}).get("dram_bytes_per_launch"), "algorithmic_bytes_per_launch": abytes,
+                "k1_ms_per_launch": k1_avg_ms, "k1_share_of_step": k1_avg_ms * args.steps / elapsed_ms}
+    if tr:
+        roofline["traffic_note"] = tr.get("note")
+
+    if rank == 0:
+        cpu = None if args.no_cpu else cpu_sample()
+        line = {
+            "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(n_streams),
+            "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "realtime_streams_per_gpu": value / world / (FS / 1e6),
+            "realtime_cw_channels_per_gpu": value / world / (FS / 1e6) * LISTENERS,
+            "parity_spot_check": parity,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def spot_check(eng, capi, iq, bins_all, sids):
+    """3 streams of the timed batch, fresh stream state, against the oracle (decisions exact up to near-ties)"""
+    from oracle import oracle as O
+    flips = 0
+    peaks_equal = True
+    worst = 0.0
+    for i in (0, len(sids) // 2, len(sids) - 1):
+        host = iq[i].reshape(-1).cpu().numpy()
+        eng.reset_stream(sids[i])
+        res = eng.collect(eng.submit([dict(stream=sids[i], iq=host, edge_width=EDGE, listener_bins=bins_all[i])],
+                                     capi.WANT_FLUSH_CUM))
+        ref = O.process_stream(host, N, edge_width=EDGE, listener_bins=bins_all[i], sample_rate=FS)
+        worst = max(worst, float(np.abs(res.psd_noise_floor - ref.noise[:, 0]).max() / ref.noise[:, 0].max()))
+        listen = ref.thresholds[:, 0] + ref.thresholds[:, 1]
+        ref_keys = (ref.taps > listen[:, None]).astype(np.uint8)
+        for b, l in np.argwhere(res.keys[:, :LISTENERS] != ref_keys):
+            if abs(float(ref.taps[b, l]) - float(listen[b])) >= 1e-3:
+                return {"ok": False, "why": f"key flip stream {i} block {b} listener {l}"}
+            flips += 1
+        got = [(int(p["from"]), int(p["to"]), int(p["signal_bin"])) for p in res.peaks(0)]
+        peaks_equal = peaks_equal and got == [p.key() for p in ref.peaks[0]]
+    return {"ok": bool(peaks_equal and worst < 1e-4), "streams": 3, "excused_near_tie_key_flips": flips,
+            "peak_lists_identical": bool(peaks_equal), "noise_floor_max_rel_err": worst}
+
+
+def run_e2e(args, capi, torch, iq, bins_all, local_rank, world, dist, device):
+    n_streams = iq.shape[0]
+    n_blocks = n_streams * BLOCKS_PER_STREAM
+    eng = capi.Engine(N, max_streams=n_streams, max_listeners=LISTENERS, max_blocks_per_batch=n_blocks,
+                      max_peaks_per_flush=128, n_slots=2, device=local_rank)
+    sids = [eng.open_stream(FS) for _ in range(n_streams)]
+    nbytes = n_blocks * 2 * N * 4
+    pinned = eng.alloc_pinned(nbytes)
+    host = pinned.view(np.float32)
+    host[:] = iq.reshape(-1).cpu().numpy()
+    per = BLOCKS_PER_STREAM * 2 * N
+    works = [dict(stream=sids[i], iq=host[i * per:(i + 1) * per], n_blocks=BLOCKS_PER_STREAM, edge_width=EDGE,
+                  peak_threshold=15.0, listener_bins=bins_all[i]) for i in range(n_streams)]
+    flags = capi.NO_TAPS
+    prepared = eng.prepare(works)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    steps = max(2, min(args.steps, args.e2e_steps))
+    for _ in range(2):
+        t = eng.submit_prepared(prepared, flags)
+        eng.collect_raw(t)
+        eng.release(t)
+    sync()
+    t0 = time.perf_counter()
+    pending = []
+    checksum = 0
+    for _ in range(steps):
+        pending.append(eng.submit_prepared(prepared, flags))
+        if len(pending) == 2:
+            r = eng.collect_raw(pending[0])
+            checksum += int(r.keys[0])  # touch the device->host result
+            eng.release(pending.pop(0))
+    for t in pending:
+        r = eng.collect_raw(t)
+        checksum += int(r.keys[0])
+        eng.release(t)
+    sync()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([dt], device=device, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    ts = (LISTENERS + 3) // 4 * 4
+    n_flush = n_streams
+    d2h = n_blocks * (4 + 8 + 16 + ts) + n_flush * (4 + 4 + 128 * 28)
+    eng.free_pinned(pinned)
+    eng.close()
+    return {"value": world * n_blocks * N * steps / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(nbytes),
+            "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": 1e3 * dt / steps,
+            "note": "pinned host IQ -> sdr_submit (H2D, K1, K2) -> sdr_collect (keys, thresholds, noise scalars, peaks D2H); "
+                    "2 slots in flight; PCIe-bound"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=9 * SM_COUNT, help="streams per GPU (x100 blocks each per step)")
+    ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-check", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -47,6 +47,7 @@ extern "C" {
 #define SDR_WANT_SPECTRUM 0x2    /* debug/parity: also store spectrum[] and psd[] per block (dsp/fft.go:23 outputs) */
 #define SDR_NO_PEAKS 0x4         /* skip FindPeaks at flushes (decode mode / pool full, rx/receiver.go:410) */
 #define SDR_NO_D2H 0x8           /* leave results on the device (throughput measurement of the kernels alone) */
+#define SDR_NO_TAPS 0x10         /* do not copy the float32 tap values back (keys, thresholds and peaks still are) */
 
 typedef struct sdr_engine sdr_engine;
 typedef int64_t sdr_ticket;
@@ -111,6 +112,7 @@ typedef struct {
     const float *spectrum;         /* [n_blocks][N] or NULL */
     const float *psd;              /* [n_blocks][N] or NULL */
     float gpu_ms;                  /* device time of this ticket's kernels (CUDA events) */
+    float k1_ms, k2_ms;            /* split: fused spectral kernel / post kernel */
     int gpu_launches;              /* kernels launched for this ticket */
 } sdr_result;
 

@@ -22,7 +22,6 @@
 #include "../../include/sdrgpu.h"
 #include "k1_spectral.cuh"
 #include "k2_post.cuh"
-#include "k3_goertzel.cuh"
 
 using namespace sdr;
 
@@ -67,7 +66,7 @@ struct Slot {
     float *h_spectrum = nullptr, *h_psd = nullptr;  // lazy
     std::vector<int> work_block_offset, work_flush_offset;
     int n_works = 0, n_blocks = 0, n_flushes = 0, launches = 0;
-    cudaEvent_t ev_h2d = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_k0 = nullptr, ev_km = nullptr, ev_k1 = nullptr, ev_done = nullptr;
 };
 
 }  // namespace
@@ -231,6 +230,7 @@ void free_slot(Slot &s) {
     cudaFreeHost(s.h_psd);
     if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
+    if (s.ev_km) cudaEventDestroy(s.ev_km);
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
     s = Slot();
@@ -263,6 +263,7 @@ int alloc_slot(sdr_engine *e, Slot &s) {
     CK(e, cudaMallocHost((void **)&s.h_flush_cum, MF * N * sizeof(float)));
     CK(e, cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
     CK(e, cudaEventCreate(&s.ev_k0));
+    CK(e, cudaEventCreate(&s.ev_km));
     CK(e, cudaEventCreate(&s.ev_k1));
     CK(e, cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
     return SDR_OK;
@@ -275,12 +276,12 @@ Slot *find_slot(sdr_engine *e, sdr_ticket t) {
 }
 
 __global__ void __launch_bounds__(128) noise_floor_kernel(const float *psd, int n, int e, float *out_min, double *out_var) {
-    __shared__ double wsum[16];
+    __shared__ double wsum[32];
     const int ws = nf_window_size(n, e);
     const int n_win = nf_window_count(n, e);
-    nf_window_sums<128>(psd, wsum, e, ws, n_win, threadIdx.x);
+    nf_window_sums<128>(psd, wsum, wsum + 16, e, ws, n_win, threadIdx.x);
     __syncthreads();
-    if (threadIdx.x < 32) nf_select_variance(psd, wsum, e, ws, n_win, threadIdx.x, out_min, out_var);
+    if (threadIdx.x < 32) nf_select_variance(psd, wsum, wsum + 16, e, ws, n_win, threadIdx.x, out_min, out_var);
 }
 
 int ensure_scratch(sdr_engine *e, size_t bytes) {
@@ -622,6 +623,7 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     a1.dbg_psd = s.d_psd;
     CK(e, cudaEventRecord(s.ev_k0, e->s_compute));
     CK(e, launch_k1(e, a1, dbg, e->s_compute));
+    CK(e, cudaEventRecord(s.ev_km, e->s_compute));
     K2Args a2;
     a2.works = reinterpret_cast<const PostWork *>(s.d_desc + dl.post);
     a2.rolling = e->d_rolling;
@@ -650,7 +652,8 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
         CK(e, cudaMemcpyAsync(s.h_psd_floor, s.d_psd_floor, nb * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
         CK(e, cudaMemcpyAsync(s.h_variance, s.d_variance, nb * sizeof(double), cudaMemcpyDeviceToHost, e->s_d2h));
         CK(e, cudaMemcpyAsync(s.h_thresholds, s.d_thresholds, nb * 4 * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
-        CK(e, cudaMemcpyAsync(s.h_taps, s.d_taps, nb * TS * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
+        if (!(flags & SDR_NO_TAPS))
+            CK(e, cudaMemcpyAsync(s.h_taps, s.d_taps, nb * TS * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
         CK(e, cudaMemcpyAsync(s.h_keys, s.d_keys, nb * TS, cudaMemcpyDeviceToHost, e->s_d2h));
         if (n_flushes > 0) {
             const size_t nf = (size_t)n_flushes;
@@ -705,7 +708,7 @@ int sdr_collect(sdr_engine *e, sdr_ticket t, int blocking, sdr_result *out) {
         out->psd_noise_floor = s.h_psd_floor;
         out->noise_variance = s.h_variance;
         out->thresholds = s.h_thresholds;
-        out->taps = s.h_taps;
+        out->taps = (s.flags & SDR_NO_TAPS) ? nullptr : s.h_taps;
         out->keys = s.h_keys;
         out->flush_block = s.h_flush_block;
         out->flush_n_peaks = s.h_flush_n_peaks;
@@ -716,6 +719,8 @@ int sdr_collect(sdr_engine *e, sdr_ticket t, int blocking, sdr_result *out) {
     }
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1) == cudaSuccess) out->gpu_ms = ms;
+    if (cudaEventElapsedTime(&ms, s.ev_k0, s.ev_km) == cudaSuccess) out->k1_ms = ms;
+    if (cudaEventElapsedTime(&ms, s.ev_km, s.ev_k1) == cudaSuccess) out->k2_ms = ms;
     out->gpu_launches = s.launches;
     return SDR_OK;
 }

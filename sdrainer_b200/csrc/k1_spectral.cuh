@@ -110,7 +110,7 @@ struct K1Geom {
     static constexpr int NSTAGE = 2;
     static constexpr int LMAX = 256;       // listener bins cached in smem per group
     static constexpr int TW2_BYTES = 15 * R3 * 8;
-    static constexpr int MISC_BYTES = 16 * 8 /*wsum*/ + LMAX * 4 + NSTAGE * 8 /*mbar*/ + 64;
+    static constexpr int MISC_BYTES = 32 * 8 /*wsum x, x^2*/ + LMAX * 4 + NSTAGE * 8 /*mbar*/ + 64;
     static constexpr int GROUP_BYTES = ((NSTAGE * STAGE_BYTES + E1_BYTES + TW2_BYTES + MISC_BYTES) + 127) / 128 * 128;
     static constexpr int G = (T >= 128) ? 1 : 128 / T;  // groups per CTA
     static constexpr int CTA_THREADS = G * T;
@@ -148,57 +148,88 @@ __device__ __forceinline__ float psd_to_db(float psd) {
 }
 
 // ---- dsp.FindNoiseFloor (dsp/fft.go:215-252), parallel form --------------------------------
-// Window w covers bins [e + w*ws, e + (w+1)*ws); its mean is only evaluated when the loop reaches
-// the next bin, so the 10th window is skipped when 10*ws == N - 2e (n_win = 9).  float64 sums of
-// float32 values as in the reference (summation order differs: tree instead of sequential, a
-// relative 1e-16 effect).
+// Reference behaviour reproduced here (quirks included; dsp/fft.go:215-252):
+//  * window w covers bins [e + w*ws, e + (w+1)*ws), ws = (N-2e)/10; its mean is only evaluated when
+//    the loop reaches the NEXT bin, so the 10th window is skipped when 10*ws == N-2e (n_win = 9);
+//  * the first window is always taken, later ones only on a strict `<` (earliest minimum wins;
+//    a NaN mean never replaces, a NaN first mean is never replaced);
+//  * `from` is only ever assigned in the very first iteration (count is 0 at the loop top only
+//    there), so the variance runs over [e .. first bin of the window after the winner] INCLUSIVE,
+//    i.e. (w+1)*ws + 1 terms around the winner's mean, divided by ws.
+// float64 sums of float32 values as in the reference.  The variance is evaluated from per-window
+// sums of x and x^2 (both exact products in float64): sum (x-m)^2 = S2 - m*(2*S1 - n*m); rounding
+// differs from the reference's sequential loop at the 1e-15 relative level.
 __host__ __device__ __forceinline__ int nf_window_size(int n, int e) { return (n - 2 * e) / 10; }
 __host__ __device__ __forceinline__ int nf_window_count(int n, int e) {
     const int ws = nf_window_size(n, e);
     return (10 * ws < n - 2 * e) ? 10 : 9;
 }
 
-// all T threads of a group (T % 32 == 0); result WSUM[0..n_win) valid after the next group barrier
+// all T threads of a group (T % 32 == 0); WS1/WS2[0..n_win) valid after the next group barrier
 template <int T>
-__device__ __forceinline__ void nf_window_sums(const float *PSD, double *WSUM, int e, int ws, int n_win, int t) {
+__device__ __forceinline__ void nf_window_sums(const float *PSD, double *WS1, double *WS2, int e, int ws, int n_win, int t) {
     const int warp = t / 32, lane = t % 32;
     constexpr int NW = T / 32;
     for (int w = warp; w < n_win; w += NW) {
         const int from = e + w * ws;
-        double acc = 0.0;
-        for (int i = lane; i < ws; i += 32) acc += (double)PSD[from + i];
-        acc = warp_sum(acc);
-        if (lane == 0) WSUM[w] = acc;
+        double a1 = 0.0, a2 = 0.0;
+        for (int i = lane; i < ws; i += 32) {
+            const double x = (double)PSD[from + i];
+            a1 += x;
+            a2 = fma(x, x, a2);
+        }
+        a1 = warp_sum(a1);
+        a2 = warp_sum(a2);
+        if (lane == 0) {
+            WS1[w] = a1;
+            WS2[w] = a2;
+        }
     }
 }
 
-// one full warp; the sequential min selection runs identically on every lane (dsp/fft.go:217-236),
-// the variance over [from..to] INCLUSIVE (ws+1 terms, :244-248) is a warp reduction.
-__device__ __forceinline__ void nf_select_variance(const float *PSD, const double *WSUM, int e, int ws, int n_win,
-                                                   int lane, float *out_min, double *out_var) {
-    double min_value = (double)PSD[0];
-    bool first = true;
-    double result_mean = 0.0;
-    int result_from = 0, result_to = 0;
-    for (int w = 0; w < n_win; w++) {
-        const double mean = WSUM[w] / (double)ws;
-        if (mean < min_value || first) {
-            min_value = mean;
-            first = false;
-            result_mean = mean;
-            result_from = e + w * ws;
-            result_to = e + (w + 1) * ws;  // first bin of the next window
+// one full warp: lane w owns window w
+__device__ __forceinline__ void nf_select_variance(const float *PSD, const double *WS1, const double *WS2, int e, int ws,
+                                                   int n_win, int lane, float *out_min, double *out_var) {
+    const unsigned full = 0xffffffffu;
+    const double dws = (double)ws;
+    const bool real = lane < n_win;
+    double s1 = real ? WS1[lane] : 0.0, s2 = real ? WS2[lane] : 0.0;
+    const double mean = s1 / dws;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    double key = mean;
+    if (!real || (lane > 0 && isnan(mean))) key = inf;
+    int idx = lane;
+    const double mean0 = __shfl_sync(full, mean, 0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ok = __shfl_xor_sync(full, key, o);
+        const int oi = __shfl_xor_sync(full, idx, o);
+        if (ok < key || (ok == key && oi < idx)) {
+            key = ok;
+            idx = oi;
         }
     }
-    double acc = 0.0;
-    for (int i = result_from + lane; i <= result_to; i += 32) {
-        const double d = (double)PSD[i] - result_mean;
-        acc += d * d;
+    const int wsel = isnan(mean0) ? 0 : idx;
+    // inclusive prefix sums over windows 0..lane
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double p1 = __shfl_up_sync(full, s1, o);
+        const double p2 = __shfl_up_sync(full, s2, o);
+        if (lane >= o) {
+            s1 += p1;
+            s2 += p2;
+        }
     }
-    acc = warp_sum(acc);
+    const double m = __shfl_sync(full, mean, wsel);
+    double P1 = __shfl_sync(full, s1, wsel);
+    double P2 = __shfl_sync(full, s2, wsel);
     if (lane == 0) {
-        *out_min = (float)min_value;
-        *out_var = acc / (double)ws;
+        const double x = (double)PSD[e + (wsel + 1) * ws];
+        P1 += x;
+        P2 = fma(x, x, P2);
+        const double n = (double)((wsel + 1) * ws + 1);
+        *out_min = (float)m;
+        *out_var = (P2 - m * (2.0 * P1 - n * m)) / dws;
     }
 }
 
@@ -217,7 +248,7 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS) k1_spectral_kernel(con
     float *PSD = reinterpret_cast<float *>(E1);  // aliases E1 (E1 is dead after pass 2 loads)
     float2 *TW2 = reinterpret_cast<float2 *>(base + NSTAGE * Gm::STAGE_BYTES + Gm::E1_BYTES);
     double *WSUM = reinterpret_cast<double *>(base + NSTAGE * Gm::STAGE_BYTES + Gm::E1_BYTES + Gm::TW2_BYTES);
-    int *LB = reinterpret_cast<int *>(WSUM + 16);
+    int *LB = reinterpret_cast<int *>(WSUM + 32);
     uint64_t *FULL = reinterpret_cast<uint64_t *>(LB + Gm::LMAX);
 
     const int group_id = blockIdx.x * G + g;
@@ -365,12 +396,12 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS) k1_spectral_kernel(con
             }
 
             // ---------------- noise floor: window sums (dsp/fft.go:224-241) ----------------
-            nf_window_sums<T>(PSD, WSUM, e, ws, n_win, t);
+            nf_window_sums<T>(PSD, WSUM, WSUM + 16, e, ws, n_win, t);
             // listener taps (rx/receiver.go:393): same dB function as the owner thread
             for (int l = t; l < L; l += T) a.taps[(size_t)ob * a.tap_stride + l] = psd_to_db<N>(PSD[LB[l]]);
             group_sync<T, G>(g);  // B3b: WSUM complete
 
-            if (t < 32) nf_select_variance(PSD, WSUM, e, ws, n_win, t, &a.psd_floor[ob], &a.variance[ob]);
+            if (t < 32) nf_select_variance(PSD, WSUM, WSUM + 16, e, ws, n_win, t, &a.psd_floor[ob], &a.variance[ob]);
             group_sync<T, G>(g);  // B4: PSD (=E1) may be overwritten by the next block
         }
 

@@ -1,0 +1,316 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs (bit-exact where the domain allows it, otherwise the tolerances of
+SURVEY.md section 8(d), written in parity_util.py)."""
+import os
+
+import numpy as np
+import pytest
+
+import parity_util as pu
+from conftest import GOLDEN
+from sdrainer_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _spec(n, fs, n_blocks, seed, k=8, keyed=True, off_center=0.0):
+    rng = np.random.default_rng(seed)
+    tones = synth.make_tones(rng, k, n, 70, wpm_range=(18.0, 28.0), keyed=keyed, off_center=off_center)
+    return synth.StreamSpec(sample_rate=fs, block_size=n, n_blocks=n_blocks, seed=seed, tones=tones)
+
+
+@pytest.mark.parametrize("n", [512, 1024, 2048, 4096])
+def test_spectrum_and_psd_parity(capi, oracle, n):
+    """dsp.FFT.IQToSpectrumAndPSD (dsp/fft.go:23-37): fp32 GPU vs the float64 reference arithmetic"""
+    spec = _spec(n, 93.75 * n, 24, seed=n, k=10, off_center=0.3)
+    iq = synth.generate(spec)
+    with capi.Engine(n, max_blocks_per_batch=64) as eng:
+        s_gpu, p_gpu = eng.iq_to_spectrum_and_psd(iq)
+    r = oracle.process_stream(iq, n, want_spectrum=True)
+    m = pu.check_spectrum(s_gpu, p_gpu, r.spectrum, r.psd)
+    assert m["n_signal_bins"] > 0
+    print(n, m)
+
+
+@pytest.mark.parametrize("n", [512, 2048])
+def test_analytic_tone_and_fftshift(capi, n):
+    """dsp/fft_test.go:10-29 semantics end to end: a tone at baseband bin k lands at (k+N/2)%N with |X|^2 = (aN)^2"""
+    a = 0.01
+    iq = np.zeros((3, n, 2), np.float32)
+    ks = (0, 37, n - 5)
+    for i, k in enumerate(ks):
+        x = a * np.exp(2j * np.pi * k * np.arange(n) / n)
+        iq[i, :, 0], iq[i, :, 1] = x.real, x.imag
+    with capi.Engine(n) as eng:
+        spec, psd = eng.iq_to_spectrum_and_psd(iq)
+    for i, k in enumerate(ks):
+        kk = (k + n // 2) % n
+        assert int(np.argmax(psd[i])) == kk
+        assert abs(psd[i, kk] / (a * n) ** 2 - 1) < 1e-5
+        expect_db = 10 * np.log10(20 * (a * n) ** 2 / n ** 2) + 120
+        assert abs(spec[i, kk] - expect_db) < 1e-3
+
+
+def test_window_extension_parity(capi, oracle):
+    n = 1024
+    spec = _spec(n, 96000, 6, seed=3)
+    iq = synth.generate(spec)
+    win = np.hanning(n).astype(np.float32) + np.float32(0.01)
+    with capi.Engine(n, window=win) as eng:
+        s_gpu, p_gpu = eng.iq_to_spectrum_and_psd(iq)
+    r = oracle.process_stream(iq, n, window=win, want_spectrum=True)
+    pu.check_spectrum(s_gpu, p_gpu, r.spectrum, r.psd)
+
+
+def _run_batch(capi, spec, iq, bins, edge=70, peak_thr=15.0, flags=0, chunks=None, n_slots=2):
+    n = spec.block_size
+    with capi.Engine(n, max_streams=2, max_listeners=max(len(bins), 1), max_blocks_per_batch=max(spec.n_blocks, 1),
+                     max_peaks_per_flush=n // 2 + 1, n_slots=n_slots) as eng:
+        s = eng.open_stream(spec.sample_rate)
+        outs = []
+        pos = 0
+        for c in (chunks or [spec.n_blocks]):
+            part = np.ascontiguousarray(iq[pos * 2 * n:(pos + c) * 2 * n])
+            t = eng.submit([dict(stream=s, iq=part, edge_width=edge, peak_threshold=peak_thr, listener_bins=bins)],
+                           flags | capi.WANT_FLUSH_CUM)
+            outs.append(eng.collect(t))
+            pos += c
+        return outs
+
+
+def _concat(outs, name):
+    return np.concatenate([getattr(o, name) for o in outs], axis=0)
+
+
+def _compare_with_oracle(oracle, spec, iq, bins, outs, edge=70, peak_thr=15.0):
+    n = spec.block_size
+    r = oracle.process_stream(iq, n, edge_width=edge, peak_threshold=peak_thr, listener_bins=bins,
+                              sample_rate=spec.sample_rate)
+    floor = _concat(outs, "psd_noise_floor")
+    var = _concat(outs, "noise_variance")
+    thr = _concat(outs, "thresholds")
+    taps = _concat(outs, "taps")[:, :len(bins)]
+    keys = _concat(outs, "keys")[:, :len(bins)]
+    # (iv) noise-floor scalars.  The window choice is a decision: same window => tiny relative error
+    pu.check_scalars(floor, r.noise[:, 0], what="psdNoiseFloor")
+    pu.check_scalars(var, r.noise[:, 1], rel=2e-3, what="noise variance")
+    # thresholds are dB values around 20..50: compare absolutely
+    assert np.abs(thr[:, :3] - r.thresholds).max() < 2e-3
+    assert np.abs(thr[:, 3] - (r.thresholds[:, 0] + r.thresholds[:, 1])).max() < 2e-3
+    # taps on keyed-down blocks are noise bins (fp32 error scales with block energy): compare in PSD domain
+    lin_g, lin_r = 10 ** (taps.astype(np.float64) / 10), 10 ** (r.taps.astype(np.float64) / 10)
+    blockmax = lin_r.max(axis=1, keepdims=True)
+    assert (np.abs(lin_g - lin_r) <= 2e-6 * np.maximum(blockmax, lin_r)).all()
+    strong = r.taps > (r.thresholds[:, :1] + 15)
+    if strong.any():
+        assert np.abs(taps[strong] - r.taps[strong]).max() < 1e-3
+    # (v) key states: exact except listed near-ties
+    listen_ref = r.thresholds[:, 0] + r.thresholds[:, 1]
+    excused = pu.check_keys(keys, r.taps, listen_ref)
+    # flushes: cumulation and peak lists
+    fc = _concat(outs, "flush_cum")
+    assert fc.shape == r.flush_cum.shape
+    assert np.abs(fc - r.flush_cum).max() < 0.5  # sum of 100 dB values; per-bin noise-level fp32 error
+    gp = []
+    for o in outs:
+        for f in range(o.n_flushes):
+            gp.append(pu.peak_keys(o.peaks(f)))
+    assert len(gp) == r.n_flush
+    fblocks = [i for i in range(spec.n_blocks) if (i + 1) % 100 == 0]
+    for f in range(r.n_flush):
+        ref_keys = [p.key() for p in r.peaks[f]]
+        pu.check_peaks(gp[f], ref_keys, r.flush_cum[f], r.thresholds[fblocks[f], 2])
+    return r, excused
+
+
+def test_cfg1_batch_against_oracle(capi, oracle):
+    """config 1: 48 kS/s, N=512, 5 keyed tones at 20 WPM (the TCI shape, tci/tci.go:157-158)"""
+    spec = synth.config(1, seconds=8.0)
+    iq = synth.generate(spec)
+    bins = [t.bin for t in spec.tones]
+    outs = _run_batch(capi, spec, iq, bins)
+    r, excused = _compare_with_oracle(oracle, spec, iq, bins, outs)
+    assert r.n_flush == spec.n_blocks // 100 and r.n_flush >= 7
+    assert len(excused) <= 2
+    # every tone is found as a peak at its own bin in the last flush
+    found = {p.signal_bin for p in r.peaks[-1]}
+    assert set(bins) <= found
+
+
+def test_cfg2_batch_against_oracle(capi, oracle):
+    """config 2: 192 kS/s, N=2048, 50 CW signals at varied SNR"""
+    spec = synth.config(2, seconds=3.3)
+    iq = synth.generate(spec)
+    bins = [t.bin for t in spec.tones]
+    outs = _run_batch(capi, spec, iq, bins)
+    _compare_with_oracle(oracle, spec, iq, bins, outs)
+
+
+def test_ragged_batches_are_bit_identical_to_one_batch(capi):
+    """state carried across submits (cumulation + rolling means) must not change a single bit"""
+    spec = _spec(1024, 96000, 337, seed=21, k=6)
+    iq = synth.generate(spec)
+    bins = [t.bin for t in spec.tones]
+    one = _run_batch(capi, spec, iq, bins)
+    ragged = _run_batch(capi, spec, iq, bins, chunks=[37, 1, 63, 100, 29, 7, 100], n_slots=1)
+    for name in ("psd_noise_floor", "noise_variance", "thresholds", "taps", "keys", "flush_cum", "flush_n_peaks"):
+        a, b = _concat(one, name), _concat(ragged, name)
+        assert a.shape == b.shape and np.array_equal(a, b, equal_nan=True), name
+    fb = np.concatenate([o.flush_block + off for o, off in zip(ragged, np.cumsum([0, 37, 1, 63, 100, 29, 7]))])
+    assert list(fb) == [99, 199, 299]
+
+
+def test_multi_stream_batch_equals_individual(capi, oracle):
+    """config 4 in miniature: independent streams in one launch, different listeners and edge widths"""
+    n = 2048
+    specs = [_spec(n, 192000, nb, seed=100 + i, k=5 + i) for i, nb in enumerate((130, 100, 57, 201))]
+    iqs = [synth.generate(s) for s in specs]
+    binss = [[t.bin for t in s.tones] for s in specs]
+    edges = [70, 24, 100, 70]
+    with capi.Engine(n, max_streams=4, max_listeners=16, max_blocks_per_batch=600, max_peaks_per_flush=256) as eng:
+        ss = [eng.open_stream(192000) for _ in specs]
+        works = [dict(stream=ss[i], iq=iqs[i], edge_width=edges[i], peak_threshold=15.0, listener_bins=binss[i])
+                 for i in range(4)]
+        res = eng.collect(eng.submit(works, capi.WANT_FLUSH_CUM))
+    assert list(res.work_block_offset) == [0, 130, 230, 287, 488]
+    assert list(res.work_flush_offset) == [0, 1, 2, 2, 4]
+    for i in range(4):
+        b0, b1 = res.work_block_offset[i], res.work_block_offset[i + 1]
+        r = oracle.process_stream(iqs[i], n, edge_width=edges[i], listener_bins=binss[i], sample_rate=192000)
+        pu.check_scalars(res.psd_noise_floor[b0:b1], r.noise[:, 0], what=f"stream {i} floor")
+        assert np.abs(res.thresholds[b0:b1, :3] - r.thresholds).max() < 2e-3
+        pu.check_keys(res.keys[b0:b1, :len(binss[i])], r.taps, r.thresholds[:, 0] + r.thresholds[:, 1])
+        f0, f1 = res.work_flush_offset[i], res.work_flush_offset[i + 1]
+        assert f1 - f0 == r.n_flush
+        for f in range(r.n_flush):
+            fb = 100 * (f + 1) - 1
+            assert res.flush_block[f0 + f] == b0 + fb
+            pu.check_peaks(pu.peak_keys(res.peaks(f0 + f)), [p.key() for p in r.peaks[f]], r.flush_cum[f],
+                           r.thresholds[fb, 2])
+
+
+def test_device_pointer_input_and_no_d2h(capi):
+    import torch
+    n = 2048
+    spec = _spec(n, 192000, 200, seed=5)
+    iq = synth.generate(spec)
+    bins = [t.bin for t in spec.tones]
+    host = _run_batch(capi, spec, iq, bins)[0]
+    d = torch.from_numpy(iq).cuda()
+    with capi.Engine(n, max_listeners=16, max_blocks_per_batch=200, max_peaks_per_flush=n // 2 + 1) as eng:
+        s = eng.open_stream(192000)
+        t = eng.submit([dict(stream=s, iq=d.data_ptr(), n_blocks=200, listener_bins=bins)], capi.WANT_FLUSH_CUM)
+        dev = eng.collect(t)
+        assert eng.launch_count() == 2
+    for name in ("psd_noise_floor", "noise_variance", "thresholds", "flush_cum"):
+        assert np.array_equal(getattr(host, name), getattr(dev, name), equal_nan=True), name
+    for name in ("taps", "keys"):
+        assert np.array_equal(getattr(host, name)[:, :len(bins)], getattr(dev, name)[:, :len(bins)]), name
+
+
+def test_single_call_noise_floor_and_peaks(capi, oracle):
+    """dsp.FindNoiseFloor / dsp.FindPeaks drop-ins on crafted vectors, incl. the reference's quirks"""
+    for n, e in ((512, 70), (512, 6), (2048, 24), (4096, 48)):
+        rng = np.random.default_rng(n + e)
+        psd = (rng.exponential(1.0, n) * 4e-5).astype(np.float32)
+        with capi.Engine(n) as eng:
+            mn, var = eng.find_noise_floor(psd, e)
+            omn, ovar = oracle.find_noise_floor(psd, e)
+            assert abs(float(mn) - float(omn)) <= 1e-6 * float(omn)
+            assert abs(var - ovar) <= 1e-9 * ovar
+            # the 10th window is never evaluated when (N-2e)%10 == 0
+            psd2 = np.full(n, 1.0, np.float32)
+            ws = (n - 2 * e) // 10
+            psd2[e + 9 * ws: e + 10 * ws] = 0.01
+            mn2, _ = eng.find_noise_floor(psd2, e)
+            assert mn2 == oracle.find_noise_floor(psd2, e)[0]
+            # peaks: plateau (first max wins), == threshold (strict >), run open at the end, NaN, -inf
+            cum = np.zeros(n, np.float32)
+            cum[100:104] = [2000, 3000, 3000, 2500]
+            cum[200] = 1500.0
+            cum[300] = 1500.1
+            cum[310:313] = [1600, np.nan, 1700]
+            cum[320] = -np.inf
+            cum[n - 2:] = [4000, 5000]
+            got, cnt = eng.find_peaks(cum, 15.0)
+            fm = oracle.freqmap(48000, n, 0)
+            ref = oracle.find_peaks(cum, 15.0, fm)
+            assert cnt == len(ref)
+            assert [p.key() for p in got] == [p.key() for p in ref]
+            assert [p.signal_value for p in got] == [p.signal_value for p in ref]
+
+
+def test_all_zero_block_poisons_like_the_reference(capi, oracle):
+    """log10(0) = -Inf, then -Inf - (-Inf) = NaN in the running sums, permanently"""
+    n = 512
+    spec = _spec(n, 48000, 70, seed=9, k=3)
+    iq = synth.generate(spec)
+    iq[5 * 2 * n:6 * 2 * n] = 0
+    bins = [t.bin for t in spec.tones]
+    out = _run_batch(capi, spec, iq, bins)[0]
+    r = oracle.process_stream(iq, n, listener_bins=bins, sample_rate=48000)
+    assert np.isneginf(out.taps[5, :len(bins)]).all() and np.isneginf(r.taps[5]).all()
+    assert np.isneginf(out.thresholds[5, 0]) and np.isneginf(r.thresholds[5, 0])
+    # the running sum stays -Inf while the -Inf sample is inside the 60-block ring and turns NaN
+    # (-Inf - (-Inf)) when it leaves it, 60 blocks later -- forever
+    assert np.isneginf(out.thresholds[5:65, 0]).all() and np.isneginf(r.thresholds[5:65, 0]).all()
+    assert np.isnan(out.thresholds[65:, 0]).all() and np.isnan(r.thresholds[65:, 0]).all()
+    assert np.array_equal(out.keys[:, :len(bins)], (r.taps > (r.thresholds[:, 0] + r.thresholds[:, 1])[:, None]))
+    assert (out.keys[65:, :len(bins)] == 0).all()
+
+
+def test_error_codes_never_crash(capi):
+    n = 512
+    with pytest.raises(capi.SdrError):
+        capi.Engine(1000)
+    with capi.Engine(n, max_listeners=4, max_blocks_per_batch=10) as eng:
+        s = eng.open_stream(48000)
+        iq = np.zeros(2 * n * 4, np.float32)
+        for bad in (dict(stream=s + 5, iq=iq), dict(stream=s, iq=iq, listener_bins=[n]),
+                    dict(stream=s, iq=iq, listener_bins=[1, 2, 3, 4, 5]), dict(stream=s, iq=iq, edge_width=252),
+                    dict(stream=s, iq=np.zeros(2 * n * 11, np.float32))):
+            with pytest.raises(capi.SdrError) as ei:
+                eng.submit([bad])
+            assert ei.value.code == capi.EINVAL
+        with pytest.raises(capi.SdrError):
+            eng.submit([dict(stream=s, iq=iq), dict(stream=s, iq=iq)])
+        t1 = eng.submit([dict(stream=s, iq=iq)])
+        t2 = eng.submit([dict(stream=s, iq=iq)])
+        with pytest.raises(capi.SdrError) as ei:
+            eng.submit([dict(stream=s, iq=iq)])  # both slots busy: caller drops (rx/receiver.go:328-333)
+        assert ei.value.code == capi.EBUSY
+        eng.collect(t1)
+        eng.collect(t2)
+        assert eng.cumulation_count(s) == 8
+
+
+def test_committed_golden_vectors_without_the_oracle(capi):
+    """GPU path against tests/golden/oracle_vectors.npz (generated by tests/golden/make_golden.py)"""
+    g = np.load(os.path.join(GOLDEN, "oracle_vectors.npz"))
+    for tag, cfg, nblk in (("c1", 1, 230), ("c2", 2, 120)):
+        spec = synth.config(cfg)
+        spec.n_blocks = nblk
+        iq = synth.generate(spec)
+        bins = [int(b) for b in g[tag + "_bins"]]
+        out = _run_batch(capi, spec, iq, bins)[0]
+        pu.check_scalars(out.psd_noise_floor, g[tag + "_noise"][:, 0], what="floor")
+        assert np.abs(out.thresholds[:, :3] - g[tag + "_thresholds"]).max() < 2e-3
+        ref_taps = g[tag + "_taps"]
+        ref_listen = g[tag + "_thresholds"][:, 0] + g[tag + "_thresholds"][:, 1]
+        pu.check_keys(out.keys[:, :len(bins)], ref_taps, ref_listen)
+        assert pu.peak_keys(out.peaks(0)) == [tuple(r) for r in g[tag + "_peaks0"]]
+
+
+def test_parseval_and_linearity_at_bench_size(capi):
+    """size-independent properties at the bench configuration's block shape: sum(psd) = N*sum|x|^2,
+    psd(c*x) = c^2 psd(x)"""
+    n = 2048
+    rng = np.random.default_rng(77)
+    nb = 1024
+    iq = (rng.standard_normal(nb * 2 * n).astype(np.float32) * np.float32(1e-3))
+    with capi.Engine(n, max_blocks_per_batch=nb) as eng:
+        _, psd = eng.iq_to_spectrum_and_psd(iq)
+        _, psd4 = eng.iq_to_spectrum_and_psd(iq * np.float32(4.0))
+    energy = (iq.astype(np.float64) ** 2).reshape(nb, -1).sum(axis=1)
+    assert np.abs(psd.astype(np.float64).sum(axis=1) / (n * energy) - 1).max() < 1e-5
+    assert np.array_equal(psd4, psd * np.float32(16.0))  # power-of-two scaling is exact in fp32
