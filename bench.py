@@ -463,7 +463,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--streams", type=int, default=9 * SM_COUNT, help="streams per GPU (x100 blocks each per step)")
+    ap.add_argument("--streams", type=int, default=12 * SM_COUNT,
+                    help="streams per GPU (x100 blocks each per step); 12*148 = 3 full waves of 4 resident CTAs per SM")
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

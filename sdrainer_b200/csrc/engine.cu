@@ -146,8 +146,14 @@ template <int N>
 cudaError_t launch_k1_n(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st) {
     using Gm = K1Geom<N>;
     const bool win = a.window != nullptr;
-    int need = (a.n_segs + Gm::G - 1) / Gm::G;
-    int grid = need < e->k1_grid_cap ? need : e->k1_grid_cap;
+    // every group walks the segment list with stride grid*G: pick the grid so that all groups get the
+    // same number of rounds (no straggler CTA running alone on its SM at the end)
+    const int need = (a.n_segs + Gm::G - 1) / Gm::G;
+    int grid = need;
+    if (need > e->k1_grid_cap) {
+        const int rounds = (need + e->k1_grid_cap - 1) / e->k1_grid_cap;
+        grid = (need + rounds - 1) / rounds;
+    }
     if (grid < 1) grid = 1;
     if (dbg) {
         if (win)
@@ -281,7 +287,12 @@ __global__ void __launch_bounds__(128) noise_floor_kernel(const float *psd, int 
     const int n_win = nf_window_count(n, e);
     nf_window_sums<128>(psd, wsum, wsum + 16, e, ws, n_win, threadIdx.x);
     __syncthreads();
-    if (threadIdx.x < 32) nf_select_variance(psd, wsum, wsum + 16, e, ws, n_win, threadIdx.x, out_min, out_var);
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const bool real = lane < n_win;
+        nf_select_variance(real ? wsum[lane] : 0.0, real ? wsum[16 + lane] : 0.0,
+                           real ? (double)psd[e + (lane + 1) * ws] : 0.0, ws, n_win, lane, out_min, out_var);
+    }
 }
 
 int ensure_scratch(sdr_engine *e, size_t bytes) {

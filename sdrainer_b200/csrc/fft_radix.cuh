@@ -5,6 +5,13 @@
 // thread keeps 16 complex points in registers and applies radix-16/8/4/2 butterflies, exchanging
 // through shared memory between passes (see k1_spectral.cuh).
 //
+// B200-specific: a complex value lives in one 64-bit register pair (re, im) and all arithmetic is
+// issued as packed f32x2 instructions (sm_100a FADD2 / FMUL2 / FFMA2).  Their operand modifiers
+// (half swap LO_HI, per-half negate, 32-bit scalar broadcast) make a complex add ONE instruction,
+// a multiplication by +-i free, and a complex multiply TWO instructions -- half the issue slots of
+// scalar code at the same FP32 pipe throughput (tools/microbench/packed_f32x2.cu).  The kernel is
+// issue-bound, so this is where the time goes.
+//
 // Register order: dftR leaves the result for frequency index OutIdx<R>::of(p) in register p
 // (digit-reversed); callers index with that constexpr map, everything is fully unrolled.
 #pragma once
@@ -12,33 +19,48 @@
 
 namespace sdr {
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-// a * w
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+// a - i*b = (a.x + b.y, a.y - b.x)
+__device__ __forceinline__ float2 csub_i(float2 a, float2 b) { return __fadd2_rn(a, make_float2(b.y, -b.x)); }
+// a + i*b = (a.x - b.y, a.y + b.x)
+__device__ __forceinline__ float2 cadd_i(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.y, b.x)); }
+// a * w = (a.x*w.x - a.y*w.y, a.y*w.x + a.x*w.y): FMUL2 with w.x broadcast, FFMA2 with swapped a and (-w.y, +w.y)
 __device__ __forceinline__ float2 cmul(float2 a, float2 w) {
-    return make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
+    const float2 t = __fmul2_rn(a, make_float2(w.x, w.x));
+    return __ffma2_rn(make_float2(a.y, a.x), make_float2(-w.y, w.y), t);
 }
-// a * (-i) = (a.y, -a.x)
+// a * (-i) = (a.y, -a.x): folded into the consumer's operand modifiers
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
 
 #define SDR_SQRT1_2 0.70710678118654752440f
 #define SDR_COS_PI_8 0.92387953251128675613f
 #define SDR_SIN_PI_8 0.38268343236508977173f
 
+// a * W8^1 = a * s(1 - i) = s(a.x + a.y, a.y - a.x)
+__device__ __forceinline__ float2 mul_w8_1(float2 a) {
+    const float2 t = __fadd2_rn(a, make_float2(a.y, -a.x));
+    return __fmul2_rn(t, make_float2(SDR_SQRT1_2, SDR_SQRT1_2));
+}
+// a * W8^3 = a * s(-1 - i) = s(a.y - a.x, -(a.x + a.y))
+__device__ __forceinline__ float2 mul_w8_3(float2 a) {
+    const float2 t = __fadd2_rn(make_float2(a.y, -a.x), make_float2(-a.x, -a.y));
+    return __fmul2_rn(t, make_float2(SDR_SQRT1_2, SDR_SQRT1_2));
+}
+
 __device__ __forceinline__ void dft2(float2 &a, float2 &b) {
-    float2 t = a;
+    const float2 t = a;
     a = cadd(t, b);
     b = csub(t, b);
 }
 
-// natural order in, natural order out
+// natural order in, natural order out: 8 packed adds
 __device__ __forceinline__ void dft4(float2 &x0, float2 &x1, float2 &x2, float2 &x3) {
-    float2 t0 = cadd(x0, x2), t1 = csub(x0, x2), t2 = cadd(x1, x3), t3 = csub(x1, x3);
+    const float2 t0 = cadd(x0, x2), t1 = csub(x0, x2), t2 = cadd(x1, x3), t3 = csub(x1, x3);
     x0 = cadd(t0, t2);
     x2 = csub(t0, t2);
-    // X1 = t1 - i*t3, X3 = t1 + i*t3
-    x1 = make_float2(t1.x + t3.y, t1.y - t3.x);
-    x3 = make_float2(t1.x - t3.y, t1.y + t3.x);
+    x1 = csub_i(t1, t3);  // t1 - i*t3
+    x3 = cadd_i(t1, t3);  // t1 + i*t3
 }
 
 template <int R>
@@ -64,14 +86,9 @@ struct OutIdx<16> {  // position p = 4*ka + kb holds X[ka + 4*kb]
 __device__ __forceinline__ void dft8(float2 (&v)[8]) {
 #pragma unroll
     for (int b = 0; b < 4; b++) dft2(v[b], v[b + 4]);
-    // ka = 1 row: v[4+b] *= W8^b
-    {
-        float2 a = v[5];  // W8^1 = s(1 - i)
-        v[5] = make_float2(SDR_SQRT1_2 * (a.x + a.y), SDR_SQRT1_2 * (a.y - a.x));
-        v[6] = mul_mi(v[6]);  // W8^2 = -i
-        a = v[7];             // W8^3 = s(-1 - i)
-        v[7] = make_float2(SDR_SQRT1_2 * (a.y - a.x), -SDR_SQRT1_2 * (a.x + a.y));
-    }
+    v[5] = mul_w8_1(v[5]);
+    v[6] = mul_mi(v[6]);  // W8^2 = -i
+    v[7] = mul_w8_3(v[7]);
     dft4(v[0], v[1], v[2], v[3]);
     dft4(v[4], v[5], v[6], v[7]);
 }
@@ -81,30 +98,17 @@ __device__ __forceinline__ void dft16(float2 (&v)[16]) {
 #pragma unroll
     for (int b = 0; b < 4; b++) dft4(v[b], v[b + 4], v[b + 8], v[b + 12]);
     // position 4*ka + b holds y[ka][b]; multiply by W16^(b*ka)
-    const float2 w1 = make_float2(SDR_COS_PI_8, -SDR_SIN_PI_8);   // W16^1
-    const float2 w3 = make_float2(SDR_SIN_PI_8, -SDR_COS_PI_8);   // W16^3
-    // ka = 1: exponents 0,1,2,3
-    v[5] = cmul(v[5], w1);
-    {
-        float2 a = v[6];  // W16^2 = s(1 - i)
-        v[6] = make_float2(SDR_SQRT1_2 * (a.x + a.y), SDR_SQRT1_2 * (a.y - a.x));
-    }
-    v[7] = cmul(v[7], w3);
-    // ka = 2: exponents 0,2,4,6
-    {
-        float2 a = v[9];  // W16^2
-        v[9] = make_float2(SDR_SQRT1_2 * (a.x + a.y), SDR_SQRT1_2 * (a.y - a.x));
-        v[10] = mul_mi(v[10]);  // W16^4 = -i
-        a = v[11];              // W16^6 = s(-1 - i)
-        v[11] = make_float2(SDR_SQRT1_2 * (a.y - a.x), -SDR_SQRT1_2 * (a.x + a.y));
-    }
-    // ka = 3: exponents 0,3,6,9
-    v[13] = cmul(v[13], w3);
-    {
-        float2 a = v[14];  // W16^6
-        v[14] = make_float2(SDR_SQRT1_2 * (a.y - a.x), -SDR_SQRT1_2 * (a.x + a.y));
-    }
-    v[15] = cmul(v[15], make_float2(-SDR_COS_PI_8, SDR_SIN_PI_8));  // W16^9 = -W16^1
+    const float2 w1 = make_float2(SDR_COS_PI_8, -SDR_SIN_PI_8);  // W16^1
+    const float2 w3 = make_float2(SDR_SIN_PI_8, -SDR_COS_PI_8);  // W16^3
+    v[5] = cmul(v[5], w1);            // ka=1: W^1
+    v[6] = mul_w8_1(v[6]);            //       W^2
+    v[7] = cmul(v[7], w3);            //       W^3
+    v[9] = mul_w8_1(v[9]);            // ka=2: W^2
+    v[10] = mul_mi(v[10]);            //       W^4 = -i
+    v[11] = mul_w8_3(v[11]);          //       W^6
+    v[13] = cmul(v[13], w3);          // ka=3: W^3
+    v[14] = mul_w8_3(v[14]);          //       W^6
+    v[15] = cmul(v[15], make_float2(-SDR_COS_PI_8, SDR_SIN_PI_8));  // W^9 = -W^1
 #pragma unroll
     for (int a = 0; a < 4; a++) dft4(v[4 * a], v[4 * a + 1], v[4 * a + 2], v[4 * a + 3]);
 }

@@ -110,7 +110,10 @@ struct K1Geom {
     static constexpr int NSTAGE = 2;
     static constexpr int LMAX = 256;       // listener bins cached in smem per group
     static constexpr int TW2_BYTES = 15 * R3 * 8;
-    static constexpr int MISC_BYTES = 32 * 8 /*wsum x, x^2*/ + LMAX * 4 + NSTAGE * 8 /*mbar*/ + 64;
+    static constexpr int TPW = (T / 10) / 3 * 3;  // noise floor: threads per window (multiple of 3: lanes 3w..3w+2 combine)
+    static constexpr int NFB = 16;               // noise floor: blocks whose window sums are batched for selection
+    static constexpr int NF_BYTES = NFB * 10 * (8 + 8 + 4);
+    static constexpr int MISC_BYTES = NF_BYTES + T * 8 /*chunk partials (s1,s2)*/ + LMAX * 4 + NSTAGE * 8 /*mbar*/ + 64;
     static constexpr int GROUP_BYTES = ((NSTAGE * STAGE_BYTES + E1_BYTES + TW2_BYTES + MISC_BYTES) + 127) / 128 * 128;
     static constexpr int G = (T >= 128) ? 1 : 128 / T;  // groups per CTA
     static constexpr int CTA_THREADS = G * T;
@@ -136,6 +139,13 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// MUFU.LG2 without the denormal fix-up sequence: a denormal |X|^2 (< 1.2e-38) is treated as 0 -> -Inf dB
+__device__ __forceinline__ float fast_log2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // dB projection of rx/receiver.go:376-378: float32(10*log10(20*psd/N^2)) + float32(120)
 template <int N>
 __device__ __forceinline__ float psd_to_db(float psd) {
@@ -143,7 +153,7 @@ __device__ __forceinline__ float psd_to_db(float psd) {
     constexpr float A = 3.01029995663981195f;  // 10*log10(2)
     constexpr double LOG2N = (N == 512) ? 9.0 : (N == 1024) ? 10.0 : (N == 2048) ? 11.0 : (N == 4096) ? 12.0 : 0.0;
     constexpr float B = (float)(13.0102999566398120 - 20.0 * LOG2N * 0.30102999566398120);  // 10*log10(20) - 20*log10(N)
-    float t = fmaf(A, __log2f(psd), B);
+    float t = fmaf(A, fast_log2(psd), B);
     return __fadd_rn(t, 120.0f);
 }
 
@@ -187,13 +197,13 @@ __device__ __forceinline__ void nf_window_sums(const float *PSD, double *WS1, do
     }
 }
 
-// one full warp: lane w owns window w
-__device__ __forceinline__ void nf_select_variance(const float *PSD, const double *WS1, const double *WS2, int e, int ws,
-                                                   int n_win, int lane, float *out_min, double *out_var) {
+// one full warp: lane w owns window w and passes in that window's sums (s1 = sum x, s2 = sum x^2)
+// and x_to = psd[e + (w+1)*ws] (the first bin of the next window); lanes >= n_win pass zeros.
+__device__ __forceinline__ void nf_select_variance(double s1, double s2, double x_to, int ws, int n_win, int lane,
+                                                   float *out_min, double *out_var) {
     const unsigned full = 0xffffffffu;
     const double dws = (double)ws;
     const bool real = lane < n_win;
-    double s1 = real ? WS1[lane] : 0.0, s2 = real ? WS2[lane] : 0.0;
     const double mean = s1 / dws;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     double key = mean;
@@ -210,9 +220,9 @@ __device__ __forceinline__ void nf_select_variance(const float *PSD, const doubl
         }
     }
     const int wsel = isnan(mean0) ? 0 : idx;
-    // inclusive prefix sums over windows 0..lane
+    // inclusive prefix sums over windows 0..lane (only lanes < 16 matter: n_win <= 10)
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
+    for (int o = 1; o < 16; o <<= 1) {
         const double p1 = __shfl_up_sync(full, s1, o);
         const double p2 = __shfl_up_sync(full, s2, o);
         if (lane >= o) {
@@ -223,14 +233,52 @@ __device__ __forceinline__ void nf_select_variance(const float *PSD, const doubl
     const double m = __shfl_sync(full, mean, wsel);
     double P1 = __shfl_sync(full, s1, wsel);
     double P2 = __shfl_sync(full, s2, wsel);
+    const double x = __shfl_sync(full, x_to, wsel);
     if (lane == 0) {
-        const double x = (double)PSD[e + (wsel + 1) * ws];
         P1 += x;
         P2 = fma(x, x, P2);
         const double n = (double)((wsel + 1) * ws + 1);
         *out_min = (float)m;
         *out_var = (P2 - m * (2.0 * P1 - n * m)) / dws;
     }
+}
+
+// One thread runs the sequential selection of dsp.FindNoiseFloor (dsp/fft.go:217-251) for one block from
+// that block's window sums: s1[w*stride] = sum x, s2[w*stride] = sum x^2, xto[w*stride] = psd[e+(w+1)*ws].
+__device__ __forceinline__ void nf_select_serial(const double *s1, const double *s2, const float *xto, int stride, int ws,
+                                                 int n_win, float *out_min, double *out_var) {
+    const double inv_ws = 1.0 / (double)ws;
+    double min_value = 0.0, P1 = 0.0, P2 = 0.0, bP1 = 0.0, bP2 = 0.0;
+    int best = 0;
+    for (int w = 0; w < n_win; w++) {
+        const double a1 = s1[w * stride];
+        P1 += a1;
+        P2 += s2[w * stride];
+        const double mean = a1 * inv_ws;
+        if (w == 0 || mean < min_value) {  // `mean < minValue || first`
+            min_value = mean;
+            best = w;
+            bP1 = P1;
+            bP2 = P2;
+        }
+    }
+    const double x = (double)xto[best * stride];
+    bP1 += x;
+    bP2 = fma(x, x, bP2);
+    const double n = (double)((best + 1) * ws + 1);  // bins e .. e+(best+1)*ws inclusive (the reference's `from` quirk)
+    *out_min = (float)min_value;
+    *out_var = (bP2 - min_value * (2.0 * bP1 - n * min_value)) * inv_ws;
+}
+
+// two bins at once (FFMA2 + FADD2); bit-identical to psd_to_db on each half
+template <int N>
+__device__ __forceinline__ float2 psd_to_db2(float2 psd) {
+    constexpr float A = 3.01029995663981195f;
+    constexpr double LOG2N = (N == 512) ? 9.0 : (N == 1024) ? 10.0 : (N == 2048) ? 11.0 : (N == 4096) ? 12.0 : 0.0;
+    constexpr float B = (float)(13.0102999566398120 - 20.0 * LOG2N * 0.30102999566398120);
+    const float2 lg = make_float2(fast_log2(psd.x), fast_log2(psd.y));
+    const float2 t = __ffma2_rn(make_float2(A, A), lg, make_float2(B, B));
+    return __fadd2_rn(t, make_float2(120.0f, 120.0f));
 }
 
 template <int N, bool DEBUG_STORE, bool HAS_WINDOW>
@@ -247,8 +295,11 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS) k1_spectral_kernel(con
     float2 *E1 = reinterpret_cast<float2 *>(base + NSTAGE * Gm::STAGE_BYTES);
     float *PSD = reinterpret_cast<float *>(E1);  // aliases E1 (E1 is dead after pass 2 loads)
     float2 *TW2 = reinterpret_cast<float2 *>(base + NSTAGE * Gm::STAGE_BYTES + Gm::E1_BYTES);
-    double *WSUM = reinterpret_cast<double *>(base + NSTAGE * Gm::STAGE_BYTES + Gm::E1_BYTES + Gm::TW2_BYTES);
-    int *LB = reinterpret_cast<int *>(WSUM + 32);
+    double *NFS1 = reinterpret_cast<double *>(base + NSTAGE * Gm::STAGE_BYTES + Gm::E1_BYTES + Gm::TW2_BYTES);
+    double *NFS2 = NFS1 + Gm::NFB * 10;
+    float *NFX = reinterpret_cast<float *>(NFS2 + Gm::NFB * 10);
+    float2 *PART = reinterpret_cast<float2 *>(NFX + Gm::NFB * 10);
+    int *LB = reinterpret_cast<int *>(PART + T);
     uint64_t *FULL = reinterpret_cast<uint64_t *>(LB + Gm::LMAX);
 
     const int group_id = blockIdx.x * G + g;
@@ -308,20 +359,37 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS) k1_spectral_kernel(con
         const int e = wp.edge_width;
         const int ws = nf_window_size(N, e);
         const int n_win = nf_window_count(N, e);  // the 10th window only closes if a later bin exists
+        // this thread's share of the window sums: TPW threads per window, <= nf_len contiguous bins each
+        constexpr int TPW = Gm::TPW;
+        int nf_lo = 0, nf_len = 0;
+        if (t < 10 * TPW) {
+            const int w = t / TPW, part = t - w * TPW;
+            const int per = (ws + TPW - 1) / TPW;
+            nf_lo = e + w * ws + part * per;
+            const int hi = min(nf_lo + per, e + (w + 1) * ws);
+            nf_len = max(hi - nf_lo, 0);
+        }
 
-        // cumulation registers: bin kk(i,k3) = (c + 256*k3 + N/2) % N with c = t + i*T
-        float cum[16];
+        // cumulation registers in pass-3 register order: cum2[i][q] holds positions p = 2q, 2q+1 of pair i,
+        // i.e. bins kk = (c + 256*OutIdx<R3>(p) + N/2) % N with c = t + i*T
+        float2 cum2[PAIRS][R3 / 2];
         if (sg.load_state) {
             const float *cs = a.cum_state + (size_t)sg.stream * N;
 #pragma unroll
             for (int i = 0; i < PAIRS; i++)
 #pragma unroll
-                for (int k3 = 0; k3 < R3; k3++) cum[i * R3 + k3] = cs[((t + i * T) + 256 * k3 + N / 2) % N];
+                for (int q = 0; q < R3 / 2; q++) {
+                    cum2[i][q].x = cs[((t + i * T) + 256 * OutIdx<R3>::of(2 * q) + N / 2) % N];
+                    cum2[i][q].y = cs[((t + i * T) + 256 * OutIdx<R3>::of(2 * q + 1) + N / 2) % N];
+                }
         } else {
 #pragma unroll
-            for (int i = 0; i < 16; i++) cum[i] = 0.f;
+            for (int i = 0; i < PAIRS; i++)
+#pragma unroll
+                for (int q = 0; q < R3 / 2; q++) cum2[i][q] = make_float2(0.f, 0.f);
         }
         group_sync<T, G>(g);  // LB visible
+        int nf_fill = 0, nf_first = sg.block_out;  // warp 0: batched noise-floor selection
 
         for (int blk = 0; blk < sg.n_blocks; blk++, item++) {
             const int s = item % NSTAGE;
@@ -337,10 +405,7 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS) k1_spectral_kernel(con
 #pragma unroll
             for (int m = 0; m < 16; m++) {
                 v[m] = IN[m * M + t];
-                if (HAS_WINDOW) {
-                    v[m].x *= win[m];
-                    v[m].y *= win[m];
-                }
+                if (HAS_WINDOW) v[m] = __fmul2_rn(v[m], make_float2(win[m], win[m]));
             }
             dft16(v);
 #pragma unroll
@@ -374,16 +439,22 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS) k1_spectral_kernel(con
                 for (int n3 = 0; n3 < R3; n3++) u[n3] = E2[n3 * S2 + c];
                 dftR<R3>(u);
 #pragma unroll
-                for (int p = 0; p < R3; p++) {
-                    const int k3 = OutIdx<R3>::of(p);
-                    const int kk = (c + 256 * k3 + N / 2) % N;  // dsp/fft.go:54-57 fftshift
-                    const float psd = fmaf(u[p].x, u[p].x, u[p].y * u[p].y);  // dsp/fft.go:71-73
-                    PSD[kk] = psd;
-                    const float db = psd_to_db<N>(psd);
-                    cum[i * R3 + k3] += db;  // rx/receiver.go:404-406
+                for (int q = 0; q < R3 / 2; q++) {
+                    // two bins at a time: |X|^2 (dsp/fft.go:71-73), dB + 120 (rx/receiver.go:376-378)
+                    const float2 sq0 = __fmul2_rn(u[2 * q], u[2 * q]);
+                    const float2 sq1 = __fmul2_rn(u[2 * q + 1], u[2 * q + 1]);
+                    const float2 psd = make_float2(sq0.x + sq0.y, sq1.x + sq1.y);
+                    const int kk0 = (c + 256 * OutIdx<R3>::of(2 * q) + N / 2) % N;  // dsp/fft.go:54-57 fftshift
+                    const int kk1 = (c + 256 * OutIdx<R3>::of(2 * q + 1) + N / 2) % N;
+                    PSD[kk0] = psd.x;
+                    PSD[kk1] = psd.y;
+                    const float2 db = psd_to_db2<N>(psd);
+                    cum2[i][q] = __fadd2_rn(cum2[i][q], db);  // rx/receiver.go:404-406
                     if (DEBUG_STORE) {
-                        a.dbg_spectrum[(size_t)ob * N + kk] = db;
-                        a.dbg_psd[(size_t)ob * N + kk] = psd;
+                        a.dbg_spectrum[(size_t)ob * N + kk0] = db.x;
+                        a.dbg_spectrum[(size_t)ob * N + kk1] = db.y;
+                        a.dbg_psd[(size_t)ob * N + kk0] = psd.x;
+                        a.dbg_psd[(size_t)ob * N + kk1] = psd.y;
                     }
                 }
             }
@@ -395,14 +466,59 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS) k1_spectral_kernel(con
                 issue_next();
             }
 
-            // ---------------- noise floor: window sums (dsp/fft.go:224-241) ----------------
-            nf_window_sums<T>(PSD, WSUM, WSUM + 16, e, ws, n_win, t);
+            // ---------------- noise floor, phase 1: per-thread partial sums of x and x^2 over a
+            // contiguous share of one window (float32 inside the <=17-bin share, float64 across shares)
+            {
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+                for (int i = 0; i < nf_len; i++) {
+                    const float x = PSD[nf_lo + i];
+                    s1 += x;
+                    s2 = fmaf(x, x, s2);
+                }
+                PART[t] = make_float2(s1, s2);
+            }
+            // x_to = psd[first bin of the next window] must be read before B4 (PSD aliases E1, which the
+            // next block overwrites); lane 3w of warp 0 owns window w in phase 2
+            float x_to = 0.f;
+            if (t < 32 && (t % 3) == 0 && t / 3 < n_win) x_to = PSD[e + (t / 3 + 1) * ws];
             // listener taps (rx/receiver.go:393): same dB function as the owner thread
             for (int l = t; l < L; l += T) a.taps[(size_t)ob * a.tap_stride + l] = psd_to_db<N>(PSD[LB[l]]);
-            group_sync<T, G>(g);  // B3b: WSUM complete
+            group_sync<T, G>(g);  // B4: partial sums complete; PSD (=E1) may be overwritten by the next block
 
-            if (t < 32) nf_select_variance(PSD, WSUM, WSUM + 16, e, ws, n_win, t, &a.psd_floor[ob], &a.variance[ob]);
-            group_sync<T, G>(g);  // B4: PSD (=E1) may be overwritten by the next block
+            // ---------------- noise floor, phase 2 (warp 0 only; the other warps run ahead) ----------------
+            // lanes 3w..3w+2 add the TPW partial sums of window w, lane 3w keeps the result for a batched
+            // selection: every NFB blocks lane l runs dsp.FindNoiseFloor's sequential selection for block l.
+            if (t < 32) {
+                const int w = t / 3, j = t - 3 * w;
+                float s1 = 0.f, s2 = 0.f;
+                if (w < 10) {
+                    const float2 *pp = PART + w * TPW + j;
+#pragma unroll
+                    for (int m = 0; m < TPW / 3; m++) {
+                        const float2 pr = pp[3 * m];
+                        s1 += pr.x;
+                        s2 += pr.y;
+                    }
+                }
+                s1 += __shfl_down_sync(0xffffffffu, s1, 1) + __shfl_down_sync(0xffffffffu, s1, 2);
+                s2 += __shfl_down_sync(0xffffffffu, s2, 1) + __shfl_down_sync(0xffffffffu, s2, 2);
+                if (j == 0 && w < n_win) {
+                    NFS1[w * Gm::NFB + nf_fill] = (double)s1;
+                    NFS2[w * Gm::NFB + nf_fill] = (double)s2;
+                    NFX[w * Gm::NFB + nf_fill] = x_to;
+                }
+                nf_fill++;
+                if (nf_fill == Gm::NFB || blk == sg.n_blocks - 1) {
+                    __syncwarp();
+                    if (t < nf_fill) nf_select_serial(NFS1 + t, NFS2 + t, NFX + t, Gm::NFB, ws, n_win, &a.psd_floor[nf_first + t],
+                                                      &a.variance[nf_first + t]);
+                    __syncwarp();
+                    nf_first += nf_fill;
+                    nf_fill = 0;
+                }
+            }
+            // PART is rewritten only after B3 of the next block, which warp 0 must also pass: no hazard
         }
 
         // ---- end of segment: flush or save the cumulation ----
@@ -410,8 +526,12 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS) k1_spectral_kernel(con
 #pragma unroll
         for (int i = 0; i < PAIRS; i++)
 #pragma unroll
-            for (int k3 = 0; k3 < R3; k3++) dst[((t + i * T) + 256 * k3 + N / 2) % N] = cum[i * R3 + k3];
+            for (int q = 0; q < R3 / 2; q++) {
+                dst[((t + i * T) + 256 * OutIdx<R3>::of(2 * q) + N / 2) % N] = cum2[i][q].x;
+                dst[((t + i * T) + 256 * OutIdx<R3>::of(2 * q + 1) + N / 2) % N] = cum2[i][q].y;
+            }
         // after a flush the state row is never read: the next segment of the stream has load_state = 0
+        group_sync<T, G>(g);  // LB / PART reuse by the next segment
     }
 }
 

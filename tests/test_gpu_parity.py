@@ -101,7 +101,9 @@ def _compare_with_oracle(oracle, spec, iq, bins, outs, edge=70, peak_thr=15.0):
     lin_g, lin_r = 10 ** (taps.astype(np.float64) / 10), 10 ** (r.taps.astype(np.float64) / 10)
     blockmax = lin_r.max(axis=1, keepdims=True)
     assert (np.abs(lin_g - lin_r) <= 2e-6 * np.maximum(blockmax, lin_r)).all()
-    strong = r.taps > (r.thresholds[:, :1] + 15)
+    # signal bins: >= settled noise floor + 15 dB (the rolling mean is biased low for its first 59 outputs)
+    settled = float(np.median(r.thresholds[60:, 0])) if r.thresholds.shape[0] > 80 else float(r.thresholds[-1, 0])
+    strong = r.taps > settled + 15
     if strong.any():
         assert np.abs(taps[strong] - r.taps[strong]).max() < 1e-3
     # (v) key states: exact except listed near-ties
