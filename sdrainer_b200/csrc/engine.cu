@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -89,6 +90,7 @@ struct sdr_engine {
     sdr_ticket next_ticket = 1;
     int64_t launches = 0;
     int k1_grid_cap = 0;  // resident CTAs of K1 on this device
+    bool k1_tw2r = true;  // kernel variant: pass-2 twiddles in registers (SDR_K1_TW2R=0 selects the smem-table variant)
     // scratch for the dsp single calls
     float *d_scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -129,14 +131,20 @@ DescLayout desc_layout(const sdr_engine *e) {
 }
 
 template <int N>
-int k1_occupancy(bool dbg, bool win) {
+const void *k1_fn(bool dbg, bool win, bool tw2r) {
+    if (tw2r) {
+        if (dbg) return win ? (const void *)k1_spectral_kernel<N, true, true, true> : (const void *)k1_spectral_kernel<N, true, false, true>;
+        return win ? (const void *)k1_spectral_kernel<N, false, true, true> : (const void *)k1_spectral_kernel<N, false, false, true>;
+    }
+    if (dbg) return win ? (const void *)k1_spectral_kernel<N, true, true, false> : (const void *)k1_spectral_kernel<N, true, false, false>;
+    return win ? (const void *)k1_spectral_kernel<N, false, true, false> : (const void *)k1_spectral_kernel<N, false, false, false>;
+}
+
+template <int N>
+int k1_occupancy(bool dbg, bool win, bool tw2r) {
     using Gm = K1Geom<N>;
     int occ = 0;
-    const void *fn;
-    if (dbg)
-        fn = win ? (const void *)k1_spectral_kernel<N, true, true> : (const void *)k1_spectral_kernel<N, true, false>;
-    else
-        fn = win ? (const void *)k1_spectral_kernel<N, false, true> : (const void *)k1_spectral_kernel<N, false, false>;
+    const void *fn = k1_fn<N>(dbg, win, tw2r);
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, Gm::SMEM_BYTES);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, Gm::CTA_THREADS, Gm::SMEM_BYTES);
     return occ;
@@ -155,18 +163,9 @@ cudaError_t launch_k1_n(const sdr_engine *e, const K1Args &a, bool dbg, cudaStre
         grid = (need + rounds - 1) / rounds;
     }
     if (grid < 1) grid = 1;
-    if (dbg) {
-        if (win)
-            k1_spectral_kernel<N, true, true><<<grid, Gm::CTA_THREADS, Gm::SMEM_BYTES, st>>>(a);
-        else
-            k1_spectral_kernel<N, true, false><<<grid, Gm::CTA_THREADS, Gm::SMEM_BYTES, st>>>(a);
-    } else {
-        if (win)
-            k1_spectral_kernel<N, false, true><<<grid, Gm::CTA_THREADS, Gm::SMEM_BYTES, st>>>(a);
-        else
-            k1_spectral_kernel<N, false, false><<<grid, Gm::CTA_THREADS, Gm::SMEM_BYTES, st>>>(a);
-    }
-    return cudaGetLastError();
+    K1Args args = a;
+    void *params[] = {&args};
+    return cudaLaunchKernel(k1_fn<N>(dbg, win, e->k1_tw2r), dim3(grid), dim3(Gm::CTA_THREADS), params, Gm::SMEM_BYTES, st);
 }
 
 cudaError_t launch_k1(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st) {
@@ -179,13 +178,13 @@ cudaError_t launch_k1(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream
     return cudaErrorInvalidValue;
 }
 
-int k1_grid_cap_for(int n, bool win, int sm_count) {
+int k1_grid_cap_for(int n, bool win, bool tw2r, int sm_count) {
     int occ = 0;
     switch (n) {
-        case 512: occ = std::max(k1_occupancy<512>(false, win), 0); k1_occupancy<512>(true, win); break;
-        case 1024: occ = k1_occupancy<1024>(false, win); k1_occupancy<1024>(true, win); break;
-        case 2048: occ = k1_occupancy<2048>(false, win); k1_occupancy<2048>(true, win); break;
-        case 4096: occ = k1_occupancy<4096>(false, win); k1_occupancy<4096>(true, win); break;
+        case 512: occ = k1_occupancy<512>(false, win, tw2r); k1_occupancy<512>(true, win, tw2r); break;
+        case 1024: occ = k1_occupancy<1024>(false, win, tw2r); k1_occupancy<1024>(true, win, tw2r); break;
+        case 2048: occ = k1_occupancy<2048>(false, win, tw2r); k1_occupancy<2048>(true, win, tw2r); break;
+        case 4096: occ = k1_occupancy<4096>(false, win, tw2r); k1_occupancy<4096>(true, win, tw2r); break;
     }
     if (occ < 1) occ = 1;
     return occ * sm_count;
@@ -384,7 +383,11 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
     CKC(cudaMalloc((void **)&e->d_rolling, (size_t)cfg->max_streams * sizeof(RollingState)));
     CKC(cudaMemset(e->d_rolling, 0, (size_t)cfg->max_streams * sizeof(RollingState)));
     e->streams.resize(cfg->max_streams);
-    e->k1_grid_cap = k1_grid_cap_for(e->N, e->d_window != nullptr, e->sm_count);
+    {
+        const char *v = getenv("SDR_K1_TW2R");  // experiment switch; default: pass-2 twiddles in registers
+        e->k1_tw2r = !(v && v[0] == '0');
+    }
+    e->k1_grid_cap = k1_grid_cap_for(e->N, e->d_window != nullptr, e->k1_tw2r, e->sm_count);
     CKC(cudaGetLastError());
     e->slots.resize(cfg->n_slots);
     for (auto &s : e->slots) {

@@ -281,8 +281,10 @@ __device__ __forceinline__ float2 psd_to_db2(float2 psd) {
     return __fadd2_rn(t, make_float2(120.0f, 120.0f));
 }
 
-template <int N, bool DEBUG_STORE, bool HAS_WINDOW>
-__global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS) k1_spectral_kernel(const K1Args a) {
+// TW2R: keep the pass-2 twiddles in registers too (15 fewer shared-memory loads per thread and block; ptxas
+// still fits 128 registers = 4 resident CTAs per SM with a 12-byte spill)
+template <int N, bool DEBUG_STORE, bool HAS_WINDOW, bool TW2R>
+__global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS, 4) k1_spectral_kernel(const K1Args a) {
     using Gm = K1Geom<N>;
     constexpr int M = Gm::M, R3 = Gm::R3, T = Gm::T, PAIRS = Gm::PAIRS, S1 = Gm::S1, S2 = Gm::S2;
     constexpr int NSTAGE = Gm::NSTAGE, G = Gm::G;
@@ -347,6 +349,11 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS) k1_spectral_kernel(con
 
     // pass-2 role of this thread
     const int k1_p2 = t / R3, n3_p2 = t % R3;
+    float2 tw2r[TW2R ? 15 : 1];
+    if (TW2R) {
+#pragma unroll
+        for (int k = 0; k < 15; k++) tw2r[k] = TW2[k * R3 + n3_p2];
+    }
     uint32_t item = 0;
 
     for (int seg = group_id; seg < a.n_segs; seg += group_stride) {
@@ -364,7 +371,9 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS) k1_spectral_kernel(con
         int nf_lo = 0, nf_len = 0;
         if (t < 10 * TPW) {
             const int w = t / TPW, part = t - w * TPW;
-            const int per = (ws + TPW - 1) / TPW;
+            // an ODD share length makes the lane stride odd: the strided reads below are bank-conflict free
+            // within a window (lanes of neighbouring windows can still collide)
+            const int per = ((ws + TPW - 1) / TPW) | 1;
             nf_lo = e + w * ws + part * per;
             const int hi = min(nf_lo + per, e + (w + 1) * ws);
             nf_len = max(hi - nf_lo, 0);
@@ -390,6 +399,40 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS) k1_spectral_kernel(con
         }
         group_sync<T, G>(g);  // LB visible
         int nf_fill = 0, nf_first = sg.block_out;  // warp 0: batched noise-floor selection
+        float x_to = 0.f;                          // warp 0: psd[first bin of the next window], carried to phase 2
+
+        // noise floor, phase 2 (warp 0 only): lanes 3w..3w+2 add the TPW partial sums of window w, lane 3w keeps
+        // the result for a batched selection: every NFB blocks lane l runs dsp.FindNoiseFloor's sequential
+        // selection (dsp/fft.go:217-251) for block l of the batch.
+        auto nf_phase2 = [&](bool last) {
+            const int w = t / 3, j = t - 3 * w;
+            float s1 = 0.f, s2 = 0.f;
+            if (w < 10) {
+                const float2 *pp = PART + w * TPW + j;
+#pragma unroll
+                for (int m = 0; m < TPW / 3; m++) {
+                    const float2 pr = pp[3 * m];
+                    s1 += pr.x;
+                    s2 += pr.y;
+                }
+            }
+            s1 += __shfl_down_sync(0xffffffffu, s1, 1) + __shfl_down_sync(0xffffffffu, s1, 2);
+            s2 += __shfl_down_sync(0xffffffffu, s2, 1) + __shfl_down_sync(0xffffffffu, s2, 2);
+            if (j == 0 && w < n_win) {
+                NFS1[nf_fill * 10 + w] = (double)s1;
+                NFS2[nf_fill * 10 + w] = (double)s2;
+                NFX[nf_fill * 10 + w] = x_to;
+            }
+            nf_fill++;
+            if (nf_fill == Gm::NFB || last) {
+                __syncwarp();
+                if (t < nf_fill) nf_select_serial(NFS1 + t * 10, NFS2 + t * 10, NFX + t * 10, 1, ws, n_win,
+                                                  &a.psd_floor[nf_first + t], &a.variance[nf_first + t]);
+                __syncwarp();
+                nf_first += nf_fill;
+                nf_fill = 0;
+            }
+        };
 
         for (int blk = 0; blk < sg.n_blocks; blk++, item++) {
             const int s = item % NSTAGE;
@@ -402,8 +445,10 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS) k1_spectral_kernel(con
 
             // ---------------- pass 1: radix-16 over n1, column j = t ----------------
             float2 v[16];
+            // loads are issued in the order the first butterfly layer consumes them (b, b+4, b+8, b+12)
 #pragma unroll
-            for (int m = 0; m < 16; m++) {
+            for (int q = 0; q < 16; q++) {
+                const int m = (q & 3) * 4 + (q >> 2);
                 v[m] = IN[m * M + t];
                 if (HAS_WINDOW) v[m] = __fmul2_rn(v[m], make_float2(win[m], win[m]));
             }
@@ -411,21 +456,28 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS) k1_spectral_kernel(con
 #pragma unroll
             for (int p = 0; p < 16; p++) {
                 const int k1 = OutIdx<16>::of(p);
-                float2 x = v[p];
-                if (k1 > 0) x = cmul(x, tw1[k1 - 1]);
-                E1[k1 * S1 + t] = x;
+                if (k1 > 0) v[p] = cmul(v[p], tw1[k1 - 1]);
             }
+            // B4 (of the previous block): its partial sums are complete and nobody reads PSD any more, so E1
+            // (which PSD aliases) may be overwritten.  Everything above overlaps the slower warps' tail.
+            if (blk > 0) group_sync<T, G>(g);
+#pragma unroll
+            for (int p = 0; p < 16; p++) E1[OutIdx<16>::of(p) * S1 + t] = v[p];
             group_sync<T, G>(g);  // B1: E1 complete, IN consumed
+            if (blk > 0 && t < 32) nf_phase2(false);  // previous block; PART is rewritten only after B3
 
             // ---------------- pass 2: radix-16 over n2 for (k1, n3) ----------------
 #pragma unroll
-            for (int n2 = 0; n2 < 16; n2++) v[n2] = E1[k1_p2 * S1 + n2 * R3 + n3_p2];
+            for (int q = 0; q < 16; q++) {
+                const int n2 = (q & 3) * 4 + (q >> 2);
+                v[n2] = E1[k1_p2 * S1 + n2 * R3 + n3_p2];
+            }
             dft16(v);
 #pragma unroll
             for (int p = 0; p < 16; p++) {
                 const int k2 = OutIdx<16>::of(p);
                 float2 x = v[p];
-                if (k2 > 0) x = cmul(x, TW2[(k2 - 1) * R3 + n3_p2]);
+                if (k2 > 0) x = cmul(x, TW2R ? tw2r[k2 - 1] : TW2[(k2 - 1) * R3 + n3_p2]);
                 E2[n3_p2 * S2 + k1_p2 + 16 * k2] = x;
             }
             group_sync<T, G>(g);  // B2: E2 complete, E1 dead
@@ -436,7 +488,10 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS) k1_spectral_kernel(con
                 const int c = t + i * T;
                 float2 u[R3];
 #pragma unroll
-                for (int n3 = 0; n3 < R3; n3++) u[n3] = E2[n3 * S2 + c];
+                for (int q = 0; q < R3; q++) {  // issue order = consumption order of the first butterfly layer
+                    const int n3 = (R3 == 16) ? (q & 3) * 4 + (q >> 2) : (R3 == 8) ? (q & 1) * 4 + (q >> 1) : q;
+                    u[n3] = E2[n3 * S2 + c];
+                }
                 dftR<R3>(u);
 #pragma unroll
                 for (int q = 0; q < R3 / 2; q++) {
@@ -469,57 +524,34 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS) k1_spectral_kernel(con
             // ---------------- noise floor, phase 1: per-thread partial sums of x and x^2 over a
             // contiguous share of one window (float32 inside the <=17-bin share, float64 across shares)
             {
-                float s1 = 0.f, s2 = 0.f;
-#pragma unroll 4
-                for (int i = 0; i < nf_len; i++) {
-                    const float x = PSD[nf_lo + i];
+                // four independent chains (two packed accumulators) hide the FADD/LDS latency
+                float2 a1 = make_float2(0.f, 0.f), a2 = make_float2(0.f, 0.f);
+                const float *pp = PSD + nf_lo;
+                int i = 0;
+                for (; i + 4 <= nf_len; i += 4) {
+                    const float2 x01 = make_float2(pp[i], pp[i + 1]);
+                    const float2 x23 = make_float2(pp[i + 2], pp[i + 3]);
+                    a1 = __fadd2_rn(a1, x01);
+                    a2 = __ffma2_rn(x01, x01, a2);
+                    a1 = __fadd2_rn(a1, x23);
+                    a2 = __ffma2_rn(x23, x23, a2);
+                }
+                float s1 = a1.x + a1.y, s2 = a2.x + a2.y;
+                for (; i < nf_len; i++) {
+                    const float x = pp[i];
                     s1 += x;
                     s2 = fmaf(x, x, s2);
                 }
                 PART[t] = make_float2(s1, s2);
             }
-            // x_to = psd[first bin of the next window] must be read before B4 (PSD aliases E1, which the
-            // next block overwrites); lane 3w of warp 0 owns window w in phase 2
-            float x_to = 0.f;
+            // x_to = psd[first bin of the next window] is read here (PSD is gone after the next B4);
+            // lane 3w of warp 0 owns window w in phase 2
             if (t < 32 && (t % 3) == 0 && t / 3 < n_win) x_to = PSD[e + (t / 3 + 1) * ws];
             // listener taps (rx/receiver.go:393): same dB function as the owner thread
             for (int l = t; l < L; l += T) a.taps[(size_t)ob * a.tap_stride + l] = psd_to_db<N>(PSD[LB[l]]);
-            group_sync<T, G>(g);  // B4: partial sums complete; PSD (=E1) may be overwritten by the next block
-
-            // ---------------- noise floor, phase 2 (warp 0 only; the other warps run ahead) ----------------
-            // lanes 3w..3w+2 add the TPW partial sums of window w, lane 3w keeps the result for a batched
-            // selection: every NFB blocks lane l runs dsp.FindNoiseFloor's sequential selection for block l.
-            if (t < 32) {
-                const int w = t / 3, j = t - 3 * w;
-                float s1 = 0.f, s2 = 0.f;
-                if (w < 10) {
-                    const float2 *pp = PART + w * TPW + j;
-#pragma unroll
-                    for (int m = 0; m < TPW / 3; m++) {
-                        const float2 pr = pp[3 * m];
-                        s1 += pr.x;
-                        s2 += pr.y;
-                    }
-                }
-                s1 += __shfl_down_sync(0xffffffffu, s1, 1) + __shfl_down_sync(0xffffffffu, s1, 2);
-                s2 += __shfl_down_sync(0xffffffffu, s2, 1) + __shfl_down_sync(0xffffffffu, s2, 2);
-                if (j == 0 && w < n_win) {
-                    NFS1[w * Gm::NFB + nf_fill] = (double)s1;
-                    NFS2[w * Gm::NFB + nf_fill] = (double)s2;
-                    NFX[w * Gm::NFB + nf_fill] = x_to;
-                }
-                nf_fill++;
-                if (nf_fill == Gm::NFB || blk == sg.n_blocks - 1) {
-                    __syncwarp();
-                    if (t < nf_fill) nf_select_serial(NFS1 + t, NFS2 + t, NFX + t, Gm::NFB, ws, n_win, &a.psd_floor[nf_first + t],
-                                                      &a.variance[nf_first + t]);
-                    __syncwarp();
-                    nf_first += nf_fill;
-                    nf_fill = 0;
-                }
-            }
-            // PART is rewritten only after B3 of the next block, which warp 0 must also pass: no hazard
         }
+        group_sync<T, G>(g);  // B4 of the last block
+        if (t < 32) nf_phase2(true);
 
         // ---- end of segment: flush or save the cumulation ----
         float *dst = (sg.flush_idx >= 0) ? a.flush_cum + (size_t)sg.flush_idx * N : a.cum_state + (size_t)sg.stream * N;
