@@ -279,7 +279,10 @@ def run_gpu(args):
     iq, bins_all = make_device_iq(torch, n_streams, seed=1234 + rank, device=device)
     torch.cuda.synchronize()
 
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream: the engine launches everything on it, so the CUDA events recorded on it
+    # bracket exactly the K timed steps (torch's default stream has handle 0, which the C ABI reads as "own streams")
+    stream = torch.cuda.Stream(device=device)
+    assert stream.cuda_stream != 0
     eng = capi.Engine(N, max_streams=n_streams, max_listeners=LISTENERS, max_blocks_per_batch=n_blocks,
                       max_peaks_per_flush=128, n_slots=2, device=local_rank, cuda_stream=stream.cuda_stream)
     sids = [eng.open_stream(FS) for _ in range(n_streams)]
