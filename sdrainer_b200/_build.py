@@ -44,6 +44,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST_LIB = os.path.join(HERE, "libsdrhost.so")
+HOST_SOURCES = [os.path.join(HERE, "host", "host_capi.cpp"), os.path.join(HERE, "host", "sdrhost.hpp")]
+
+
+def build_host(force: bool = False) -> str:
+    """libsdrhost.so: the C++ host mirror of the Go interface (dsp/cw/rx) over the C ABI, linked to libsdrgpu.so.
+    -ffp-contract=off: the decoder's float64 arithmetic follows Go/amd64 (no fused multiply-add)."""
+    build(force=False)
+    stale = (not os.path.exists(HOST_LIB)) or any(os.path.getmtime(d) > os.path.getmtime(HOST_LIB) for d in HOST_SOURCES + [LIB])
+    if force or stale:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-o", HOST_LIB,
+                               HOST_SOURCES[0], "-L" + HERE, "-lsdrgpu", "-Wl,-rpath,$ORIGIN"])
+    return HOST_LIB
+
+
 if __name__ == "__main__":
     import sys
     print(build(force=True, verbose="-v" in sys.argv))
+    print(build_host(force=True))
