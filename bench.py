@@ -330,12 +330,13 @@ def run_gpu(args):
     barrier()
     clocks = sampler.stop()
     launches = eng.launch_count() - launches0
+    from sdrainer_b200 import sharding
     elapsed_ms = e0.elapsed_time(e1)
-    if world > 1:
-        tt = torch.tensor([elapsed_ms], device=device, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(tt.item())
-    value = world * samples_per_step * args.steps / (elapsed_ms * 1e-3) / 1e6
+    # whole-job throughput: units of all ranks / max-over-ranks device time (no data-path collective)
+    total_samples, max_s = sharding.aggregate(dist if world > 1 else None, torch, samples_per_step * args.steps,
+                                              elapsed_ms * 1e-3, device)
+    elapsed_ms = max_s * 1e3
+    value = total_samples / max_s / 1e6
     k1_avg_ms = float(np.mean(k1_ms))
 
     # parity spot check of the timed configuration (rank 0): a few streams against the oracle
