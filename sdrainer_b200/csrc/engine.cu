@@ -23,6 +23,7 @@
 #include "../../include/sdrgpu.h"
 #include "k1_spectral.cuh"
 #include "k2_post.cuh"
+#include "k1_large.cuh"
 
 using namespace sdr;
 
@@ -55,6 +56,7 @@ struct Slot {
     float *d_flush_cum = nullptr;
     float *d_spectrum = nullptr, *d_psd = nullptr;  // lazy (SDR_WANT_SPECTRUM)
     float *d_iq = nullptr;                          // lazy (host inputs)
+    float2 *d_tmp = nullptr;                        // large-block path: four-step intermediate
     // pinned host mirrors
     float *h_psd_floor = nullptr;
     double *h_variance = nullptr;
@@ -82,6 +84,10 @@ struct sdr_engine {
     cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     bool own_streams = true;
     float2 *d_tw1 = nullptr, *d_tw2 = nullptr;
+    // large-block path (N >= 8192): four-step split N = n1 * n2
+    bool large = false;
+    LargeGeom lg{};
+    float2 *d_tw_sub1 = nullptr, *d_tw_sub2 = nullptr, *d_tw_n = nullptr;
     float *d_window = nullptr;
     float *d_cum_state = nullptr;
     RollingState *d_rolling = nullptr;
@@ -113,7 +119,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // descriptor block layout (same on host and device)
 struct DescLayout {
-    size_t segs, works, post, lbins, total;
+    size_t segs, works, post, lbins, block_seg, total;
 };
 DescLayout desc_layout(const sdr_engine *e) {
     DescLayout l;
@@ -126,6 +132,8 @@ DescLayout desc_layout(const sdr_engine *e) {
     off = align_up(off + sizeof(PostWork) * (size_t)e->cfg.max_streams, 256);
     l.lbins = off;
     off = align_up(off + sizeof(int) * (size_t)e->cfg.max_streams * (size_t)(e->cfg.max_listeners > 0 ? e->cfg.max_listeners : 1), 256);
+    l.block_seg = off;
+    if (e->large) off = align_up(off + sizeof(int) * (size_t)e->cfg.max_blocks_per_batch, 256);
     l.total = off;
     return l;
 }
@@ -166,6 +174,71 @@ cudaError_t launch_k1_n(const sdr_engine *e, const K1Args &a, bool dbg, cudaStre
     K1Args args = a;
     void *params[] = {&args};
     return cudaLaunchKernel(k1_fn<N>(dbg, win, e->k1_tw2r), dim3(grid), dim3(Gm::CTA_THREADS), params, Gm::SMEM_BYTES, st);
+}
+
+template <int L, int STEP>
+cudaError_t launch_sub_fft(const SubFftArgs &sa, int n_ffts, int n_blocks, cudaStream_t st) {
+    const size_t smem = (size_t)2 * SUBFFT_F * (L + 1) * sizeof(float2);
+    sub_fft_kernel<L, STEP><<<dim3(n_ffts / SUBFFT_F, n_blocks), SUBFFT_F * L / 4, smem, st>>>(sa);
+    return cudaGetLastError();
+}
+
+template <int STEP>
+cudaError_t launch_sub_fft_len(int len, const SubFftArgs &sa, int n_ffts, int n_blocks, cudaStream_t st) {
+    switch (len) {
+        case 64: return launch_sub_fft<64, STEP>(sa, n_ffts, n_blocks, st);
+        case 128: return launch_sub_fft<128, STEP>(sa, n_ffts, n_blocks, st);
+        case 256: return launch_sub_fft<256, STEP>(sa, n_ffts, n_blocks, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// large-block path: step 1, step 2, noise floor + taps, cumulation (k1_large.cuh)
+cudaError_t launch_large(const sdr_engine *e, const K1Args &a, float2 *d_tmp, const int *d_block_seg, int n_blocks, int n_segs,
+                         cudaStream_t st) {
+    const int N = e->N;
+    SubFftArgs sa{};
+    sa.in = d_tmp;
+    sa.tmp = d_tmp;
+    sa.spectrum = a.dbg_spectrum;
+    sa.psd = a.dbg_psd;
+    sa.tw_n = e->d_tw_n;
+    sa.window = e->d_window;
+    sa.segs = a.segs;
+    sa.block_seg = d_block_seg;
+    sa.n = N;
+    sa.n1 = e->lg.n1;
+    sa.n2 = e->lg.n2;
+    sa.db_offset = (float)(10.0 * log10(20.0 / ((double)N * (double)N)));
+    sa.tw_sub = e->d_tw_sub1;
+    cudaError_t rc = launch_sub_fft_len<1>(e->lg.n1, sa, e->lg.n2, n_blocks, st);
+    if (rc != cudaSuccess) return rc;
+    sa.tw_sub = e->d_tw_sub2;
+    rc = launch_sub_fft_len<2>(e->lg.n2, sa, e->lg.n1, n_blocks, st);
+    if (rc != cudaSuccess) return rc;
+    LargePostArgs pa{};
+    pa.psd = a.dbg_psd;
+    pa.spectrum = a.dbg_spectrum;
+    pa.segs = a.segs;
+    pa.block_seg = d_block_seg;
+    pa.works = a.works;
+    pa.listener_bins = a.listener_bins;
+    pa.psd_floor = a.psd_floor;
+    pa.variance = a.variance;
+    pa.taps = a.taps;
+    pa.tap_stride = a.tap_stride;
+    pa.n = N;
+    large_post_kernel<<<n_blocks, 128, 0, st>>>(pa);
+    rc = cudaGetLastError();
+    if (rc != cudaSuccess) return rc;
+    LargeCumArgs ca{};
+    ca.spectrum = a.dbg_spectrum;
+    ca.segs = a.segs;
+    ca.cum_state = a.cum_state;
+    ca.flush_cum = a.flush_cum;
+    ca.n = N;
+    large_cum_kernel<<<dim3(N / 256, n_segs), 256, 0, st>>>(ca);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_k1(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st) {
@@ -222,6 +295,7 @@ void free_slot(Slot &s) {
     cudaFree(s.d_spectrum);
     cudaFree(s.d_psd);
     cudaFree(s.d_iq);
+    cudaFree(s.d_tmp);
     cudaFreeHost(s.h_psd_floor);
     cudaFreeHost(s.h_variance);
     cudaFreeHost(s.h_thresholds);
@@ -266,6 +340,11 @@ int alloc_slot(sdr_engine *e, Slot &s) {
     CK(e, cudaMallocHost((void **)&s.h_flush_n_peaks, MF * sizeof(int)));
     CK(e, cudaMallocHost((void **)&s.h_flush_peaks, MF * MP * sizeof(sdr_peak)));
     CK(e, cudaMallocHost((void **)&s.h_flush_cum, MF * N * sizeof(float)));
+    if (e->large) {  // the large-block path always materialises spectrum / psd / the four-step intermediate
+        CK(e, cudaMalloc((void **)&s.d_tmp, MB * N * sizeof(float2)));
+        CK(e, cudaMalloc((void **)&s.d_spectrum, MB * N * sizeof(float)));
+        CK(e, cudaMalloc((void **)&s.d_psd, MB * N * sizeof(float)));
+    }
     CK(e, cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
     CK(e, cudaEventCreate(&s.ev_k0));
     CK(e, cudaEventCreate(&s.ev_km));
@@ -321,8 +400,10 @@ const char *sdr_last_error(const sdr_engine *e) { return e ? e->err.c_str() : g_
 int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
     if (!cfg || !out) return SDR_EINVAL;
     *out = nullptr;
-    if (!supported_fused_n(cfg->block_size)) {
-        g_create_error = "block_size must be 512, 1024, 2048 or 4096 for the fused path";
+    LargeGeom lgeom{};
+    const bool is_large = large_geom(cfg->block_size, &lgeom);
+    if (!supported_fused_n(cfg->block_size) && !is_large) {
+        g_create_error = "block_size must be 512..4096 (fused path) or 8192..65536 (large-block path), a power of two";
         return SDR_EINVAL;
     }
     if (cfg->max_streams < 1 || cfg->max_blocks_per_batch < 1 || cfg->n_slots < 1 || cfg->max_listeners < 0 ||
@@ -334,6 +415,8 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
     if (!e) return SDR_ENOMEM;
     e->cfg = *cfg;
     e->N = cfg->block_size;
+    e->large = is_large;
+    e->lg = lgeom;
     e->tap_stride = ((cfg->max_listeners > 0 ? cfg->max_listeners : 1) + 3) / 4 * 4;
     e->max_segs = cfg->max_blocks_per_batch / SDR_CUMULATION_SIZE + 2 * cfg->max_streams + 2;
     e->max_flushes = cfg->max_blocks_per_batch / SDR_CUMULATION_SIZE + cfg->max_streams + 1;
@@ -367,12 +450,29 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
         CKC(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
         CKC(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
     }
-    std::vector<float2> tw1, tw2;
-    build_twiddles(e->N, tw1, tw2);
-    CKC(cudaMalloc((void **)&e->d_tw1, tw1.size() * sizeof(float2)));
-    CKC(cudaMalloc((void **)&e->d_tw2, tw2.size() * sizeof(float2)));
-    CKC(cudaMemcpy(e->d_tw1, tw1.data(), tw1.size() * sizeof(float2), cudaMemcpyHostToDevice));
-    CKC(cudaMemcpy(e->d_tw2, tw2.data(), tw2.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    if (!e->large) {
+        std::vector<float2> tw1, tw2;
+        build_twiddles(e->N, tw1, tw2);
+        CKC(cudaMalloc((void **)&e->d_tw1, tw1.size() * sizeof(float2)));
+        CKC(cudaMalloc((void **)&e->d_tw2, tw2.size() * sizeof(float2)));
+        CKC(cudaMemcpy(e->d_tw1, tw1.data(), tw1.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        CKC(cudaMemcpy(e->d_tw2, tw2.data(), tw2.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    } else {
+        auto table = [&](int len, float2 **dst) -> cudaError_t {
+            std::vector<float2> t(len);
+            const double two_pi = 6.283185307179586476925286766559;
+            for (int m = 0; m < len; m++) {
+                const double ang = -two_pi * (double)m / (double)len;
+                t[m] = make_float2((float)cos(ang), (float)sin(ang));
+            }
+            cudaError_t st = cudaMalloc((void **)dst, (size_t)len * sizeof(float2));
+            if (st != cudaSuccess) return st;
+            return cudaMemcpy(*dst, t.data(), (size_t)len * sizeof(float2), cudaMemcpyHostToDevice);
+        };
+        CKC(table(e->lg.n1, &e->d_tw_sub1));
+        CKC(table(e->lg.n2, &e->d_tw_sub2));
+        CKC(table(e->N, &e->d_tw_n));
+    }
     if (cfg->window) {
         CKC(cudaMalloc((void **)&e->d_window, (size_t)e->N * sizeof(float)));
         CKC(cudaMemcpy(e->d_window, cfg->window, (size_t)e->N * sizeof(float), cudaMemcpyHostToDevice));
@@ -387,7 +487,7 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
         const char *v = getenv("SDR_K1_TW2R");  // experiment switch; default: pass-2 twiddles in registers
         e->k1_tw2r = !(v && v[0] == '0');
     }
-    e->k1_grid_cap = k1_grid_cap_for(e->N, e->d_window != nullptr, e->k1_tw2r, e->sm_count);
+    if (!e->large) e->k1_grid_cap = k1_grid_cap_for(e->N, e->d_window != nullptr, e->k1_tw2r, e->sm_count);
     CKC(cudaGetLastError());
     e->slots.resize(cfg->n_slots);
     for (auto &s : e->slots) {
@@ -407,6 +507,9 @@ void sdr_engine_destroy(sdr_engine *e) {
     for (auto &s : e->slots) free_slot(s);
     cudaFree(e->d_tw1);
     cudaFree(e->d_tw2);
+    cudaFree(e->d_tw_sub1);
+    cudaFree(e->d_tw_sub2);
+    cudaFree(e->d_tw_n);
     cudaFree(e->d_window);
     cudaFree(e->d_cum_state);
     cudaFree(e->d_rolling);
@@ -534,10 +637,12 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     }
     Slot &s = *sp;
     const bool dbg = (flags & SDR_WANT_SPECTRUM) != 0;
-    if (dbg && !s.d_spectrum) {
+    if (dbg && !s.h_spectrum) {
         const size_t bytes = (size_t)e->cfg.max_blocks_per_batch * N * sizeof(float);
-        CK(e, cudaMalloc((void **)&s.d_spectrum, bytes));
-        CK(e, cudaMalloc((void **)&s.d_psd, bytes));
+        if (!s.d_spectrum) {
+            CK(e, cudaMalloc((void **)&s.d_spectrum, bytes));
+            CK(e, cudaMalloc((void **)&s.d_psd, bytes));
+        }
         CK(e, cudaMallocHost((void **)&s.h_spectrum, bytes));
         CK(e, cudaMallocHost((void **)&s.h_psd, bytes));
     }
@@ -588,6 +693,10 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
                 e->err = "internal: descriptor capacity exceeded";
                 return SDR_ESTATE;
             }
+            if (e->large) {
+                int *bs = reinterpret_cast<int *>(s.h_desc + dl.block_seg);
+                for (int b = 0; b < take; b++) bs[block_off + pos + b] = n_segs;
+            }
             Segment &sg = segs[n_segs++];
             sg.iq = dev_iq + (size_t)pos * 2 * N;
             sg.n_blocks = take;
@@ -636,7 +745,13 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     a1.dbg_spectrum = s.d_spectrum;
     a1.dbg_psd = s.d_psd;
     CK(e, cudaEventRecord(s.ev_k0, e->s_compute));
-    CK(e, launch_k1(e, a1, dbg, e->s_compute));
+    int k1_launches = 1;
+    if (!e->large) {
+        CK(e, launch_k1(e, a1, dbg, e->s_compute));
+    } else {
+        CK(e, launch_large(e, a1, s.d_tmp, reinterpret_cast<const int *>(s.d_desc + dl.block_seg), block_off, n_segs, e->s_compute));
+        k1_launches = 4;
+    }
     CK(e, cudaEventRecord(s.ev_km, e->s_compute));
     K2Args a2;
     a2.works = reinterpret_cast<const PostWork *>(s.d_desc + dl.post);
@@ -656,8 +771,8 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     k2_post_kernel<<<n_works, K2_THREADS, 0, e->s_compute>>>(a2);
     CK(e, cudaGetLastError());
     CK(e, cudaEventRecord(s.ev_k1, e->s_compute));
-    s.launches = 2;
-    e->launches += 2;
+    s.launches = k1_launches + 1;
+    e->launches += k1_launches + 1;
 
     // ---- D2H ----
     if (!(flags & SDR_NO_D2H)) {
@@ -778,8 +893,9 @@ int sdr_dsp_iq_to_spectrum_and_psd(sdr_engine *e, const float *iq, int n_blocks,
     const size_t out_bytes = (size_t)n_blocks * N * sizeof(float);
     const size_t seg_bytes = align_up(sizeof(Segment) * (size_t)n_blocks, 256);
     const size_t misc = 4096;
+    const size_t large_bytes = e->large ? align_up(iq_bytes, 256) + align_up((size_t)n_blocks * sizeof(int), 256) : 0;
     size_t need = align_up(iq_bytes, 256) + 2 * align_up(out_bytes, 256) + seg_bytes + misc +
-                  align_up((size_t)n_blocks * 16, 256) * 2 + align_up((size_t)N * sizeof(float), 256);
+                  align_up((size_t)n_blocks * 16, 256) * 2 + align_up((size_t)N * sizeof(float), 256) + large_bytes;
     int rc = ensure_scratch(e, need);
     if (rc != SDR_OK) return rc;
     unsigned char *p = reinterpret_cast<unsigned char *>(e->d_scratch);
@@ -800,6 +916,10 @@ int sdr_dsp_iq_to_spectrum_and_psd(sdr_engine *e, const float *iq, int n_blocks,
     float *d_taps = reinterpret_cast<float *>(p);
     p += 256;
     float *d_cum = reinterpret_cast<float *>(p);
+    p += align_up((size_t)N * sizeof(float), 256);
+    float2 *d_tmp = reinterpret_cast<float2 *>(p);  // large-block path only
+    p += e->large ? align_up(iq_bytes, 256) : 0;
+    int *d_block_seg = reinterpret_cast<int *>(p);
     std::vector<Segment> segs(n_blocks);
     for (int b = 0; b < n_blocks; b++) {
         Segment &sg = segs[b];
@@ -836,8 +956,17 @@ int sdr_dsp_iq_to_spectrum_and_psd(sdr_engine *e, const float *iq, int n_blocks,
     a.flush_cum = d_cum;
     a.dbg_spectrum = d_spec;
     a.dbg_psd = d_psd;
-    CK(e, launch_k1(e, a, true, e->s_compute));
-    e->launches += 1;
+    if (!e->large) {
+        CK(e, launch_k1(e, a, true, e->s_compute));
+        e->launches += 1;
+    } else {
+        std::vector<int> bs(n_blocks);
+        for (int b = 0; b < n_blocks; b++) bs[b] = b;
+        CK(e, cudaMemcpyAsync(d_block_seg, bs.data(), sizeof(int) * (size_t)n_blocks, cudaMemcpyHostToDevice, e->s_compute));
+        CK(e, cudaStreamSynchronize(e->s_compute));  // bs is a stack-lifetime buffer
+        CK(e, launch_large(e, a, d_tmp, d_block_seg, n_blocks, n_blocks, e->s_compute));
+        e->launches += 4;
+    }
     CK(e, cudaMemcpyAsync(spectrum, d_spec, out_bytes, cudaMemcpyDeviceToHost, e->s_compute));
     CK(e, cudaMemcpyAsync(psd, d_psd, out_bytes, cudaMemcpyDeviceToHost, e->s_compute));
     CK(e, cudaStreamSynchronize(e->s_compute));

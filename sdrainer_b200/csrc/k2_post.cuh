@@ -64,7 +64,7 @@ __device__ __forceinline__ float psd_value_in_db_shifted(float psd_value, double
     return __fadd_rn(db, (float)SDR_DBM_SHIFT);
 }
 
-constexpr int K2_THREADS = 256;
+constexpr int K2_THREADS = 64;   // one CTA per work; small CTAs so that ~2000 works fit in one wave (latency-bound kernel)
 constexpr int K2_CHUNK = 1024;  // blocks staged in shared memory per sequential pass
 
 // dsp.FindPeaks on one vector `cum` of n bins; all K2_THREADS threads of the CTA participate.

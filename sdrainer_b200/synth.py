@@ -113,8 +113,12 @@ def generate(spec: StreamSpec) -> np.ndarray:
     z[:] = rng.standard_normal((total, 2), dtype=np.float32) * np.float32(spec.noise_sigma)
     sig = np.zeros(total, dtype=np.complex128)
     nidx = np.arange(n, dtype=np.float64)
+    steady = np.zeros(n, dtype=np.complex128)  # unkeyed on-bin carriers repeat identically in every block
     for tn in spec.tones:
         k = tn.bin - n // 2  # baseband bin
+        if tn.bin_offset == 0.0 and not tn.keyed:
+            steady += tn.amplitude * np.exp(2j * np.pi * (k * nidx / n) + 1j * tn.phase)
+            continue
         if tn.bin_offset == 0.0:
             one = np.exp(2j * np.pi * (k * nidx / n) + 1j * tn.phase)  # identical in every block
             carrier = np.tile(one, spec.n_blocks)
@@ -125,6 +129,8 @@ def generate(spec: StreamSpec) -> np.ndarray:
         if tn.keyed:
             carrier = carrier * keying(tn.text, tn.wpm, fs, total, tn.start_s)
         sig += tn.amplitude * carrier
+    if steady.any():
+        sig += np.tile(steady, spec.n_blocks)
     z[:, 0] += sig.real.astype(np.float32)
     z[:, 1] += sig.imag.astype(np.float32)
     return z.reshape(-1)

@@ -316,3 +316,67 @@ def test_parseval_and_linearity_at_bench_size(capi):
     energy = (iq.astype(np.float64) ** 2).reshape(nb, -1).sum(axis=1)
     assert np.abs(psd.astype(np.float64).sum(axis=1) / (n * energy) - 1).max() < 1e-5
     assert np.array_equal(psd4, psd * np.float32(16.0))  # power-of-two scaling is exact in fp32
+
+
+@pytest.mark.parametrize("n", [8192, 65536])
+def test_large_block_path_spectrum_parity(capi, oracle, n):
+    """configs 3 and 5: N = 8192 / 65536 through the four-step large-block path (k1_large.cuh)"""
+    nb = 4 if n == 8192 else 2
+    spec = _spec(n, int(93.75 * n) if n == 8192 else 24576000, nb, seed=n, k=40, keyed=False)
+    iq = synth.generate(spec)
+    with capi.Engine(n, max_blocks_per_batch=8, max_listeners=8) as eng:
+        s_gpu, p_gpu = eng.iq_to_spectrum_and_psd(iq)
+    r = oracle.process_stream(iq, n, want_spectrum=True)
+    m = pu.check_spectrum(s_gpu, p_gpu, r.spectrum, r.psd)
+    assert m["n_signal_bins"] >= 40
+    print(n, m)
+
+
+def test_cfg3_shape_8192_with_200_listeners(capi, oracle):
+    """config 3: 768 kS/s, N=8192, ~200 listeners force-attached at the tone bins, two cumulation windows"""
+    n, fs = 8192, 768000
+    rng = np.random.default_rng(33)
+    tones = synth.make_tones(rng, 200, n, 70, wpm_range=(15.0, 30.0))
+    spec = synth.StreamSpec(sample_rate=fs, block_size=n, n_blocks=205, seed=33, tones=tones)
+    iq = synth.generate(spec)
+    bins = [t.bin for t in tones]
+    with capi.Engine(n, max_streams=1, max_listeners=200, max_blocks_per_batch=128, max_peaks_per_flush=1024) as eng:
+        s = eng.open_stream(fs)
+        outs = []
+        for lo, hi in ((0, 128), (128, 205)):
+            t = eng.submit([dict(stream=s, iq=np.ascontiguousarray(iq[lo * 2 * n:hi * 2 * n]), listener_bins=bins)],
+                           capi.WANT_FLUSH_CUM)
+            outs.append(eng.collect(t))
+    r = oracle.process_stream(iq, n, listener_bins=bins, sample_rate=fs)
+    floor = _concat(outs, "psd_noise_floor")
+    thr = _concat(outs, "thresholds")
+    keys = _concat(outs, "keys")[:, :len(bins)]
+    pu.check_scalars(floor, r.noise[:, 0], what="psdNoiseFloor")
+    assert np.abs(thr[:, :3] - r.thresholds).max() < 2e-3
+    pu.check_keys(keys, r.taps, r.thresholds[:, 0] + r.thresholds[:, 1])
+    gp = [pu.peak_keys(o.peaks(f)) for o in outs for f in range(o.n_flushes)]
+    assert len(gp) == r.n_flush == 2
+    for f in range(2):
+        pu.check_peaks(gp[f], [p.key() for p in r.peaks[f]], r.flush_cum[f], r.thresholds[100 * (f + 1) - 1, 2])
+    # with 200 signals every noise window holds several of them, so the reference's floor/threshold sit above
+    # the averaged tone levels and FindPeaks reports little or nothing -- identically on both sides (checked above)
+
+
+def test_cfg5_shape_65536_peak_scan(capi, oracle):
+    """config 5: 24.576 MS/s wideband, N=65536, ~500 carriers, peak scan only (no listeners)"""
+    n, fs = 65536, 24576000
+    rng = np.random.default_rng(55)
+    tones = synth.make_tones(rng, 500, n, 70, keyed=False, min_spacing=12)
+    spec = synth.StreamSpec(sample_rate=fs, block_size=n, n_blocks=100, seed=55, tones=tones)
+    iq = synth.generate(spec)
+    with capi.Engine(n, max_streams=1, max_listeners=4, max_blocks_per_batch=100, max_peaks_per_flush=2048) as eng:
+        s = eng.open_stream(fs)
+        res = eng.collect(eng.submit([dict(stream=s, iq=iq)], capi.WANT_FLUSH_CUM))
+    r = oracle.process_stream(iq, n, sample_rate=fs)
+    pu.check_scalars(res.psd_noise_floor, r.noise[:, 0], what="psdNoiseFloor")
+    assert res.n_flushes == 1
+    pu.check_peaks(pu.peak_keys(res.peaks(0)), [p.key() for p in r.peaks[0]], r.flush_cum[0], r.thresholds[99, 2])
+    # with 500 carriers every noise window contains carriers, so the reference's floor estimate (and with it
+    # the threshold) sits far above the true noise: only the strongest carriers are reported -- by both sides
+    found = {int(p["signal_bin"]) for p in res.peaks(0)}
+    assert len(found) >= 20 and found <= {t.bin for t in tones}
