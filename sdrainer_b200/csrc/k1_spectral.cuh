@@ -399,16 +399,21 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS, 4) k1_spectral_kernel(
         }
         group_sync<T, G>(g);  // LB visible
         int nf_fill = 0, nf_first = sg.block_out;  // warp 0: batched noise-floor selection
-        float x_to = 0.f;                          // warp 0: psd[first bin of the next window], carried to phase 2
-
-        // noise floor, phase 2 (warp 0 only): lanes 3w..3w+2 add the TPW partial sums of window w, lane 3w keeps
-        // the result for a batched selection: every NFB blocks lane l runs dsp.FindNoiseFloor's sequential
-        // selection (dsp/fft.go:217-251) for block l of the batch.
-        auto nf_phase2 = [&](bool last) {
-            const int w = t / 3, j = t - 3 * w;
+        // noise floor, phase 2, spread over all warps: warp q owns windows q, q+NW, q+2NW, ...; its lanes
+        // 3*slot .. 3*slot+2 add the TPW partial sums of window w = q + NW*slot and lane 3*slot keeps the result
+        // (and x_to = psd[first bin of the next window], read while PSD is still alive) for a batched selection:
+        // every NFB blocks lane l of warp 0 runs dsp.FindNoiseFloor's sequential selection (dsp/fft.go:217-251)
+        // for block l of the batch.
+        constexpr int NW = T / 32;
+        constexpr int NF_SLOTS = (10 + NW - 1) / NW;
+        const int nf_slot = (t & 31) / 3, nf_j = (t & 31) - 3 * nf_slot;
+        const int nf_w = (t >> 5) + NW * nf_slot;
+        const bool nf_owner = nf_slot < NF_SLOTS && nf_w < n_win;
+        float x_to = 0.f;
+        auto nf_phase2 = [&]() {
             float s1 = 0.f, s2 = 0.f;
-            if (w < 10) {
-                const float2 *pp = PART + w * TPW + j;
+            if (nf_owner) {
+                const float2 *pp = PART + nf_w * TPW + nf_j;
 #pragma unroll
                 for (int m = 0; m < TPW / 3; m++) {
                     const float2 pr = pp[3 * m];
@@ -418,20 +423,18 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS, 4) k1_spectral_kernel(
             }
             s1 += __shfl_down_sync(0xffffffffu, s1, 1) + __shfl_down_sync(0xffffffffu, s1, 2);
             s2 += __shfl_down_sync(0xffffffffu, s2, 1) + __shfl_down_sync(0xffffffffu, s2, 2);
-            if (j == 0 && w < n_win) {
-                NFS1[nf_fill * 10 + w] = (double)s1;
-                NFS2[nf_fill * 10 + w] = (double)s2;
-                NFX[nf_fill * 10 + w] = x_to;
+            if (nf_owner && nf_j == 0) {
+                NFS1[nf_fill * 10 + nf_w] = (double)s1;
+                NFS2[nf_fill * 10 + nf_w] = (double)s2;
+                NFX[nf_fill * 10 + nf_w] = x_to;
             }
             nf_fill++;
-            if (nf_fill == Gm::NFB || last) {
-                __syncwarp();
-                if (t < nf_fill) nf_select_serial(NFS1 + t * 10, NFS2 + t * 10, NFX + t * 10, 1, ws, n_win,
-                                                  &a.psd_floor[nf_first + t], &a.variance[nf_first + t]);
-                __syncwarp();
-                nf_first += nf_fill;
-                nf_fill = 0;
-            }
+        };
+        auto nf_select = [&]() {  // after a group barrier that follows nf_phase2; counters stay uniform in the group
+            if (t < nf_fill) nf_select_serial(NFS1 + t * 10, NFS2 + t * 10, NFX + t * 10, 1, ws, n_win,
+                                              &a.psd_floor[nf_first + t], &a.variance[nf_first + t]);
+            nf_first += nf_fill;
+            nf_fill = 0;
         };
 
         for (int blk = 0; blk < sg.n_blocks; blk++, item++) {
@@ -464,7 +467,7 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS, 4) k1_spectral_kernel(
 #pragma unroll
             for (int p = 0; p < 16; p++) E1[OutIdx<16>::of(p) * S1 + t] = v[p];
             group_sync<T, G>(g);  // B1: E1 complete, IN consumed
-            if (blk > 0 && t < 32) nf_phase2(false);  // previous block; PART is rewritten only after B3
+            if (blk > 0) nf_phase2();  // previous block's window sums; PART is rewritten only after B3
 
             // ---------------- pass 2: radix-16 over n2 for (k1, n3) ----------------
 #pragma unroll
@@ -481,6 +484,7 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS, 4) k1_spectral_kernel(
                 E2[n3_p2 * S2 + k1_p2 + 16 * k2] = x;
             }
             group_sync<T, G>(g);  // B2: E2 complete, E1 dead
+            if (nf_fill == Gm::NFB) nf_select();  // all warps' NFS stores of the batch happened before B2
 
             // ---------------- pass 3: radix-R3 over n3 for pairs c = t + i*T ----------------
 #pragma unroll
@@ -546,12 +550,15 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS, 4) k1_spectral_kernel(
             }
             // x_to = psd[first bin of the next window] is read here (PSD is gone after the next B4);
             // lane 3w of warp 0 owns window w in phase 2
-            if (t < 32 && (t % 3) == 0 && t / 3 < n_win) x_to = PSD[e + (t / 3 + 1) * ws];
-            // listener taps (rx/receiver.go:393): same dB function as the owner thread
-            for (int l = t; l < L; l += T) a.taps[(size_t)ob * a.tap_stride + l] = psd_to_db<N>(PSD[LB[l]]);
+            if (nf_owner && nf_j == 0) x_to = PSD[e + (nf_w + 1) * ws];
+            // listener taps (rx/receiver.go:393): same dB function as the owner thread; served from the last
+            // threads of the group so that warp 0 (TMA issue) is not the straggler
+            for (int l = T - 1 - t; l < L; l += T) a.taps[(size_t)ob * a.tap_stride + l] = psd_to_db<N>(PSD[LB[l]]);
         }
         group_sync<T, G>(g);  // B4 of the last block
-        if (t < 32) nf_phase2(true);
+        nf_phase2();
+        group_sync<T, G>(g);
+        nf_select();
 
         // ---- end of segment: flush or save the cumulation ----
         float *dst = (sg.flush_idx >= 0) ? a.flush_cum + (size_t)sg.flush_idx * N : a.cum_state + (size_t)sg.stream * N;

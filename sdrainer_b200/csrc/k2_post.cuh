@@ -64,7 +64,7 @@ __device__ __forceinline__ float psd_value_in_db_shifted(float psd_value, double
     return __fadd_rn(db, (float)SDR_DBM_SHIFT);
 }
 
-constexpr int K2_THREADS = 64;   // one CTA per work; small CTAs so that ~2000 works fit in one wave (latency-bound kernel)
+constexpr int K2_THREADS = 128;  // one CTA per work; ~2000 works fit in one wave of 148 x 12 CTAs (latency-bound kernel)
 constexpr int K2_CHUNK = 1024;  // blocks staged in shared memory per sequential pass
 
 // dsp.FindPeaks on one vector `cum` of n bins; all K2_THREADS threads of the CTA participate.
@@ -74,21 +74,31 @@ __device__ void find_peaks_block(const float *__restrict__ cum, int n, float cum
     const int per = (n + K2_THREADS - 1) / K2_THREADS;
     const int lo = tid * per, hi = min(n, lo + per);
     auto val = [&](int i) { return __fdiv_rn(cum[i], cumulation_size); };  // v / T(cumulationSize)
-    // a run starts at i when value > threshold and no run is open; a run stays open until the
-    // first value <= threshold (a NaN neither opens nor closes a run, as in the Go if/else chain)
-    auto starts_at = [&](int i) -> bool {
-        if (!(val(i) > thr)) return false;
-        int j = i - 1;
-        while (j >= 0) {
-            const float p = val(j);
-            if (p > thr) return false;   // previous bin is inside an open run
-            if (p <= thr) return true;   // previous bin closed any run
-            j--;                         // NaN: look further back
+    // The Go loop is a two-state machine: a run opens at value > threshold while closed, and closes at the first
+    // value <= threshold (a NaN neither opens nor closes a run).  Each thread replays it over its chunk; the
+    // state at the chunk start is found by looking back (past NaNs) at the last decisive bin.
+    bool open0 = false;
+    for (int j = lo - 1; j >= 0 && lo < hi; j--) {
+        const float p = val(j);
+        if (p > thr) {
+            open0 = true;
+            break;
         }
-        return true;
-    };
+        if (p <= thr) break;
+    }
     int count = 0;
-    for (int i = lo; i < hi; i++) count += starts_at(i) ? 1 : 0;
+    {
+        bool open = open0;
+        for (int i = lo; i < hi; i++) {
+            const float v = val(i);
+            if (!open && v > thr) {
+                count++;
+                open = true;
+            } else if (open && v <= thr) {
+                open = false;
+            }
+        }
+    }
     // block-wide exclusive scan of `count`
     s_scan[tid] = count;
     __syncthreads();
@@ -100,33 +110,42 @@ __device__ void find_peaks_block(const float *__restrict__ cum, int n, float cum
     }
     int slot = s_scan[tid] - count;
     if (tid == K2_THREADS - 1) *n_out = s_scan[tid];
-    for (int i = lo; i < hi; i++) {
-        if (!starts_at(i)) continue;
-        int from = i, bin = i;
-        float best = val(i);
-        int j = i + 1;
-        while (j < n) {
-            const float v = val(j);
-            if (v <= thr) break;
-            if (best < v) {  // strict: the first maximum wins
-                best = v;
-                bin = j;
+    if (count > 0) {
+        bool open = open0;
+        for (int i = lo; i < hi; i++) {
+            const float v0 = val(i);
+            if (open) {
+                if (v0 <= thr) open = false;
+                continue;
             }
-            j++;
+            if (!(v0 > thr)) continue;
+            open = true;
+            int bin = i;
+            float best = v0;
+            int j = i + 1;
+            while (j < n) {  // the run may extend past this thread's chunk
+                const float v = val(j);
+                if (v <= thr) break;
+                if (best < v) {  // strict: the first maximum wins
+                    best = v;
+                    bin = j;
+                }
+                j++;
+            }
+            if (slot < max_peaks) {
+                sdr_peak p;
+                p.from = i;
+                p.to = j - 1;
+                p.signal_bin = bin;
+                p.signal_value = best;
+                const bool inner = bin > 0 && bin < n - 1;
+                p.y1 = inner ? cum[bin - 1] : 0.f;
+                p.y2 = cum[bin];
+                p.y3 = inner ? cum[bin + 1] : 0.f;
+                out[slot] = p;
+            }
+            slot++;
         }
-        if (slot < max_peaks) {
-            sdr_peak p;
-            p.from = from;
-            p.to = j - 1;
-            p.signal_bin = bin;
-            p.signal_value = best;
-            const bool inner = bin > 0 && bin < n - 1;
-            p.y1 = inner ? cum[bin - 1] : 0.f;
-            p.y2 = cum[bin];
-            p.y3 = inner ? cum[bin + 1] : 0.f;
-            out[slot] = p;
-        }
-        slot++;
     }
     __syncthreads();
 }
@@ -140,7 +159,11 @@ __global__ void __launch_bounds__(K2_THREADS) k2_post_kernel(const K2Args a) {
     const int tid = threadIdx.x;
     const double n2 = (double)a.n * (double)a.n;
 
-    if (tid == 0) s_roll = a.rolling[w.stream];
+    {  // all threads copy the stream's rolling state (124 words) instead of one thread walking it
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(a.rolling + w.stream);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&s_roll);
+        for (int i = tid; i < (int)(sizeof(RollingState) / 4); i += K2_THREADS) dst[i] = src[i];
+    }
     __syncthreads();
 
     for (int c0 = 0; c0 < w.n_blocks; c0 += K2_CHUNK) {
@@ -189,17 +212,37 @@ __global__ void __launch_bounds__(K2_THREADS) k2_post_kernel(const K2Args a) {
             reinterpret_cast<float4 *>(a.thresholds)[b] = th;
         }
         __syncthreads();
-        // key states (cw/spectral.go:49) for this chunk
+        // key states (cw/spectral.go:49) for this chunk: the listen threshold of block i is kept in s_floor[i]
+        for (int i = tid; i < cn; i += K2_THREADS)
+            s_floor[i] = __fadd_rn(__fdiv_rn(s_floor[i], (float)SDR_NOISE_WINDOW), __fdiv_rn(s_dev[i], (float)SDR_NOISE_WINDOW));
+        __syncthreads();
         const int L = w.n_listeners;
-        for (int idx = tid; idx < cn * L; idx += K2_THREADS) {
-            const int i = idx / L, l = idx % L;
-            const int b = w.block_out + c0 + i;
-            const float listen = a.thresholds[(size_t)b * 4 + 3];
-            a.keys[(size_t)b * a.tap_stride + l] = a.taps[(size_t)b * a.tap_stride + l] > listen ? 1 : 0;
+        const int total = cn * L;
+        const float *__restrict__ taps = a.taps + (size_t)(w.block_out + c0) * a.tap_stride;
+        uint8_t *__restrict__ keys = a.keys + (size_t)(w.block_out + c0) * a.tap_stride;
+        for (int base = 0; base < total; base += 4 * K2_THREADS) {
+            float v[4], th[4];
+            int off[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {  // four independent global loads in flight per thread
+                const int idx = base + u * K2_THREADS + tid;
+                const int i = idx < total ? idx / L : 0, l = idx < total ? idx - (idx / L) * L : 0;
+                off[u] = idx < total ? i * a.tap_stride + l : -1;
+                th[u] = s_floor[i];
+                v[u] = off[u] >= 0 ? taps[off[u]] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (off[u] >= 0) keys[off[u]] = v[u] > th[u] ? 1 : 0;
         }
         __syncthreads();
     }
-    if (tid == 0) a.rolling[w.stream] = s_roll;
+    __syncthreads();
+    {
+        uint32_t *dst = reinterpret_cast<uint32_t *>(a.rolling + w.stream);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(&s_roll);
+        for (int i = tid; i < (int)(sizeof(RollingState) / 4); i += K2_THREADS) dst[i] = src[i];
+    }
 
     // flushes of this work (rx/receiver.go:409-425)
     for (int f = 0; f < w.n_flushes; f++) {
