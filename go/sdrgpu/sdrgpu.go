@@ -100,6 +100,7 @@ func (e *Engine) Submit(works []Work, flags int) (Ticket, error) {
 		cw[i].n_blocks = C.int(len(w.IQ) / (2 * e.blockSize))
 		cw[i].iq = (*C.float)(unsafe.Pointer(&w.IQ[0]))
 		cw[i].mem = C.SDR_MEM_HOST
+		cw[i].format = C.SDR_FMT_F32
 		cw[i].edge_width = C.int(w.EdgeWidth)
 		cw[i].peak_threshold = C.float(w.PeakThreshold)
 		cw[i].n_listeners = C.int(len(w.ListenerBins))

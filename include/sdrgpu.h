@@ -42,6 +42,11 @@ extern "C" {
 #define SDR_MEM_HOST 0
 #define SDR_MEM_DEVICE 1
 
+/* sdr_work.format: sample encoding of `iq` */
+#define SDR_FMT_F32 0        /* interleaved float32 I,Q (tci/tci.go:264; kiwi after decodeIQBytes) */
+#define SDR_FMT_KIWI_I16BE 1 /* KiwiSDR wire format: interleaved big-endian int16 I,Q; the division by 32767
+                                of kiwi/client.go:298-308 is fused into the kernel's load (4 bytes per sample) */
+
 /* sdr_submit flags */
 #define SDR_WANT_FLUSH_CUM 0x1   /* copy each flushed cumulation vector back (scope feed, rx/receiver.go:428-457) */
 #define SDR_WANT_SPECTRUM 0x2    /* debug/parity: also store spectrum[] and psd[] per block (dsp/fft.go:23 outputs) */
@@ -78,6 +83,7 @@ typedef struct {
     float peak_threshold;     /* rx.Receiver.peakThreshold (default 15 dB, :24) */
     int n_listeners;          /* attached listeners */
     const int *listener_bins; /* Listener.SignalBin() of each (rx/listener.go:119-124); host memory */
+    int format;               /* SDR_FMT_F32 (default 0) or SDR_FMT_KIWI_I16BE; one format per submit */
 } sdr_work;
 
 /* dsp.Peak as found by dsp.FindPeaks (dsp/fft.go:254-285), before the host's frequency mapping.
@@ -158,6 +164,10 @@ int sdr_dsp_find_noise_floor(sdr_engine *e, const float *psd, int edge_width, fl
 /* dsp.FindPeaks (dsp/fft.go:254-285) on a host cumulation vector of length N; returns count in *n_peaks */
 int sdr_dsp_find_peaks(sdr_engine *e, const float *cumulation, int cumulation_size, float threshold,
                        sdr_peak *peaks, int max_peaks, int *n_peaks);
+
+/* kiwi.decodeIQBytes (kiwi/client.go:298-308) on the GPU: n_bytes/2 big-endian int16 -> float32 / 32767, bit-exact
+ * (the same conversion the fused SDR_FMT_KIWI_I16BE load performs).  Host pointers. */
+int sdr_kiwi_decode_iq_bytes(sdr_engine *e, const unsigned char *bytes, int n_bytes, float *out);
 
 /* ---- Goertzel / envelope bank (dsp.Goertzel, dsp/dsp.go:34-136; cw/audio.go:184-195) --------- */
 typedef struct sdr_goertzel_bank sdr_goertzel_bank;

@@ -10,6 +10,7 @@ from . import _build
 
 OK, EINVAL, ECUDA, ENOMEM, EBUSY, ENOTREADY, ESTATE = 0, -1, -2, -3, -4, -5, -6
 MEM_HOST, MEM_DEVICE = 0, 1
+FMT_F32, FMT_KIWI_I16BE = 0, 1
 WANT_FLUSH_CUM, WANT_SPECTRUM, NO_PEAKS, NO_D2H, NO_TAPS = 1, 2, 4, 8, 16
 CUMULATION_SIZE = 100
 
@@ -28,7 +29,7 @@ class EngineConfig(C.Structure):
 class Work(C.Structure):
     _fields_ = [("stream", C.c_int), ("n_blocks", C.c_int), ("iq", C.c_void_p), ("mem", C.c_int),
                 ("edge_width", C.c_int), ("peak_threshold", C.c_float), ("n_listeners", C.c_int),
-                ("listener_bins", _i32p)]
+                ("listener_bins", _i32p), ("format", C.c_int)]
 
 
 class Peak(C.Structure):
@@ -64,7 +65,7 @@ SYMBOLS = [
     "sdr_alloc_pinned", "sdr_free_pinned", "sdr_stream_open", "sdr_stream_close", "sdr_stream_reset",
     "sdr_stream_cumulation_count", "sdr_submit", "sdr_collect", "sdr_release", "sdr_ticket_device_ptrs",
     "sdr_engine_launch_count", "sdr_dsp_iq_to_spectrum_and_psd", "sdr_dsp_find_noise_floor",
-    "sdr_dsp_find_peaks", "sdr_goertzel_create", "sdr_goertzel_destroy", "sdr_goertzel_last_error",
+    "sdr_dsp_find_peaks", "sdr_kiwi_decode_iq_bytes", "sdr_goertzel_create", "sdr_goertzel_destroy", "sdr_goertzel_last_error",
     "sdr_goertzel_blocksize", "sdr_goertzel_process_audio", "sdr_goertzel_process_iq",
 ]
 
@@ -113,6 +114,7 @@ def lib():
     L.sdr_dsp_iq_to_spectrum_and_psd.argtypes = [C.c_void_p, _f32p, C.c_int, _f32p, _f32p]
     L.sdr_dsp_find_noise_floor.argtypes = [C.c_void_p, _f32p, C.c_int, _f32p, _f64p]
     L.sdr_dsp_find_peaks.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_float, C.POINTER(Peak), C.c_int, _i32p]
+    L.sdr_kiwi_decode_iq_bytes.argtypes = [C.c_void_p, C.c_char_p, C.c_int, _f32p]
     L.sdr_goertzel_create.argtypes = [C.POINTER(GoertzelConfig), C.POINTER(C.c_void_p)]
     L.sdr_goertzel_destroy.argtypes = [C.c_void_p]
     L.sdr_goertzel_destroy.restype = None
@@ -244,12 +246,16 @@ class Engine:
         for i, w in enumerate(works):
             iq = w["iq"]
             arr[i].stream = w["stream"]
+            fmt = w.get("format", FMT_F32)
+            arr[i].format = fmt
             if isinstance(iq, np.ndarray):
-                if iq.dtype != np.float32 or not iq.flags["C_CONTIGUOUS"]:
-                    raise SdrError(EINVAL, "iq must be contiguous float32")
+                want = np.float32 if fmt == FMT_F32 else np.uint8
+                if iq.dtype != want or not iq.flags["C_CONTIGUOUS"]:
+                    raise SdrError(EINVAL, "iq must be contiguous float32 (FMT_F32) or uint8 wire bytes (FMT_KIWI_I16BE)")
                 arr[i].iq = iq.ctypes.data
                 arr[i].mem = MEM_HOST
-                arr[i].n_blocks = w.get("n_blocks", iq.size // (2 * self.block_size))
+                per_block = 2 * self.block_size if fmt == FMT_F32 else 4 * self.block_size
+                arr[i].n_blocks = w.get("n_blocks", iq.size // per_block)
                 keep.append(iq)
             else:
                 arr[i].iq = int(iq)
@@ -327,6 +333,12 @@ class Engine:
         self._ck(self.L.sdr_dsp_find_peaks(self.h, cum.ctypes.data_as(_f32p), cumulation_size, C.c_float(threshold), arr,
                                            max_peaks, C.byref(n)))
         return [arr[i] for i in range(min(n.value, max_peaks))], n.value
+
+
+def kiwi_decode(engine: "Engine", raw: bytes) -> np.ndarray:
+    out = np.empty(len(raw) // 2, np.float32)
+    engine._ck(engine.L.sdr_kiwi_decode_iq_bytes(engine.h, raw, len(raw), out.ctypes.data_as(_f32p)))
+    return out
 
 
 class GoertzelBank:

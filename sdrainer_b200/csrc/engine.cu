@@ -139,7 +139,8 @@ DescLayout desc_layout(const sdr_engine *e) {
 }
 
 template <int N>
-const void *k1_fn(bool dbg, bool win, bool tw2r) {
+const void *k1_fn(bool dbg, bool win, bool tw2r, bool i16 = false) {
+    if (i16) return dbg ? (const void *)k1_spectral_kernel<N, true, false, true, true> : (const void *)k1_spectral_kernel<N, false, false, true, true>;
     if (tw2r) {
         if (dbg) return win ? (const void *)k1_spectral_kernel<N, true, true, true> : (const void *)k1_spectral_kernel<N, true, false, true>;
         return win ? (const void *)k1_spectral_kernel<N, false, true, true> : (const void *)k1_spectral_kernel<N, false, false, true>;
@@ -155,11 +156,14 @@ int k1_occupancy(bool dbg, bool win, bool tw2r) {
     const void *fn = k1_fn<N>(dbg, win, tw2r);
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, Gm::SMEM_BYTES);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, Gm::CTA_THREADS, Gm::SMEM_BYTES);
+    if (!win) {  // the KiwiSDR int16 variants exist for the unwindowed configuration only
+        cudaFuncSetAttribute(k1_fn<N>(dbg, false, true, true), cudaFuncAttributeMaxDynamicSharedMemorySize, Gm::SMEM_BYTES);
+    }
     return occ;
 }
 
 template <int N>
-cudaError_t launch_k1_n(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st) {
+cudaError_t launch_k1_n(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st, bool i16) {
     using Gm = K1Geom<N>;
     const bool win = a.window != nullptr;
     // every group walks the segment list with stride grid*G: pick the grid so that all groups get the
@@ -173,7 +177,7 @@ cudaError_t launch_k1_n(const sdr_engine *e, const K1Args &a, bool dbg, cudaStre
     if (grid < 1) grid = 1;
     K1Args args = a;
     void *params[] = {&args};
-    return cudaLaunchKernel(k1_fn<N>(dbg, win, e->k1_tw2r), dim3(grid), dim3(Gm::CTA_THREADS), params, Gm::SMEM_BYTES, st);
+    return cudaLaunchKernel(k1_fn<N>(dbg, win, e->k1_tw2r, i16), dim3(grid), dim3(Gm::CTA_THREADS), params, Gm::SMEM_BYTES, st);
 }
 
 template <int L, int STEP>
@@ -241,12 +245,12 @@ cudaError_t launch_large(const sdr_engine *e, const K1Args &a, float2 *d_tmp, co
     return cudaGetLastError();
 }
 
-cudaError_t launch_k1(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st) {
+cudaError_t launch_k1(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st, bool i16 = false) {
     switch (e->N) {
-        case 512: return launch_k1_n<512>(e, a, dbg, st);
-        case 1024: return launch_k1_n<1024>(e, a, dbg, st);
-        case 2048: return launch_k1_n<2048>(e, a, dbg, st);
-        case 4096: return launch_k1_n<4096>(e, a, dbg, st);
+        case 512: return launch_k1_n<512>(e, a, dbg, st, i16);
+        case 1024: return launch_k1_n<1024>(e, a, dbg, st, i16);
+        case 2048: return launch_k1_n<2048>(e, a, dbg, st, i16);
+        case 4096: return launch_k1_n<4096>(e, a, dbg, st, i16);
     }
     return cudaErrorInvalidValue;
 }
@@ -371,6 +375,11 @@ __global__ void __launch_bounds__(128) noise_floor_kernel(const float *psd, int 
         nf_select_variance(real ? wsum[lane] : 0.0, real ? wsum[16 + lane] : 0.0,
                            real ? (double)psd[e + (lane + 1) * ws] : 0.0, ws, n_win, lane, out_min, out_var);
     }
+}
+
+__global__ void kiwi_decode_kernel(const uint32_t *raw, int n_samples, float2 *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_samples) out[i] = kiwi_decode_sample(raw[i]);
 }
 
 int ensure_scratch(sdr_engine *e, size_t bytes) {
@@ -617,6 +626,14 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
                 e->err = "work " + std::to_string(w) + ": device iq must be 16-byte aligned";
                 return SDR_EINVAL;
             }
+            if (wk.format != works[0].format || (wk.format != SDR_FMT_F32 && wk.format != SDR_FMT_KIWI_I16BE)) {
+                e->err = "work " + std::to_string(w) + ": all works of one submit must share one valid sample format";
+                return SDR_EINVAL;
+            }
+            if (wk.format == SDR_FMT_KIWI_I16BE && (e->large || e->d_window)) {
+                e->err = "SDR_FMT_KIWI_I16BE is supported on the fused, unwindowed path (N <= 4096)";
+                return SDR_EINVAL;
+            }
             if (wk.mem != SDR_MEM_DEVICE) any_host = true;
             total_blocks += wk.n_blocks;
         }
@@ -637,6 +654,8 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     }
     Slot &s = *sp;
     const bool dbg = (flags & SDR_WANT_SPECTRUM) != 0;
+    const bool i16 = works[0].format == SDR_FMT_KIWI_I16BE;
+    const size_t sample_floats = i16 ? 1 : 2;  // a complex sample is 4 bytes on the Kiwi wire, 8 as float32 pairs
     if (dbg && !s.h_spectrum) {
         const size_t bytes = (size_t)e->cfg.max_blocks_per_batch * N * sizeof(float);
         if (!s.d_spectrum) {
@@ -664,8 +683,9 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
         const float *dev_iq = wk.iq;
         if (wk.mem != SDR_MEM_DEVICE) {
             dev_iq = s.d_iq + iq_off;
-            CK(e, cudaMemcpyAsync(s.d_iq + iq_off, wk.iq, (size_t)wk.n_blocks * 2 * N * sizeof(float), cudaMemcpyHostToDevice, e->s_h2d));
-            iq_off += (size_t)wk.n_blocks * 2 * N;
+            CK(e, cudaMemcpyAsync(s.d_iq + iq_off, wk.iq, (size_t)wk.n_blocks * sample_floats * N * sizeof(float),
+                                  cudaMemcpyHostToDevice, e->s_h2d));
+            iq_off += (size_t)wk.n_blocks * sample_floats * N;
         }
         wps[w].edge_width = wk.edge_width;
         wps[w].n_listeners = wk.n_listeners;
@@ -698,7 +718,7 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
                 for (int b = 0; b < take; b++) bs[block_off + pos + b] = n_segs;
             }
             Segment &sg = segs[n_segs++];
-            sg.iq = dev_iq + (size_t)pos * 2 * N;
+            sg.iq = dev_iq + (size_t)pos * sample_floats * N;
             sg.n_blocks = take;
             sg.stream = wk.stream;
             sg.work = w;
@@ -747,7 +767,7 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     CK(e, cudaEventRecord(s.ev_k0, e->s_compute));
     int k1_launches = 1;
     if (!e->large) {
-        CK(e, launch_k1(e, a1, dbg, e->s_compute));
+        CK(e, launch_k1(e, a1, dbg, e->s_compute, i16));
     } else {
         CK(e, launch_large(e, a1, s.d_tmp, reinterpret_cast<const int *>(s.d_desc + dl.block_seg), block_off, n_segs, e->s_compute));
         k1_launches = 4;
@@ -1018,6 +1038,24 @@ int sdr_dsp_find_peaks(sdr_engine *e, const float *cumulation, int cumulation_si
     *n_peaks = n;
     const int ncopy = n < max_peaks ? n : max_peaks;
     if (ncopy > 0) CK(e, cudaMemcpy(peaks, d_peaks, (size_t)ncopy * sizeof(sdr_peak), cudaMemcpyDeviceToHost));
+    return SDR_OK;
+}
+
+int sdr_kiwi_decode_iq_bytes(sdr_engine *e, const unsigned char *bytes, int n_bytes, float *out) {
+    if (!e || !bytes || !out || n_bytes < 4 || (n_bytes & 3)) return SDR_EINVAL;
+    CK(e, cudaSetDevice(e->cfg.device));
+    const int n_samples = n_bytes / 4;
+    int rc = ensure_scratch(e, (size_t)n_bytes + 256 + (size_t)n_samples * sizeof(float2));
+    if (rc != SDR_OK) return rc;
+    unsigned char *p = reinterpret_cast<unsigned char *>(e->d_scratch);
+    uint32_t *d_raw = reinterpret_cast<uint32_t *>(p);
+    float2 *d_out = reinterpret_cast<float2 *>(p + align_up((size_t)n_bytes, 256));
+    CK(e, cudaMemcpyAsync(d_raw, bytes, (size_t)n_bytes, cudaMemcpyHostToDevice, e->s_compute));
+    kiwi_decode_kernel<<<(n_samples + 255) / 256, 256, 0, e->s_compute>>>(d_raw, n_samples, d_out);
+    CK(e, cudaGetLastError());
+    e->launches += 1;
+    CK(e, cudaMemcpyAsync(out, d_out, (size_t)n_samples * sizeof(float2), cudaMemcpyDeviceToHost, e->s_compute));
+    CK(e, cudaStreamSynchronize(e->s_compute));
     return SDR_OK;
 }
 

@@ -96,6 +96,19 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
+// kiwi.decodeIQBytes (kiwi/client.go:298-308): one sample = 4 wire bytes I_hi I_lo Q_hi Q_lo (big-endian int16
+// pair) -> (float32(int16) / float32(32767)) for I and Q.  The IEEE division is done as a reciprocal multiply plus
+// one FMA residual correction (Markstein), which is correctly rounded for these operands -- verified bit-exact
+// over all 65536 inputs (tests/test_gpu_kiwi.py) -- so the FFT input equals the reference's float32 values.
+__device__ __forceinline__ float2 kiwi_decode_sample(uint32_t raw) {
+    const uint32_t sw = __byte_perm(raw, 0, 0x2301);  // swap the bytes of each half-word
+    const float2 x = make_float2((float)(short)(sw & 0xffffu), (float)(short)(sw >> 16));
+    const float r = 1.0f / 32767.0f;                  // correctly rounded reciprocal (compile-time constant)
+    const float2 q = __fmul2_rn(x, make_float2(r, r));
+    const float2 rem = __ffma2_rn(make_float2(-q.x, -q.y), make_float2(32767.0f, 32767.0f), x);  // exact residual
+    return __ffma2_rn(rem, make_float2(r, r), q);
+}
+
 template <int N>
 struct K1Geom {
     static constexpr int M = N / 16;       // points per pass-1 column set == threads per group
@@ -283,7 +296,8 @@ __device__ __forceinline__ float2 psd_to_db2(float2 psd) {
 
 // TW2R: keep the pass-2 twiddles in registers too (15 fewer shared-memory loads per thread and block; ptxas
 // still fits 128 registers = 4 resident CTAs per SM with a 12-byte spill)
-template <int N, bool DEBUG_STORE, bool HAS_WINDOW, bool TW2R>
+// IN_I16: the IQ blocks are KiwiSDR wire bytes (4 per sample); the conversion is fused into the pass-1 load.
+template <int N, bool DEBUG_STORE, bool HAS_WINDOW, bool TW2R, bool IN_I16 = false>
 __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS, 4) k1_spectral_kernel(const K1Args a) {
     using Gm = K1Geom<N>;
     constexpr int M = Gm::M, R3 = Gm::R3, T = Gm::T, PAIRS = Gm::PAIRS, S1 = Gm::S1, S2 = Gm::S2;
@@ -330,10 +344,11 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS, 4) k1_spectral_kernel(
     uint32_t issued = 0;
     auto issue_next = [&]() {
         if (pseg >= a.n_segs) return;
-        const float *src = a.segs[pseg].iq + (size_t)pblk * 2 * N;
+        constexpr uint32_t BLOCK_BYTES = IN_I16 ? 4 * N : 8 * N;
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(a.segs[pseg].iq) + (size_t)pblk * BLOCK_BYTES;
         int s = issued % NSTAGE;
-        mbar_expect_tx(&FULL[s], 8 * N);
-        tma_load_1d(stage_base + (size_t)s * Gm::STAGE_BYTES, src, 8 * N, &FULL[s]);
+        mbar_expect_tx(&FULL[s], BLOCK_BYTES);
+        tma_load_1d(stage_base + (size_t)s * Gm::STAGE_BYTES, src, BLOCK_BYTES, &FULL[s]);
         issued++;
         pblk++;
         if (pblk == pn) {
@@ -452,7 +467,8 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS, 4) k1_spectral_kernel(
 #pragma unroll
             for (int q = 0; q < 16; q++) {
                 const int m = (q & 3) * 4 + (q >> 2);
-                v[m] = IN[m * M + t];
+                if (IN_I16) v[m] = kiwi_decode_sample(reinterpret_cast<const uint32_t *>(IN)[m * M + t]);
+                else v[m] = IN[m * M + t];
                 if (HAS_WINDOW) v[m] = __fmul2_rn(v[m], make_float2(win[m], win[m]));
             }
             dft16(v);
