@@ -677,15 +677,27 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     s.work_flush_offset.assign(n_works + 1, 0);
     int n_segs = 0, n_flushes = 0, block_off = 0, lb_off = 0;
     size_t iq_off = 0;  // floats into d_iq
+    const float *pend_src = nullptr;  // pending coalesced H2D copy
+    float *pend_dst = nullptr;
+    size_t pend_n = 0;
     for (int w = 0; w < n_works; w++) {
         const sdr_work &wk = works[w];
         StreamInfo &si = e->streams[wk.stream];
         const float *dev_iq = wk.iq;
         if (wk.mem != SDR_MEM_DEVICE) {
+            // host IQ: stage it in the slot's device buffer.  Works whose host ranges are adjacent (one pinned
+            // ring filled stream after stream) are coalesced into ONE copy: fewer, larger H2D transfers.
             dev_iq = s.d_iq + iq_off;
-            CK(e, cudaMemcpyAsync(s.d_iq + iq_off, wk.iq, (size_t)wk.n_blocks * sample_floats * N * sizeof(float),
-                                  cudaMemcpyHostToDevice, e->s_h2d));
-            iq_off += (size_t)wk.n_blocks * sample_floats * N;
+            const size_t nfl = (size_t)wk.n_blocks * sample_floats * N;
+            if (pend_n > 0 && pend_src + pend_n == wk.iq && pend_dst + pend_n == s.d_iq + iq_off) {
+                pend_n += nfl;
+            } else {
+                if (pend_n > 0) CK(e, cudaMemcpyAsync(pend_dst, pend_src, pend_n * sizeof(float), cudaMemcpyHostToDevice, e->s_h2d));
+                pend_src = wk.iq;
+                pend_dst = s.d_iq + iq_off;
+                pend_n = nfl;
+            }
+            iq_off += nfl;
         }
         wps[w].edge_width = wk.edge_width;
         wps[w].n_listeners = wk.n_listeners;
@@ -742,6 +754,7 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     s.flags = flags;
     s.launches = 0;
 
+    if (pend_n > 0) CK(e, cudaMemcpyAsync(pend_dst, pend_src, pend_n * sizeof(float), cudaMemcpyHostToDevice, e->s_h2d));
     // ---- H2D: descriptors (+ IQ queued above) ----
     CK(e, cudaMemcpyAsync(s.d_desc, s.h_desc, dl.total, cudaMemcpyHostToDevice, e->s_h2d));
     CK(e, cudaEventRecord(s.ev_h2d, e->s_h2d));
