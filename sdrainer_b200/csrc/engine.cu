@@ -97,6 +97,8 @@ struct sdr_engine {
     int64_t launches = 0;
     int k1_grid_cap = 0;  // resident CTAs of K1 on this device
     bool k1_tw2r = true;  // kernel variant: pass-2 twiddles in registers (SDR_K1_TW2R=0 selects the smem-table variant)
+    // cache of choose_nf_map results, indexed by edge width (first byte 0xff = not computed)
+    std::vector<unsigned char> nf_map_cache;
     // scratch for the dsp single calls
     float *d_scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -265,6 +267,63 @@ int k1_grid_cap_for(int n, bool win, bool tw2r, int sm_count) {
     }
     if (occ < 1) occ = 1;
     return occ * sm_count;
+}
+
+// Noise-floor window sums (k1_spectral_kernel, phase 1): thread group g of TPW consecutive threads sums window
+// map[g] in shares of `per` contiguous bins.  Windows that share a warp can collide in shared-memory banks; this
+// host-side search simulates the warp access pattern and keeps the window permutation with the fewest wavefronts.
+template <int N>
+void choose_nf_map_n(int e, unsigned char *map) {
+    using Gm = K1Geom<N>;
+    constexpr int T = Gm::T, TPW = Gm::TPW;
+    const int ws = nf_window_size(N, e);
+    const int per = ((ws + TPW - 1) / TPW) | 1;
+    auto cost = [&](const unsigned char *m) {
+        long wf = 0;
+        for (int warp = 0; warp < (T + 31) / 32; warp++)
+            for (int i = 0; i < per; i++) {
+                int cnt[32] = {0}, mx = 0;
+                for (int lane = 0; lane < 32; lane++) {
+                    const int t = warp * 32 + lane;
+                    if (t >= T || t >= 10 * TPW) continue;
+                    const int w = m[t / TPW], part = t % TPW;
+                    const int lo = e + w * ws + part * per;
+                    int hi = lo + per;
+                    if (hi > e + (w + 1) * ws) hi = e + (w + 1) * ws;
+                    if (lo + i >= hi) continue;
+                    if (++cnt[(lo + i) & 31] > mx) mx = cnt[(lo + i) & 31];
+                }
+                wf += mx;
+            }
+        return wf;
+    };
+    unsigned char cur[16], best[16];
+    for (int i = 0; i < 16; i++) cur[i] = best[i] = (unsigned char)i;
+    long best_cost = cost(best);
+    uint64_t rng = 0x9E3779B97F4A7C15ull ^ (uint64_t)(e * 2654435761u);
+    for (int trial = 0; trial < 1500 && T >= 64; trial++) {
+        for (int i = 9; i > 0; i--) {  // Fisher-Yates with xorshift
+            rng ^= rng >> 12; rng ^= rng << 25; rng ^= rng >> 27;
+            const int j = (int)((rng * 0x2545F4914F6CDD1Dull >> 33) % (uint64_t)(i + 1));
+            const unsigned char tmp = cur[i]; cur[i] = cur[j]; cur[j] = tmp;
+        }
+        const long c = cost(cur);
+        if (c < best_cost) {
+            best_cost = c;
+            memcpy(best, cur, 16);
+        }
+    }
+    memcpy(map, best, 16);
+}
+
+void choose_nf_map(int n, int e, unsigned char *map) {
+    switch (n) {
+        case 512: choose_nf_map_n<512>(e, map); return;
+        case 1024: choose_nf_map_n<1024>(e, map); return;
+        case 2048: choose_nf_map_n<2048>(e, map); return;
+        case 4096: choose_nf_map_n<4096>(e, map); return;
+    }
+    for (int i = 0; i < 16; i++) map[i] = (unsigned char)i;
 }
 
 void build_twiddles(int n, std::vector<float2> &tw1, std::vector<float2> &tw2) {
@@ -492,6 +551,7 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
     CKC(cudaMalloc((void **)&e->d_rolling, (size_t)cfg->max_streams * sizeof(RollingState)));
     CKC(cudaMemset(e->d_rolling, 0, (size_t)cfg->max_streams * sizeof(RollingState)));
     e->streams.resize(cfg->max_streams);
+    e->nf_map_cache.assign((size_t)(e->N / 2 + 1) * 16, 0xff);
     {
         const char *v = getenv("SDR_K1_TW2R");  // experiment switch; default: pass-2 twiddles in registers
         e->k1_tw2r = !(v && v[0] == '0');
@@ -703,6 +763,11 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
         wps[w].n_listeners = wk.n_listeners;
         wps[w].listener_off = lb_off;
         wps[w].pad = 0;
+        {
+            unsigned char *cm = &e->nf_map_cache[(size_t)wk.edge_width * 16];
+            if (cm[0] == 0xff) choose_nf_map(N, wk.edge_width, cm);
+            memcpy(wps[w].nf_map, cm, 16);
+        }
         for (int l = 0; l < wk.n_listeners; l++) lbins[lb_off + l] = wk.listener_bins[l];
         lb_off += wk.n_listeners;
         PostWork &pw = pws[w];
@@ -970,6 +1035,7 @@ int sdr_dsp_iq_to_spectrum_and_psd(sdr_engine *e, const float *iq, int n_blocks,
     wp.n_listeners = 0;
     wp.listener_off = 0;
     wp.pad = 0;
+    for (int i = 0; i < 16; i++) wp.nf_map[i] = (unsigned char)i;
     CK(e, cudaMemcpyAsync(d_iq, iq, iq_bytes, cudaMemcpyHostToDevice, e->s_compute));
     CK(e, cudaMemcpyAsync(d_segs, segs.data(), sizeof(Segment) * (size_t)n_blocks, cudaMemcpyHostToDevice, e->s_compute));
     CK(e, cudaMemcpyAsync(d_work, &wp, sizeof(wp), cudaMemcpyHostToDevice, e->s_compute));

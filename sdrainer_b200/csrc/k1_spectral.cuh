@@ -40,6 +40,10 @@ struct WorkParams {
     int n_listeners;
     int listener_off;  // offset into the listener bin array
     int pad;
+    // noise-floor window sums: lane group g (TPW consecutive threads) sums window nf_map[g].  The host picks the
+    // permutation (per N and edge width) that minimises shared-memory bank conflicts between the windows that
+    // share a warp (engine.cu choose_nf_map); the identity is always correct.
+    unsigned char nf_map[16];
 };
 
 struct K1Args {
@@ -124,6 +128,7 @@ struct K1Geom {
     static constexpr int LMAX = 256;       // listener bins cached in smem per group
     static constexpr int TW2_BYTES = 15 * R3 * 8;
     static constexpr int TPW = (T / 10) / 3 * 3;  // noise floor: threads per window (multiple of 3: lanes 3w..3w+2 combine)
+    static constexpr int NF_MAX = ((N / 10 + TPW - 1) / TPW) | 1;  // longest per-thread share of a noise window (edge 0)
     static constexpr int NFB = 16;               // noise floor: blocks whose window sums are batched for selection
     static constexpr int NF_BYTES = NFB * 10 * (8 + 8 + 4);
     static constexpr int MISC_BYTES = NF_BYTES + T * 8 /*chunk partials (s1,s2)*/ + LMAX * 4 + NSTAGE * 8 /*mbar*/ + 64;
@@ -383,9 +388,11 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS, 4) k1_spectral_kernel(
         const int n_win = nf_window_count(N, e);  // the 10th window only closes if a later bin exists
         // this thread's share of the window sums: TPW threads per window, <= nf_len contiguous bins each
         constexpr int TPW = Gm::TPW;
-        int nf_lo = 0, nf_len = 0;
+        int nf_lo = 0, nf_len = 0, nf_part = t;  // nf_part: slot of this thread's partial sums in PART ([window][part])
         if (t < 10 * TPW) {
-            const int w = t / TPW, part = t - w * TPW;
+            const int grp = t / TPW, part = t - grp * TPW;
+            const int w = wp.nf_map[grp];
+            nf_part = w * TPW + part;
             // an ODD share length makes the lane stride odd: the strided reads below are bank-conflict free
             // within a window (lanes of neighbouring windows can still collide)
             const int per = ((ws + TPW - 1) / TPW) | 1;
@@ -544,25 +551,28 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS, 4) k1_spectral_kernel(
             // ---------------- noise floor, phase 1: per-thread partial sums of x and x^2 over a
             // contiguous share of one window (float32 inside the <=17-bin share, float64 across shares)
             {
-                // four independent chains (two packed accumulators) hide the FADD/LDS latency
-                float2 a1 = make_float2(0.f, 0.f), a2 = make_float2(0.f, 0.f);
+                // branch-free: a share never exceeds NF_MAX bins for the supported edge widths (host-checked), all
+                // loads are issued up front, bins beyond the share contribute +0; four independent packed chains
+                float2 a1 = make_float2(0.f, 0.f), a2 = make_float2(0.f, 0.f), b1 = a1, b2 = a1;
                 const float *pp = PSD + nf_lo;
-                int i = 0;
-                for (; i + 4 <= nf_len; i += 4) {
-                    const float2 x01 = make_float2(pp[i], pp[i + 1]);
-                    const float2 x23 = make_float2(pp[i + 2], pp[i + 3]);
+                float xs[Gm::NF_MAX];
+#pragma unroll
+                for (int i = 0; i < Gm::NF_MAX; i++) xs[i] = (i < nf_len) ? pp[i] : 0.f;
+#pragma unroll
+                for (int i = 0; i + 3 < Gm::NF_MAX; i += 4) {
+                    const float2 x01 = make_float2(xs[i], xs[i + 1]), x23 = make_float2(xs[i + 2], xs[i + 3]);
                     a1 = __fadd2_rn(a1, x01);
                     a2 = __ffma2_rn(x01, x01, a2);
-                    a1 = __fadd2_rn(a1, x23);
-                    a2 = __ffma2_rn(x23, x23, a2);
+                    b1 = __fadd2_rn(b1, x23);
+                    b2 = __ffma2_rn(x23, x23, b2);
                 }
-                float s1 = a1.x + a1.y, s2 = a2.x + a2.y;
-                for (; i < nf_len; i++) {
-                    const float x = pp[i];
-                    s1 += x;
-                    s2 = fmaf(x, x, s2);
+                float s1 = (a1.x + a1.y) + (b1.x + b1.y), s2 = (a2.x + a2.y) + (b2.x + b2.y);
+#pragma unroll
+                for (int i = Gm::NF_MAX / 4 * 4; i < Gm::NF_MAX; i++) {
+                    s1 += xs[i];
+                    s2 = fmaf(xs[i], xs[i], s2);
                 }
-                PART[t] = make_float2(s1, s2);
+                PART[nf_part] = make_float2(s1, s2);
             }
             // x_to = psd[first bin of the next window] is read here (PSD is gone after the next B4);
             // lane 3w of warp 0 owns window w in phase 2
