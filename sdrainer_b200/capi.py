@@ -79,7 +79,8 @@ class SdrError(RuntimeError):
 
 
 def lib_path() -> str:
-    return _build.LIB
+    # SDRGPU_LIB selects another build of the same library (kernel-variant experiments); default: the in-tree build
+    return os.environ.get("SDRGPU_LIB") or _build.LIB
 
 
 def lib():

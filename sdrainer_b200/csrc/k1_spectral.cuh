@@ -22,6 +22,10 @@
 
 #include "fft_radix.cuh"
 
+#ifndef SDR_K1_MINB
+#define SDR_K1_MINB 4
+#endif
+
 namespace sdr {
 
 struct Segment {
@@ -303,7 +307,7 @@ __device__ __forceinline__ float2 psd_to_db2(float2 psd) {
 // still fits 128 registers = 4 resident CTAs per SM with a 12-byte spill)
 // IN_I16: the IQ blocks are KiwiSDR wire bytes (4 per sample); the conversion is fused into the pass-1 load.
 template <int N, bool DEBUG_STORE, bool HAS_WINDOW, bool TW2R, bool IN_I16 = false>
-__global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS, 4) k1_spectral_kernel(const K1Args a) {
+__global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS, SDR_K1_MINB) k1_spectral_kernel(const K1Args a) {
     using Gm = K1Geom<N>;
     constexpr int M = Gm::M, R3 = Gm::R3, T = Gm::T, PAIRS = Gm::PAIRS, S1 = Gm::S1, S2 = Gm::S2;
     constexpr int NSTAGE = Gm::NSTAGE, G = Gm::G;
