@@ -1,0 +1,100 @@
+#!/usr/bin/env python
+"""Device-resident throughput of the hot path for every BASELINE.json config shape (single GPU).
+
+Not the contract bench (that is bench.py on configs[1]); this reports Msamples/s and the HBM-roofline fraction of
+the dominant kernel stage for the other block sizes so that DESIGN.md can quote them.
+Usage: python tools/bench_configs.py [--out profiles/r1_all_configs.json]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from sdrainer_b200 import capi  # noqa: E402
+
+CASES = [
+    # name, N, fs, listeners, streams, blocks per stream
+    ("cfg1 48 kS/s N=512 L=5", 512, 48000, 5, 4 * 148 * 12, 100),
+    ("N=1024 L=25", 1024, 96000, 25, 2 * 148 * 12, 100),
+    ("cfg2/cfg4 192 kS/s N=2048 L=50", 2048, 192000, 50, 148 * 12, 100),
+    ("N=4096 L=100", 4096, 384000, 100, 148 * 4, 100),
+    ("cfg3 768 kS/s N=8192 L=200 (large-block path)", 8192, 768000, 200, 64, 100),
+    ("cfg5 24.576 MS/s N=65536 peak scan (large-block path)", 65536, 24576000, 0, 8, 100),
+]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--steps", type=int, default=20)
+    args = ap.parse_args()
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(device=dev)
+    rows = []
+    for name, n, fs, nl, n_streams, nb in CASES:
+        g = torch.Generator(device=dev)
+        g.manual_seed(n)
+        iq = torch.randn((n_streams, nb * n * 2), generator=g, device=dev, dtype=torch.float32) * 1e-4
+        rng = np.random.default_rng(n)
+        bins = [np.sort(rng.choice(np.arange(80, n - 80), size=nl, replace=False)).astype(np.int32) for _ in range(n_streams)]
+        # a keyed-looking carrier on every listener bin so that peaks/keys have work to do
+        t = torch.arange(n, device=dev, dtype=torch.float32)
+        for s in range(min(n_streams, 64)):
+            for b in bins[s][:8]:
+                ph = 2 * np.pi * float(b - n // 2) / n
+                v = iq[s].view(nb, n, 2)
+                v[:, :, 0] += 0.01 * torch.cos(ph * t)
+                v[:, :, 1] += 0.01 * torch.sin(ph * t)
+        eng = capi.Engine(n, max_streams=n_streams, max_listeners=max(nl, 1), max_blocks_per_batch=n_streams * nb,
+                          max_peaks_per_flush=128, n_slots=2, cuda_stream=stream.cuda_stream)
+        sids = [eng.open_stream(fs) for _ in range(n_streams)]
+        per = nb * 2 * n * 4
+        prepared = eng.prepare([dict(stream=sids[i], iq=iq.data_ptr() + i * per, n_blocks=nb, listener_bins=bins[i])
+                                for i in range(n_streams)])
+        for _ in range(3):
+            tk = eng.submit_prepared(prepared, capi.NO_D2H)
+            eng.collect_raw(tk)
+            eng.release(tk)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k1 = []
+        e0.record(stream)
+        pend = []
+        for _ in range(args.steps):
+            pend.append(eng.submit_prepared(prepared, capi.NO_D2H))
+            if len(pend) == 2:
+                r = eng.collect_raw(pend[0])
+                k1.append(r.k1_ms)
+                eng.release(pend.pop(0))
+        e1.record(stream)
+        for tk in pend:
+            r = eng.collect_raw(tk)
+            k1.append(r.k1_ms)
+            eng.release(tk)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        samples = n_streams * nb * n
+        alg = (8 * n + 4 * n / 100.0 + 4 * nl + 16) * n_streams * nb
+        k1_ms = float(np.mean(k1))
+        rows.append({"config": name, "block_size": n, "streams": n_streams, "listeners": nl,
+                     "batch_bytes": samples * 8, "msamples_per_s": samples / (ms * 1e-3) / 1e6, "ms_per_step": ms,
+                     "spectral_stage_ms": k1_ms, "spectral_stage_gbs": alg / (k1_ms * 1e-3) / 1e9,
+                     "hbm_roofline_frac": alg / (k1_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                     "realtime_streams": samples / (ms * 1e-3) / fs})
+        print(json.dumps(rows[-1]))
+        eng.close()
+        del iq
+        torch.cuda.empty_cache()
+    if args.out:
+        with open(args.out, "w") as f:
+            json.dump({"peak_hbm_gbs": peaks["hbm_gbs"], "rows": rows}, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
