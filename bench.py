@@ -136,34 +136,47 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summarises the samples that arrived inside [t0, t1] (the timed region); when the region is shorter than
+        a few sampling periods, falls back to every sample since the sampler started (warm-up included: the GPU is
+        under the same load) and says so."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-                pw.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+
+        def summarise(rows):
+            sm, mx, pw, reasons = [], [], [], set()
+            for _, r in rows:
+                f = [x.strip() for x in r.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[0]))
+                    mx.append(float(f[1]))
+                    pw.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, pw, reasons
+
+        inside = [r for r in self.rows if t0 is not None and t0 <= r[0] <= (t1 or 1e99)]
+        window = "timed region"
+        sm, mx, pw, reasons = summarise(inside)
+        if len(sm) < 3:
+            sm, mx, pw, reasons = summarise(self.rows)
+            window = "warm-up + timed region (timed region shorter than 3 sampling periods)"
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -303,14 +316,15 @@ def run_gpu(args):
         return eng.submit_prepared(prepared, capi.NO_D2H)
 
     k1_ms, k2_ms = [], []
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # started before the warm-up so that nvidia-smi is up when the timed region begins
     for _ in range(args.warmup):
         t = step()
         eng.collect_raw(t)
         eng.release(t)
     barrier()
     launches0 = eng.launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    t_region0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tickets = []
     e0.record(stream)
@@ -330,8 +344,20 @@ def run_gpu(args):
         k2_ms.append(r.k2_ms)
         eng.release(t)
     barrier()
-    clocks = sampler.stop()
-    launches = eng.launch_count() - launches0
+    t_region1 = time.time()
+    launches = eng.launch_count() - launches0  # kernels launched inside the timed region
+    if sum(1 for r in sampler.rows if t_region0 <= r[0] <= t_region1) < 3:
+        # the timed region was shorter than a few nvidia-smi periods: keep the identical load running (untimed)
+        # until enough clock samples exist, and report those
+        t_probe = time.time()
+        while time.time() - t_probe < 1.5 and sum(1 for r in sampler.rows if r[0] >= t_probe) < 6:
+            t = step()
+            eng.collect_raw(t)
+            eng.release(t)
+        clocks = sampler.stop(t_probe, time.time())
+        clocks["window"] = "identical load repeated right after the timed region (region shorter than the sampling period)"
+    else:
+        clocks = sampler.stop(t_region0, t_region1)
     from sdrainer_b200 import sharding
     elapsed_ms = e0.elapsed_time(e1)
     # whole-job throughput: units of all ranks / max-over-ranks device time (no data-path collective)
