@@ -152,6 +152,12 @@ void sdrh_receiver_set(void *p, float peak_threshold, int edge_width, double sil
     r.SetSignalDebounce(debounce);
     r.SetCenterFrequency(center);
 }
+// rx/peaks.go:183-207: FindNext's random probe, seeded (the reference uses unseeded math/rand); call before start
+void sdrh_receiver_set_find_next(void *p, int deterministic, unsigned long long seed) {
+    rx::Receiver &r = ((ReceiverBox *)p)->rx;
+    r.deterministicFindNext = deterministic != 0;
+    r.rngSeed = seed;
+}
 int sdrh_receiver_iq_data(void *p, int fs, const float *data, long long len) { return ((ReceiverBox *)p)->rx.IQData(fs, data, (size_t)len) ? 1 : 0; }
 int sdrh_receiver_process(void *p) {
     try {
