@@ -380,3 +380,27 @@ def test_cfg5_shape_65536_peak_scan(capi, oracle):
     # the threshold) sits far above the true noise: only the strongest carriers are reported -- by both sides
     found = {int(p["signal_bin"]) for p in res.peaks(0)}
     assert len(found) >= 20 and found <= {t.bin for t in tones}
+
+
+def test_stream_reset_close_reopen_and_flags(capi):
+    """Receiver.Stop/Start (rx/receiver.go:130-164) map to close/open; reset clears cumulation + rolling means"""
+    n = 1024
+    spec = _spec(n, 96000, 150, seed=8, k=4)
+    iq = synth.generate(spec)
+    bins = [t.bin for t in spec.tones]
+    with capi.Engine(n, max_streams=2, max_listeners=8, max_blocks_per_batch=200, max_peaks_per_flush=64, n_slots=1) as eng:
+        s = eng.open_stream(96000)
+        first = eng.collect(eng.submit([dict(stream=s, iq=iq, listener_bins=bins)], capi.WANT_FLUSH_CUM))
+        assert eng.cumulation_count(s) == 50 and first.n_flushes == 1
+        eng.reset_stream(s)
+        assert eng.cumulation_count(s) == 0
+        again = eng.collect(eng.submit([dict(stream=s, iq=iq, listener_bins=bins)], capi.WANT_FLUSH_CUM))
+        for name in ("psd_noise_floor", "thresholds", "keys", "flush_cum"):
+            assert np.array_equal(getattr(first, name), getattr(again, name)), name  # identical after a reset
+        eng.close_stream(s)
+        s2 = eng.open_stream(96000)  # a reopened slot starts from scratch as well
+        third = eng.collect(eng.submit([dict(stream=s2, iq=iq, listener_bins=bins)], capi.NO_PEAKS | capi.NO_TAPS))
+        assert np.array_equal(third.thresholds, first.thresholds)
+        assert third.taps is None and (third.flush_n_peaks == 0).all()
+        with pytest.raises(capi.SdrError):
+            eng.submit([dict(stream=s + 1, iq=iq)])  # never opened
