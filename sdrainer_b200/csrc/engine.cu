@@ -22,6 +22,7 @@
 
 #include "../../include/sdrgpu.h"
 #include "k1_spectral.cuh"
+#include "k1_pair.cuh"
 #include "k2_post.cuh"
 #include "k1_large.cuh"
 
@@ -96,6 +97,13 @@ struct sdr_engine {
     sdr_ticket next_ticket = 1;
     int64_t launches = 0;
     int k1_grid_cap = 0;  // resident CTAs of K1 on this device
+    // N = 2048: SDR_K1_PAIR=1 selects the warp-pair kernel (k1_pair.cuh) instead of the three-pass kernel as the
+    // spectral stage (same results, same speed on B200: DESIGN.md section 4); SDR_K1_PAIR_STAGES=1|2 is the depth of
+    // its TMA ring
+    float2 *d_twp = nullptr;
+    bool k1_pair = false;
+    int k1p_stages = 1;
+    int k1p_grid_cap = 0;
     bool k1_tw2r = true;  // kernel variant: pass-2 twiddles in registers (SDR_K1_TW2R=0 selects the smem-table variant)
     // cache of choose_nf_map results, indexed by edge width (first byte 0xff = not computed)
     std::vector<unsigned char> nf_map_cache;
@@ -114,6 +122,12 @@ namespace {
             return SDR_ECUDA;                                                                        \
         }                                                                                            \
     } while (0)
+
+// dsp.FindNoiseFloor (dsp/fft.go:215-252) closes a window whenever `count == ws` on entry, for every i < N-e: with
+// ws = (N-2e)/10 >= 9 the remainder (N-2e) - 10*ws <= 9 never completes an 11th window, which is what the kernels
+// assume (9 or 10 evaluated windows).  Narrower windows (ws < 9: the reference would evaluate up to 19 of them, and
+// 0/0 for ws == 0) are rejected.
+bool nf_edge_supported(int n, int e) { return e >= 0 && nf_window_size(n, e) >= 9; }
 
 bool supported_fused_n(int n) { return n == 512 || n == 1024 || n == 2048 || n == 4096; }
 
@@ -247,7 +261,45 @@ cudaError_t launch_large(const sdr_engine *e, const K1Args &a, float2 *d_tmp, co
     return cudaGetLastError();
 }
 
-cudaError_t launch_k1(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st, bool i16 = false) {
+template <int NSTAGE>
+const void *k1p_fn(bool dbg, bool win, bool i16) {
+    if (i16) return dbg ? (const void *)k1_pair_kernel<true, false, true, NSTAGE> : (const void *)k1_pair_kernel<false, false, true, NSTAGE>;
+    if (dbg) return win ? (const void *)k1_pair_kernel<true, true, false, NSTAGE> : (const void *)k1_pair_kernel<true, false, false, NSTAGE>;
+    return win ? (const void *)k1_pair_kernel<false, true, false, NSTAGE> : (const void *)k1_pair_kernel<false, false, false, NSTAGE>;
+}
+const void *k1p_fn(int stages, bool dbg, bool win, bool i16) { return stages == 2 ? k1p_fn<2>(dbg, win, i16) : k1p_fn<1>(dbg, win, i16); }
+
+// resident pairs per SM x SMs; also opts every variant in to its dynamic shared memory size
+int k1p_grid_cap_for(int stages, bool win, int sm_count) {
+    const int smem = K1PairGeom::smem_bytes(stages);
+    int occ = 0;
+    for (int dbg = 0; dbg < 2; dbg++) {
+        const void *fn = k1p_fn(stages, dbg != 0, win, false);
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (!dbg) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 64, smem);
+        if (!win) cudaFuncSetAttribute(k1p_fn(stages, dbg != 0, false, true), cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    }
+    if (occ < 1) occ = 1;
+    return occ * sm_count;
+}
+
+cudaError_t launch_k1_pair(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st, bool i16) {
+    // one pair of warps per CTA walks the segment list with stride grid: whole rounds, no straggler
+    int grid = a.n_segs;
+    if (grid > e->k1p_grid_cap) {
+        const int rounds = (grid + e->k1p_grid_cap - 1) / e->k1p_grid_cap;
+        grid = (a.n_segs + rounds - 1) / rounds;
+    }
+    if (grid < 1) grid = 1;
+    K1Args args = a;
+    void *params[] = {&args};
+    return cudaLaunchKernel(k1p_fn(e->k1p_stages, dbg, a.window != nullptr, i16), dim3(grid), dim3(64), params,
+                            K1PairGeom::smem_bytes(e->k1p_stages), st);
+}
+
+// pair_ok: every work of the launch has noise windows of at least K1PairGeom::MIN_WS bins
+cudaError_t launch_k1(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st, bool i16 = false, bool pair_ok = true) {
+    if (e->k1_pair && pair_ok) return launch_k1_pair(e, a, dbg, st, i16);
     switch (e->N) {
         case 512: return launch_k1_n<512>(e, a, dbg, st, i16);
         case 1024: return launch_k1_n<1024>(e, a, dbg, st, i16);
@@ -525,6 +577,21 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
         CKC(cudaMalloc((void **)&e->d_tw2, tw2.size() * sizeof(float2)));
         CKC(cudaMemcpy(e->d_tw1, tw1.data(), tw1.size() * sizeof(float2), cudaMemcpyHostToDevice));
         CKC(cudaMemcpy(e->d_tw2, tw2.data(), tw2.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        if (e->N == K1PairGeom::N) {
+            // k1_pair.cuh: lane l of warp h multiplies DFT32 output position p (row j = OutIdx<32>(p)) by
+            // W_2048^(l (2j + h))
+            std::vector<float2> twp((size_t)2 * 32 * 32);
+            const double two_pi = 6.283185307179586476925286766559;
+            for (int h = 0; h < 2; h++)
+                for (int p = 0; p < 32; p++)
+                    for (int l = 0; l < 32; l++) {
+                        const int ex = (l * (2 * OutIdx<32>::of(p) + h)) % 2048;
+                        const double ang = -two_pi * (double)ex / 2048.0;
+                        twp[((size_t)h * 32 + p) * 32 + l] = make_float2((float)cos(ang), (float)sin(ang));
+                    }
+            CKC(cudaMalloc((void **)&e->d_twp, twp.size() * sizeof(float2)));
+            CKC(cudaMemcpy(e->d_twp, twp.data(), twp.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        }
     } else {
         auto table = [&](int len, float2 **dst) -> cudaError_t {
             std::vector<float2> t(len);
@@ -557,6 +624,13 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
         e->k1_tw2r = !(v && v[0] == '0');
     }
     if (!e->large) e->k1_grid_cap = k1_grid_cap_for(e->N, e->d_window != nullptr, e->k1_tw2r, e->sm_count);
+    if (e->d_twp) {
+        const char *v = getenv("SDR_K1_PAIR");
+        e->k1_pair = (v && v[0] == '1');
+        const char *st = getenv("SDR_K1_PAIR_STAGES");
+        e->k1p_stages = (st && st[0] == '2') ? 2 : 1;
+        if (e->k1_pair) e->k1p_grid_cap = k1p_grid_cap_for(e->k1p_stages, e->d_window != nullptr, e->sm_count);
+    }
     CKC(cudaGetLastError());
     e->slots.resize(cfg->n_slots);
     for (auto &s : e->slots) {
@@ -576,6 +650,7 @@ void sdr_engine_destroy(sdr_engine *e) {
     for (auto &s : e->slots) free_slot(s);
     cudaFree(e->d_tw1);
     cudaFree(e->d_tw2);
+    cudaFree(e->d_twp);
     cudaFree(e->d_tw_sub1);
     cudaFree(e->d_tw_sub2);
     cudaFree(e->d_tw_n);
@@ -678,8 +753,8 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
                     e->err = "work " + std::to_string(w) + ": listener bin out of range";
                     return SDR_EINVAL;
                 }
-            if (wk.edge_width < 0 || nf_window_size(N, wk.edge_width) < 1) {
-                e->err = "work " + std::to_string(w) + ": edge_width leaves no noise window ((N-2e)/10 < 1)";
+            if (!nf_edge_supported(N, wk.edge_width)) {
+                e->err = "work " + std::to_string(w) + ": edge_width leaves noise windows of fewer than 9 bins ((N-2e)/10 < 9)";
                 return SDR_EINVAL;
             }
             if (wk.mem == SDR_MEM_DEVICE && ((uintptr_t)wk.iq & 15)) {
@@ -737,6 +812,7 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     s.work_flush_offset.assign(n_works + 1, 0);
     int n_segs = 0, n_flushes = 0, block_off = 0, lb_off = 0;
     size_t iq_off = 0;  // floats into d_iq
+    bool pair_ok = true;              // every work's noise windows are wide enough for k1_pair_kernel
     const float *pend_src = nullptr;  // pending coalesced H2D copy
     float *pend_dst = nullptr;
     size_t pend_n = 0;
@@ -760,6 +836,7 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
             iq_off += nfl;
         }
         wps[w].edge_width = wk.edge_width;
+        if (nf_window_size(N, wk.edge_width) < K1PairGeom::MIN_WS) pair_ok = false;
         wps[w].n_listeners = wk.n_listeners;
         wps[w].listener_off = lb_off;
         wps[w].pad = 0;
@@ -833,6 +910,7 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     a1.listener_bins = reinterpret_cast<const int *>(s.d_desc + dl.lbins);
     a1.tw1 = e->d_tw1;
     a1.tw2 = e->d_tw2;
+    a1.twp = e->d_twp;
     a1.window = e->d_window;
     a1.cum_state = e->d_cum_state;
     a1.psd_floor = s.d_psd_floor;
@@ -845,7 +923,7 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     CK(e, cudaEventRecord(s.ev_k0, e->s_compute));
     int k1_launches = 1;
     if (!e->large) {
-        CK(e, launch_k1(e, a1, dbg, e->s_compute, i16));
+        CK(e, launch_k1(e, a1, dbg, e->s_compute, i16, pair_ok));
     } else {
         CK(e, launch_large(e, a1, s.d_tmp, reinterpret_cast<const int *>(s.d_desc + dl.block_seg), block_off, n_segs, e->s_compute));
         k1_launches = 4;
@@ -1046,6 +1124,7 @@ int sdr_dsp_iq_to_spectrum_and_psd(sdr_engine *e, const float *iq, int n_blocks,
     a.listener_bins = nullptr;
     a.tw1 = e->d_tw1;
     a.tw2 = e->d_tw2;
+    a.twp = e->d_twp;
     a.window = e->d_window;
     a.cum_state = d_cum;
     a.psd_floor = d_floor;
@@ -1075,8 +1154,8 @@ int sdr_dsp_iq_to_spectrum_and_psd(sdr_engine *e, const float *iq, int n_blocks,
 int sdr_dsp_find_noise_floor(sdr_engine *e, const float *psd, int edge_width, float *min_value, double *variance) {
     if (!e || !psd || !min_value || !variance) return SDR_EINVAL;
     const int N = e->N;
-    if (edge_width < 0 || nf_window_size(N, edge_width) < 1) {
-        e->err = "edge_width leaves no noise window ((N-2e)/10 < 1)";
+    if (!nf_edge_supported(N, edge_width)) {
+        e->err = "edge_width leaves noise windows of fewer than 9 bins ((N-2e)/10 < 9)";
         return SDR_EINVAL;
     }
     CK(e, cudaSetDevice(e->cfg.device));

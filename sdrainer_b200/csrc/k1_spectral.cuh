@@ -66,6 +66,7 @@ struct K1Args {
     float *flush_cum;       // [flushes][N]
     float *dbg_spectrum;    // [blocks][N] (DEBUG_STORE)
     float *dbg_psd;         // [blocks][N]
+    const float2 *twp;      // k1_pair.cuh: [2][32][32] W_2048^(l (2 j(p) + h)), nullptr when N != 2048
 };
 
 // ---- PTX helpers: mbarrier + TMA bulk copy -------------------------------------------------
@@ -527,9 +528,16 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS, SDR_K1_MINB) k1_spectr
 #pragma unroll
                 for (int q = 0; q < R3 / 2; q++) {
                     // two bins at a time: |X|^2 (dsp/fft.go:71-73), dB + 120 (rx/receiver.go:376-378)
+#ifdef SDR_K1_PSD_PACKED
                     const float2 sq0 = __fmul2_rn(u[2 * q], u[2 * q]);
                     const float2 sq1 = __fmul2_rn(u[2 * q + 1], u[2 * q + 1]);
                     const float2 psd = make_float2(sq0.x + sq0.y, sq1.x + sq1.y);
+#else
+                    // FMUL + FFMA per bin: 2 FP32-pipe cycles instead of 3 (FMUL2 + FADD); one rounding fewer than
+                    // the reference's two float64 products, far below the fp32-FFT error of the bin
+                    const float2 psd = make_float2(fmaf(u[2 * q].x, u[2 * q].x, u[2 * q].y * u[2 * q].y),
+                                                   fmaf(u[2 * q + 1].x, u[2 * q + 1].x, u[2 * q + 1].y * u[2 * q + 1].y));
+#endif
                     const int kk0 = (c + 256 * OutIdx<R3>::of(2 * q) + N / 2) % N;  // dsp/fft.go:54-57 fftshift
                     const int kk1 = (c + 256 * OutIdx<R3>::of(2 * q + 1) + N / 2) % N;
                     PSD[kk0] = psd.x;
