@@ -36,6 +36,7 @@ struct StreamInfo {
     bool open = false;
     int sample_rate = 0;
     int cum_count = 0;  // cumulationCount (rx/receiver.go:347)
+    int state_row = 0;  // which of the stream's two cum_state rows holds the open window's partial cumulation
 };
 
 struct Slot {
@@ -89,6 +90,7 @@ struct sdr_engine {
     bool large = false;
     LargeGeom lg{};
     float2 *d_tw_sub1 = nullptr, *d_tw_sub2 = nullptr, *d_tw_n = nullptr;
+    float2 *d_tw_step = nullptr;  // [k1][c] = W_N^(c k1): step-1 twiddles of the register-resident kernels
     float *d_window = nullptr;
     float *d_cum_state = nullptr;
     RollingState *d_rolling = nullptr;
@@ -230,12 +232,37 @@ cudaError_t launch_large(const sdr_engine *e, const K1Args &a, float2 *d_tmp, co
     sa.n1 = e->lg.n1;
     sa.n2 = e->lg.n2;
     sa.db_offset = (float)(10.0 * log10(20.0 / ((double)N * (double)N)));
-    sa.tw_sub = e->d_tw_sub1;
-    cudaError_t rc = launch_sub_fft_len<1>(e->lg.n1, sa, e->lg.n2, n_blocks, st);
-    if (rc != cudaSuccess) return rc;
-    sa.tw_sub = e->d_tw_sub2;
-    rc = launch_sub_fft_len<2>(e->lg.n2, sa, e->lg.n1, n_blocks, st);
-    if (rc != cudaSuccess) return rc;
+    cudaError_t rc;
+    if (e->d_tw_step) {  // (32 | 256) x 256: half-warp / per-thread register transforms
+        FastStepArgs fa{};
+        fa.tmp = d_tmp;
+        fa.spectrum = a.dbg_spectrum;
+        fa.psd = a.dbg_psd;
+        fa.tw256 = e->d_tw_sub2;
+        fa.tw_step = e->d_tw_step;
+        fa.window = e->d_window;
+        fa.segs = a.segs;
+        fa.block_seg = d_block_seg;
+        fa.n = N;
+        fa.n1 = e->lg.n1;
+        fa.n2 = e->lg.n2;
+        fa.db_offset = sa.db_offset;
+        const size_t smem = (size_t)16 * HW_PITCH * sizeof(float2);
+        if (e->lg.n1 == 256) fast_cols256_kernel<<<dim3(e->lg.n2 / 16, n_blocks), 256, smem, st>>>(fa);
+        else fast_cols32_kernel<<<dim3(e->lg.n2 / 256, n_blocks), 256, 0, st>>>(fa);
+        rc = cudaGetLastError();
+        if (rc != cudaSuccess) return rc;
+        fast_rows256_kernel<<<dim3(e->lg.n1 / 16, n_blocks), 256, smem, st>>>(fa);
+        rc = cudaGetLastError();
+        if (rc != cudaSuccess) return rc;
+    } else {
+        sa.tw_sub = e->d_tw_sub1;
+        rc = launch_sub_fft_len<1>(e->lg.n1, sa, e->lg.n2, n_blocks, st);
+        if (rc != cudaSuccess) return rc;
+        sa.tw_sub = e->d_tw_sub2;
+        rc = launch_sub_fft_len<2>(e->lg.n2, sa, e->lg.n1, n_blocks, st);
+        if (rc != cudaSuccess) return rc;
+    }
     LargePostArgs pa{};
     pa.psd = a.dbg_psd;
     pa.spectrum = a.dbg_spectrum;
@@ -607,14 +634,26 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
         CKC(table(e->lg.n1, &e->d_tw_sub1));
         CKC(table(e->lg.n2, &e->d_tw_sub2));
         CKC(table(e->N, &e->d_tw_n));
+        if (large_fast_geom(e->lg.n1, e->lg.n2)) {
+            const int n1 = e->lg.n1, n2 = e->lg.n2;
+            std::vector<float2> t((size_t)n1 * n2);
+            const double two_pi = 6.283185307179586476925286766559;
+            for (int k = 0; k < n1; k++)
+                for (int c = 0; c < n2; c++) {
+                    const double ang = -two_pi * (double)(((long long)c * k) % e->N) / (double)e->N;
+                    t[(size_t)k * n2 + c] = make_float2((float)cos(ang), (float)sin(ang));
+                }
+            CKC(cudaMalloc((void **)&e->d_tw_step, t.size() * sizeof(float2)));
+            CKC(cudaMemcpy(e->d_tw_step, t.data(), t.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        }
     }
     if (cfg->window) {
         CKC(cudaMalloc((void **)&e->d_window, (size_t)e->N * sizeof(float)));
         CKC(cudaMemcpy(e->d_window, cfg->window, (size_t)e->N * sizeof(float), cudaMemcpyHostToDevice));
         e->cfg.window = nullptr;  // never retain the caller's pointer (cgo rule)
     }
-    CKC(cudaMalloc((void **)&e->d_cum_state, (size_t)cfg->max_streams * e->N * sizeof(float)));
-    CKC(cudaMemset(e->d_cum_state, 0, (size_t)cfg->max_streams * e->N * sizeof(float)));
+    CKC(cudaMalloc((void **)&e->d_cum_state, (size_t)2 * cfg->max_streams * e->N * sizeof(float)));
+    CKC(cudaMemset(e->d_cum_state, 0, (size_t)2 * cfg->max_streams * e->N * sizeof(float)));
     CKC(cudaMalloc((void **)&e->d_rolling, (size_t)cfg->max_streams * sizeof(RollingState)));
     CKC(cudaMemset(e->d_rolling, 0, (size_t)cfg->max_streams * sizeof(RollingState)));
     e->streams.resize(cfg->max_streams);
@@ -651,6 +690,7 @@ void sdr_engine_destroy(sdr_engine *e) {
     cudaFree(e->d_tw1);
     cudaFree(e->d_tw2);
     cudaFree(e->d_twp);
+    cudaFree(e->d_tw_step);
     cudaFree(e->d_tw_sub1);
     cudaFree(e->d_tw_sub2);
     cudaFree(e->d_tw_n);
@@ -877,9 +917,13 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
             sg.stream = wk.stream;
             sg.work = w;
             sg.block_out = block_off + pos;
-            sg.load_state = c > 0 ? 1 : 0;
+            // the partial cumulation of a stream ping-pongs between its two state rows: a work that crosses a window
+            // boundary has a first segment that READS the saved state and a last one that WRITES the new state,
+            // both in this launch
+            sg.state_in = c > 0 ? 2 * wk.stream + si.state_row : -1;
             sg.flush_idx = (c + take == SDR_CUMULATION_SIZE) ? n_flushes++ : -1;
-            sg.pad = 0;
+            sg.state_out = 2 * wk.stream + (si.state_row ^ 1);
+            if (sg.flush_idx < 0) si.state_row ^= 1;  // only the last segment of a work can leave a window open
             if (sg.flush_idx >= 0) pw.n_flushes++;
             c = (c + take) % SDR_CUMULATION_SIZE;
             pos += take;
@@ -1105,8 +1149,8 @@ int sdr_dsp_iq_to_spectrum_and_psd(sdr_engine *e, const float *iq, int n_blocks,
         sg.work = 0;
         sg.block_out = b;
         sg.flush_idx = 0;  // cumulation goes to the throw-away row
-        sg.load_state = 0;
-        sg.pad = 0;
+        sg.state_in = -1;
+        sg.state_out = 0;
     }
     WorkParams wp;
     wp.edge_width = 0;

@@ -18,16 +18,18 @@
 #include <stdint.h>
 
 #include "k1_spectral.cuh"
+#include "k1_pair.cuh"
 
 namespace sdr {
 
 struct LargeGeom {
-    int n, n1, n2;  // N = n1 * n2, both in {64, 128, 256}
+    int n, n1, n2;  // N = n1 * n2; (32 | 256) x 256 run the register-resident kernels, the rest the Stockham kernels
 };
+__host__ __device__ inline bool large_fast_geom(int n1, int n2) { return n2 == 256 && (n1 == 32 || n1 == 256); }
 __host__ __device__ inline bool large_geom(int n, LargeGeom *g) {
     g->n = n;
     switch (n) {
-        case 8192: g->n1 = 128; g->n2 = 64; return true;
+        case 8192: g->n1 = 32; g->n2 = 256; return true;
         case 16384: g->n1 = 128; g->n2 = 128; return true;
         case 32768: g->n1 = 256; g->n2 = 128; return true;
         case 65536: g->n1 = 256; g->n2 = 256; return true;
@@ -163,6 +165,161 @@ __global__ void __launch_bounds__(SUBFFT_F *L / 4) sub_fft_kernel(const SubFftAr
     }
 }
 
+// ---- register-resident sub-FFTs for the two BASELINE shapes (N = 8192 = 32 x 256, N = 65536 = 256 x 256) ----------
+// A 256-point transform is run by a HALF-WARP: lane hl keeps 16 points, radix-16 over n1 (x[16 n1 + hl]), twiddle
+// W256^(hl k1), one 16x16 transpose through the FFT's own shared-memory column (pitch 17, conflict-free, __syncwarp
+// only), radix-16 over n2.  Lane hl ends with X[hl + 16*OutIdx<16>(p)] in register p.  Same packed-f32x2 butterflies
+// as K1 (fft_radix.cuh); no CTA barrier inside the transform.
+constexpr int HW_PITCH = 273;  // complex slots per column: >= 16*17 (transpose), odd multiple-of-16 remainder 1
+
+struct HwTwiddle {
+    float2 w[15];  // W256^(hl * k1), k1 = 1..15
+};
+__device__ __forceinline__ void hw_twiddle_load(HwTwiddle &t, const float2 *__restrict__ tw256, int hl) {
+#pragma unroll
+    for (int k = 1; k < 16; k++) t.w[k - 1] = __ldg(&tw256[(hl * k) & 255]);
+}
+// col: this FFT's 256 inputs in natural order (pitch HW_PITCH); all 32 lanes of the warp call it (two FFTs per warp)
+__device__ __forceinline__ void fft256_halfwarp(float2 (&v)[16], float2 *col, const HwTwiddle &t, int hl) {
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        const int n1 = (q & 3) * 4 + (q >> 2);
+        v[n1] = col[16 * n1 + hl];
+    }
+    dft16(v);
+#pragma unroll
+    for (int p = 0; p < 16; p++) {
+        const int k1 = OutIdx<16>::of(p);
+        if (k1 > 0) v[p] = cmul(v[p], t.w[k1 - 1]);
+    }
+    __syncwarp();  // every lane has read its inputs: the column may be overwritten by the transpose
+#pragma unroll
+    for (int p = 0; p < 16; p++) col[OutIdx<16>::of(p) * 17 + hl] = v[p];
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        const int n2 = (q & 3) * 4 + (q >> 2);
+        v[n2] = col[hl * 17 + n2];
+    }
+    dft16(v);
+}
+
+struct FastStepArgs {
+    float2 *tmp;            // [blocks][N] four-step intermediate
+    float *spectrum, *psd;  // step 2 outputs [blocks][N]
+    const float2 *tw256;    // W_256^m
+    const float2 *tw_step;  // [k1][c] = W_N^(c k1), k1 < N1, c < N2 (step 1)
+    const float *window;
+    const Segment *segs;
+    const int *block_seg;
+    int n, n1, n2;
+    float db_offset;
+};
+
+// step 1, N1 = 256: grid (N2 / 16, blocks), 256 threads; half-warp f owns column c0 + f
+__global__ void __launch_bounds__(256) fast_cols256_kernel(const FastStepArgs a) {
+    extern __shared__ __align__(16) unsigned char sub_smem[];
+    float2 *cols = reinterpret_cast<float2 *>(sub_smem);  // [16][HW_PITCH]
+    const int tid = threadIdx.x, hl = tid & 15, f = tid >> 4;
+    const int blk = blockIdx.y, c0 = blockIdx.x * 16;
+    const int N = a.n, N2 = a.n2;
+    const Segment sg = a.segs[a.block_seg[blk]];
+    const float2 *src = reinterpret_cast<const float2 *>(sg.iq) + (size_t)(blk - sg.block_out) * N + c0;
+    HwTwiddle t;
+    hw_twiddle_load(t, a.tw256, hl);
+    // tile load: half-warp = one 128-byte row segment (16 columns); transposed into per-column buffers
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const int r = f + 16 * i;
+        float2 x = __ldg(&src[(size_t)r * N2 + hl]);
+        if (a.window) {
+            const float w = __ldg(&a.window[r * N2 + c0 + hl]);
+            x = __fmul2_rn(x, make_float2(w, w));
+        }
+        cols[hl * HW_PITCH + r] = x;
+    }
+    __syncthreads();
+    float2 v[16];
+    float2 *col = cols + f * HW_PITCH;
+    fft256_halfwarp(v, col, t, hl);
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < 16; p++) col[hl + 16 * OutIdx<16>::of(p)] = v[p];  // natural order k = hl + 16 k2
+    __syncthreads();
+    // A_c[k] * W_N^(c k) -> tmp[k*N2 + c]: half-warp = 128 contiguous bytes
+    float2 *dst = a.tmp + (size_t)blk * N + c0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const int k = f + 16 * i;
+        const float2 w = __ldg(&a.tw_step[(size_t)k * N2 + c0 + hl]);
+        dst[(size_t)k * N2 + hl] = cmul(cols[hl * HW_PITCH + k], w);
+    }
+}
+
+// step 1, N1 = 32: one thread per column, the whole 32-point transform in registers; grid (N2 / 256, blocks)
+__global__ void __launch_bounds__(256) fast_cols32_kernel(const FastStepArgs a) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    const int blk = blockIdx.y;
+    const int N = a.n, N2 = a.n2;
+    const Segment sg = a.segs[a.block_seg[blk]];
+    const float2 *src = reinterpret_cast<const float2 *>(sg.iq) + (size_t)(blk - sg.block_out) * N + c;
+    float2 v[32];
+#pragma unroll
+    for (int q = 0; q < 32; q++) {
+        const int r = (q & 3) * 8 + (q >> 2);
+        v[r] = __ldg(&src[(size_t)r * N2]);
+        if (a.window) {
+            const float w = __ldg(&a.window[r * N2 + c]);
+            v[r] = __fmul2_rn(v[r], make_float2(w, w));
+        }
+    }
+    dft32(v);
+    float2 *dst = a.tmp + (size_t)blk * N + c;
+#pragma unroll
+    for (int p = 0; p < 32; p++) {
+        const int k1 = OutIdx<32>::of(p);
+        float2 x = v[p];
+        if (k1 > 0) x = cmul(x, __ldg(&a.tw_step[(size_t)k1 * N2 + c]));
+        dst[(size_t)k1 * N2] = x;
+    }
+}
+
+// step 2, N2 = 256: grid (N1 / 16, blocks), 256 threads; half-warp f owns row r0 + f (bins r0 + f + N1*k2)
+__global__ void __launch_bounds__(256) fast_rows256_kernel(const FastStepArgs a) {
+    extern __shared__ __align__(16) unsigned char sub_smem[];
+    float2 *cols = reinterpret_cast<float2 *>(sub_smem);  // [16][HW_PITCH]; reused as the (psd, dB) output tile
+    const int tid = threadIdx.x, hl = tid & 15, f = tid >> 4;
+    const int blk = blockIdx.y, r0 = blockIdx.x * 16;
+    const int N = a.n, N1 = a.n1;
+    HwTwiddle t;
+    hw_twiddle_load(t, a.tw256, hl);
+    const float2 *src = a.tmp + (size_t)blk * N + (size_t)r0 * 256;  // 16 contiguous rows
+#pragma unroll
+    for (int i = 0; i < 16; i++) cols[i * HW_PITCH + tid] = src[i * 256 + tid];
+    __syncthreads();
+    float2 v[16];
+    float2 *col = cols + f * HW_PITCH;
+    fft256_halfwarp(v, col, t, hl);
+    __syncwarp();
+    // |X|^2 (dsp/fft.go:71-73) and dB + 120 (rx/receiver.go:376-378) of X[k1 + N1*k2], k2 = hl + 16*OutIdx<16>(p)
+#pragma unroll
+    for (int p = 0; p < 16; p++) {
+        const float psd = fmaf(v[p].x, v[p].x, v[p].y * v[p].y);
+        const float db = __fadd_rn(fmaf(3.01029995663981195f, fast_log2(psd), a.db_offset), 120.0f);
+        col[hl + 16 * OutIdx<16>::of(p)] = make_float2(psd, db);
+    }
+    __syncthreads();
+    // fftshifted stores (dsp/fft.go:54-57): half-warp = 16 consecutive bins
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const int k2 = f + 16 * i;
+        const float2 o = cols[hl * HW_PITCH + k2];
+        const int kk = ((r0 + hl) + N1 * k2 + N / 2) & (N - 1);
+        a.psd[(size_t)blk * N + kk] = o.x;
+        a.spectrum[(size_t)blk * N + kk] = o.y;
+    }
+}
+
 struct LargePostArgs {
     const float *psd, *spectrum;  // [blocks][N]
     const Segment *segs;
@@ -208,9 +365,9 @@ struct LargeCumArgs {
 __global__ void __launch_bounds__(256) large_cum_kernel(const LargeCumArgs a) {
     const Segment sg = a.segs[blockIdx.y];
     const int bin = blockIdx.x * 256 + threadIdx.x;
-    float cum = sg.load_state ? a.cum_state[(size_t)sg.stream * a.n + bin] : 0.f;
+    float cum = sg.state_in >= 0 ? a.cum_state[(size_t)sg.state_in * a.n + bin] : 0.f;
     for (int b = 0; b < sg.n_blocks; b++) cum = __fadd_rn(cum, a.spectrum[(size_t)(sg.block_out + b) * a.n + bin]);
-    float *dst = (sg.flush_idx >= 0) ? a.flush_cum + (size_t)sg.flush_idx * a.n : a.cum_state + (size_t)sg.stream * a.n;
+    float *dst = (sg.flush_idx >= 0) ? a.flush_cum + (size_t)sg.flush_idx * a.n : a.cum_state + (size_t)sg.state_out * a.n;
     dst[bin] = cum;
 }
 

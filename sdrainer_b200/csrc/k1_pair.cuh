@@ -301,8 +301,8 @@ __global__ void SDR_K1P_BOUNDS k1_pair_kernel(const K1Args a) {
         // cumulation registers in dft32 output order: cum2[q] = positions p = 2q, 2q+1;
         // position p is bin kk = 2*lane + h + 64*((OutIdx<32>(p) + 16) & 31)   (fftshift, dsp/fft.go:54-57)
         float2 cum2[16];
-        if (sg.load_state) {
-            const float *cs = a.cum_state + (size_t)sg.stream * N + 2 * lane + h;
+        if (sg.state_in >= 0) {
+            const float *cs = a.cum_state + (size_t)sg.state_in * N + 2 * lane + h;
 #pragma unroll
             for (int q = 0; q < 16; q++) {
                 cum2[q].x = cs[64 * ((OutIdx<32>::of(2 * q) + 16) & 31)];
@@ -468,7 +468,7 @@ if (h == 0) pair_load_all<0, IN_I16, HAS_WINDOW>(v, IN, a.window, lane);
         nf_select();
 
         // ---- end of segment: flush or save the cumulation ----
-        float *dst = ((sg.flush_idx >= 0) ? a.flush_cum + (size_t)sg.flush_idx * N : a.cum_state + (size_t)sg.stream * N) +
+        float *dst = ((sg.flush_idx >= 0) ? a.flush_cum + (size_t)sg.flush_idx * N : a.cum_state + (size_t)sg.state_out * N) +
                      2 * lane + h;
 #pragma unroll
         for (int q = 0; q < 16; q++) {

@@ -35,8 +35,10 @@ struct Segment {
     int work;             // index into WorkParams
     int block_out;        // index of the first block in the per-block output arrays
     int flush_idx;        // >=0: this segment closes a window -> write cumulation there; -1: store to state
-    int load_state;       // 1: start from the stream's saved partial cumulation
-    int pad;
+    int state_in;         // >= 0: start from the partial cumulation saved in this row of cum_state; -1: start at 0
+    int state_out;        // row of cum_state that receives the partial cumulation when the segment does not flush.
+                          // A stream owns two rows and alternates: the segment that continues a window (reads a row)
+                          // and the one that leaves the next window open (writes a row) can share a launch.
 };
 
 struct WorkParams {
@@ -58,7 +60,7 @@ struct K1Args {
     const float2 *tw1;      // [15][M]  W_N^(j*k1)
     const float2 *tw2;      // [15][R3] W_M^(n3*k2)
     const float *window;    // [N] or nullptr
-    float *cum_state;       // [max_streams][N]
+    float *cum_state;       // [2 * max_streams][N]
     float *psd_floor;       // [blocks]
     double *variance;       // [blocks]
     float *taps;            // [blocks][tap_stride]
@@ -409,8 +411,8 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS, SDR_K1_MINB) k1_spectr
         // cumulation registers in pass-3 register order: cum2[i][q] holds positions p = 2q, 2q+1 of pair i,
         // i.e. bins kk = (c + 256*OutIdx<R3>(p) + N/2) % N with c = t + i*T
         float2 cum2[PAIRS][R3 / 2];
-        if (sg.load_state) {
-            const float *cs = a.cum_state + (size_t)sg.stream * N;
+        if (sg.state_in >= 0) {
+            const float *cs = a.cum_state + (size_t)sg.state_in * N;
 #pragma unroll
             for (int i = 0; i < PAIRS; i++)
 #pragma unroll
@@ -599,7 +601,7 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS, SDR_K1_MINB) k1_spectr
         nf_select();
 
         // ---- end of segment: flush or save the cumulation ----
-        float *dst = (sg.flush_idx >= 0) ? a.flush_cum + (size_t)sg.flush_idx * N : a.cum_state + (size_t)sg.stream * N;
+        float *dst = (sg.flush_idx >= 0) ? a.flush_cum + (size_t)sg.flush_idx * N : a.cum_state + (size_t)sg.state_out * N;
 #pragma unroll
         for (int i = 0; i < PAIRS; i++)
 #pragma unroll
@@ -607,7 +609,7 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS, SDR_K1_MINB) k1_spectr
                 dst[((t + i * T) + 256 * OutIdx<R3>::of(2 * q) + N / 2) % N] = cum2[i][q].x;
                 dst[((t + i * T) + 256 * OutIdx<R3>::of(2 * q + 1) + N / 2) % N] = cum2[i][q].y;
             }
-        // after a flush the state row is never read: the next segment of the stream has load_state = 0
+        // after a flush the state row is never read: the next segment of the stream has state_in = -1
         group_sync<T, G>(g);  // LB / PART reuse by the next segment
     }
 }

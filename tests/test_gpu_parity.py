@@ -404,3 +404,56 @@ def test_stream_reset_close_reopen_and_flags(capi):
         assert third.taps is None and (third.flush_n_peaks == 0).all()
         with pytest.raises(capi.SdrError):
             eng.submit([dict(stream=s + 1, iq=iq)])  # never opened
+
+
+def test_large_block_ragged_multi_stream_bit_identical_and_oracle(capi, oracle):
+    """large-block path (N=8192): rounds of capped segments chained through cum_state must not change a bit, whatever
+    the batching; three streams in one submit; noise floor / keys / peaks against the oracle"""
+    n, fs, nb = 8192, 768000, 230
+    rng = np.random.default_rng(81)
+    specs = [synth.StreamSpec(sample_rate=fs, block_size=n, n_blocks=nb, seed=810 + i,
+                              tones=synth.make_tones(rng, 12, n, 70, wpm_range=(18.0, 28.0))) for i in range(3)]
+    iqs = [synth.generate(sp) for sp in specs]
+    binss = [[t.bin for t in sp.tones] for sp in specs]
+    names = ("psd_noise_floor", "noise_variance", "thresholds", "taps", "keys", "flush_cum", "flush_n_peaks")
+
+    def run(chunks):
+        res = [[] for _ in specs]
+        with capi.Engine(n, max_streams=3, max_listeners=16, max_blocks_per_batch=3 * nb, max_peaks_per_flush=n // 2 + 1) as eng:
+            ss = [eng.open_stream(fs) for _ in specs]
+            pos = 0
+            for c in chunks:
+                works = [dict(stream=ss[i], iq=np.ascontiguousarray(iqs[i][pos * 2 * n:(pos + c) * 2 * n]), edge_width=70,
+                              peak_threshold=15.0, listener_bins=binss[i]) for i in range(3)]
+                o = eng.collect(eng.submit(works, capi.WANT_FLUSH_CUM))
+                for i in range(3):
+                    res[i].append({k: getattr(o, k) for k in names} | {"o": o})
+                pos += c
+        return res
+
+    def per_stream(res, i, name):
+        parts = []
+        for r in res[i]:
+            v = r[name]
+            if name.startswith("flush"):
+                fo = r["o"]
+                lo, hi = fo.work_flush_offset[i], fo.work_flush_offset[i + 1]
+                parts.append(v[lo:hi])
+            else:
+                lo, hi = r["o"].work_block_offset[i], r["o"].work_block_offset[i + 1]
+                parts.append(v[lo:hi])
+        return np.concatenate(parts, axis=0)
+
+    one = run([nb])
+    ragged = run([37, 1, 63, 100, 29])
+    for i in range(3):
+        for name in names:
+            a, b = per_stream(one, i, name), per_stream(ragged, i, name)
+            assert a.shape == b.shape and np.array_equal(a, b, equal_nan=True), (i, name)
+        r = oracle.process_stream(iqs[i], n, edge_width=70, peak_threshold=15.0, listener_bins=binss[i], sample_rate=fs)
+        pu.check_scalars(per_stream(one, i, "psd_noise_floor"), r.noise[:, 0], what="psdNoiseFloor")
+        pu.check_scalars(per_stream(one, i, "noise_variance"), r.noise[:, 1], rel=2e-3, what="noise variance")
+        keys = per_stream(one, i, "keys")[:, :len(binss[i])]
+        pu.check_keys(keys, r.taps, r.thresholds[:, 0] + r.thresholds[:, 1])
+        fc = per_stream(one, i, "flush_cum")
+        assert fc.shape == r.flush_cum.shape and np.abs(fc - r.flush_cum).max() < 0.5

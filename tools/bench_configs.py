@@ -32,12 +32,17 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
     ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--only", default=None, help="substring filter on the case name")
+    ap.add_argument("--stream-scale", type=int, default=1, help="multiply the stream count of the selected cases")
     args = ap.parse_args()
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
     dev = torch.device("cuda", 0)
     stream = torch.cuda.Stream(device=dev)
     rows = []
     for name, n, fs, nl, n_streams, nb in CASES:
+        if args.only and args.only not in name:
+            continue
+        n_streams *= args.stream_scale
         g = torch.Generator(device=dev)
         g.manual_seed(n)
         iq = torch.randn((n_streams, nb * n * 2), generator=g, device=dev, dtype=torch.float32) * 1e-4
