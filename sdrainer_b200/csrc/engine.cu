@@ -58,7 +58,11 @@ struct Slot {
     float *d_flush_cum = nullptr;
     float *d_spectrum = nullptr, *d_psd = nullptr;  // lazy (SDR_WANT_SPECTRUM)
     float *d_iq = nullptr;                          // lazy (host inputs)
-    float2 *d_tmp = nullptr;                        // large-block path: four-step intermediate
+    float2 *d_tmp = nullptr;                        // large-block path: four-step intermediate (of one round)
+    float *d_spec_round = nullptr;                  // register-resident large path: dB spectrum of one round
+    double2 *d_nf_part = nullptr;                   //   per-CTA noise-window sums
+    float *d_xto = nullptr;
+    int *d_nf_edge = nullptr;
     // pinned host mirrors
     float *h_psd_floor = nullptr;
     double *h_variance = nullptr;
@@ -91,6 +95,7 @@ struct sdr_engine {
     LargeGeom lg{};
     float2 *d_tw_sub1 = nullptr, *d_tw_sub2 = nullptr, *d_tw_n = nullptr;
     float2 *d_tw_step = nullptr;  // [k1][c] = W_N^(c k1): step-1 twiddles of the register-resident kernels
+    int round_blocks = 0;         // register-resident large path: blocks per L2-resident round (SDR_LARGE_ROUND_MB)
     float *d_window = nullptr;
     float *d_cum_state = nullptr;
     RollingState *d_rolling = nullptr;
@@ -215,6 +220,79 @@ cudaError_t launch_sub_fft_len(int len, const SubFftArgs &sa, int n_ffts, int n_
     return cudaErrorInvalidValue;
 }
 
+// register-resident large path (k1_large.cuh): per round of consecutive blocks step 1, step 2 + epilogue, cumulation;
+// once per batch the noise-floor finish
+struct LargeRound {
+    int blk0, n_blocks, seg0, n_segs;
+};
+struct LargeFastBufs {
+    float2 *tmp;
+    float *spec_round;
+    double2 *nf_part;
+    float *xto;
+    int *nf_edge;
+};
+cudaError_t launch_large_fast(const sdr_engine *e, const K1Args &a, const LargeFastBufs &lb, const int *d_block_seg,
+                              const std::vector<LargeRound> &rounds, int n_blocks, bool dbg, cudaStream_t st, int *n_launches) {
+    const int N = e->N;
+    FastStepArgs fa{};
+    fa.tmp = lb.tmp;
+    fa.spec_round = lb.spec_round;
+    fa.spectrum = dbg ? a.dbg_spectrum : nullptr;
+    fa.psd = dbg ? a.dbg_psd : nullptr;
+    fa.tw256 = e->d_tw_sub2;
+    fa.tw_step = e->d_tw_step;
+    fa.window = e->d_window;
+    fa.segs = a.segs;
+    fa.block_seg = d_block_seg;
+    fa.works = a.works;
+    fa.listener_bins = a.listener_bins;
+    fa.nf_part = lb.nf_part;
+    fa.xto = lb.xto;
+    fa.nf_edge = lb.nf_edge;
+    fa.taps = a.taps;
+    fa.tap_stride = a.tap_stride;
+    fa.n = N;
+    fa.n1 = e->lg.n1;
+    fa.n2 = e->lg.n2;
+    fa.db_offset = (float)(10.0 * log10(20.0 / ((double)N * (double)N)));
+    const size_t smem = (size_t)16 * HW_PITCH * sizeof(float2);
+    int launches = 0;
+    for (const LargeRound &r : rounds) {
+        fa.blk0 = r.blk0;
+        if (e->lg.n1 == 256) fast_cols256_kernel<<<dim3(e->lg.n2 / 16, r.n_blocks), 256, smem, st>>>(fa);
+        else fast_cols32_kernel<<<dim3(e->lg.n2 / 256, r.n_blocks), 256, 0, st>>>(fa);
+        cudaError_t rc = cudaGetLastError();
+        if (rc != cudaSuccess) return rc;
+        fast_rows256_kernel<<<dim3(e->lg.n1 / 16, r.n_blocks), 256, smem, st>>>(fa);
+        rc = cudaGetLastError();
+        if (rc != cudaSuccess) return rc;
+        RoundCumArgs ca{};
+        ca.spec_round = lb.spec_round;
+        ca.segs = a.segs + r.seg0;
+        ca.cum_state = a.cum_state;
+        ca.flush_cum = a.flush_cum;
+        ca.blk0 = r.blk0;
+        ca.n = N;
+        large_round_cum_kernel<<<dim3(N / 256, r.n_segs), 256, 0, st>>>(ca);
+        rc = cudaGetLastError();
+        if (rc != cudaSuccess) return rc;
+        launches += 3;
+    }
+    LargeFinishArgs fin{};
+    fin.nf_part = lb.nf_part;
+    fin.xto = lb.xto;
+    fin.nf_edge = lb.nf_edge;
+    fin.psd_floor = a.psd_floor;
+    fin.variance = a.variance;
+    fin.n_blocks = n_blocks;
+    fin.n_cta = e->lg.n1 / 16;
+    fin.n = N;
+    large_nf_finish_kernel<<<(n_blocks + 3) / 4, 128, 0, st>>>(fin);
+    if (n_launches) *n_launches = launches + 1;
+    return cudaGetLastError();
+}
+
 // large-block path: step 1, step 2, noise floor + taps, cumulation (k1_large.cuh)
 cudaError_t launch_large(const sdr_engine *e, const K1Args &a, float2 *d_tmp, const int *d_block_seg, int n_blocks, int n_segs,
                          cudaStream_t st) {
@@ -233,36 +311,12 @@ cudaError_t launch_large(const sdr_engine *e, const K1Args &a, float2 *d_tmp, co
     sa.n2 = e->lg.n2;
     sa.db_offset = (float)(10.0 * log10(20.0 / ((double)N * (double)N)));
     cudaError_t rc;
-    if (e->d_tw_step) {  // (32 | 256) x 256: half-warp / per-thread register transforms
-        FastStepArgs fa{};
-        fa.tmp = d_tmp;
-        fa.spectrum = a.dbg_spectrum;
-        fa.psd = a.dbg_psd;
-        fa.tw256 = e->d_tw_sub2;
-        fa.tw_step = e->d_tw_step;
-        fa.window = e->d_window;
-        fa.segs = a.segs;
-        fa.block_seg = d_block_seg;
-        fa.n = N;
-        fa.n1 = e->lg.n1;
-        fa.n2 = e->lg.n2;
-        fa.db_offset = sa.db_offset;
-        const size_t smem = (size_t)16 * HW_PITCH * sizeof(float2);
-        if (e->lg.n1 == 256) fast_cols256_kernel<<<dim3(e->lg.n2 / 16, n_blocks), 256, smem, st>>>(fa);
-        else fast_cols32_kernel<<<dim3(e->lg.n2 / 256, n_blocks), 256, 0, st>>>(fa);
-        rc = cudaGetLastError();
-        if (rc != cudaSuccess) return rc;
-        fast_rows256_kernel<<<dim3(e->lg.n1 / 16, n_blocks), 256, smem, st>>>(fa);
-        rc = cudaGetLastError();
-        if (rc != cudaSuccess) return rc;
-    } else {
-        sa.tw_sub = e->d_tw_sub1;
-        rc = launch_sub_fft_len<1>(e->lg.n1, sa, e->lg.n2, n_blocks, st);
-        if (rc != cudaSuccess) return rc;
-        sa.tw_sub = e->d_tw_sub2;
-        rc = launch_sub_fft_len<2>(e->lg.n2, sa, e->lg.n1, n_blocks, st);
-        if (rc != cudaSuccess) return rc;
-    }
+    sa.tw_sub = e->d_tw_sub1;
+    rc = launch_sub_fft_len<1>(e->lg.n1, sa, e->lg.n2, n_blocks, st);
+    if (rc != cudaSuccess) return rc;
+    sa.tw_sub = e->d_tw_sub2;
+    rc = launch_sub_fft_len<2>(e->lg.n2, sa, e->lg.n1, n_blocks, st);
+    if (rc != cudaSuccess) return rc;
     LargePostArgs pa{};
     pa.psd = a.dbg_psd;
     pa.spectrum = a.dbg_spectrum;
@@ -435,6 +489,10 @@ void free_slot(Slot &s) {
     cudaFree(s.d_flush_peaks);
     cudaFree(s.d_flush_cum);
     cudaFree(s.d_spectrum);
+    cudaFree(s.d_spec_round);
+    cudaFree(s.d_nf_part);
+    cudaFree(s.d_xto);
+    cudaFree(s.d_nf_edge);
     cudaFree(s.d_psd);
     cudaFree(s.d_iq);
     cudaFree(s.d_tmp);
@@ -482,7 +540,15 @@ int alloc_slot(sdr_engine *e, Slot &s) {
     CK(e, cudaMallocHost((void **)&s.h_flush_n_peaks, MF * sizeof(int)));
     CK(e, cudaMallocHost((void **)&s.h_flush_peaks, MF * MP * sizeof(sdr_peak)));
     CK(e, cudaMallocHost((void **)&s.h_flush_cum, MF * N * sizeof(float)));
-    if (e->large) {  // the large-block path always materialises spectrum / psd / the four-step intermediate
+    if (e->large && e->d_tw_step) {
+        // register-resident path: intermediate + dB spectrum of ONE round; spectrum / psd only on request (lazy)
+        const size_t RB = (size_t)e->round_blocks < MB ? (size_t)e->round_blocks : MB;
+        CK(e, cudaMalloc((void **)&s.d_tmp, RB * N * sizeof(float2)));
+        CK(e, cudaMalloc((void **)&s.d_spec_round, RB * N * sizeof(float)));
+        CK(e, cudaMalloc((void **)&s.d_nf_part, MB * (size_t)(e->lg.n1 / 16) * 10 * sizeof(double2)));
+        CK(e, cudaMalloc((void **)&s.d_xto, MB * 10 * sizeof(float)));
+        CK(e, cudaMalloc((void **)&s.d_nf_edge, MB * sizeof(int)));
+    } else if (e->large) {  // Stockham path: materialises spectrum / psd / the four-step intermediate of the batch
         CK(e, cudaMalloc((void **)&s.d_tmp, MB * N * sizeof(float2)));
         CK(e, cudaMalloc((void **)&s.d_spectrum, MB * N * sizeof(float)));
         CK(e, cudaMalloc((void **)&s.d_psd, MB * N * sizeof(float)));
@@ -567,6 +633,7 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
     e->tap_stride = ((cfg->max_listeners > 0 ? cfg->max_listeners : 1) + 3) / 4 * 4;
     e->max_segs = cfg->max_blocks_per_batch / SDR_CUMULATION_SIZE + 2 * cfg->max_streams + 2;
     e->max_flushes = cfg->max_blocks_per_batch / SDR_CUMULATION_SIZE + cfg->max_streams + 1;
+    if (is_large) e->max_segs += cfg->max_blocks_per_batch / 16 + 2;  // segments are also cut at round boundaries (>= 16 blocks)
     auto fail = [&](int code) {
         g_create_error = e->err;
         sdr_engine_destroy(e);
@@ -645,6 +712,16 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
                 }
             CKC(cudaMalloc((void **)&e->d_tw_step, t.size() * sizeof(float2)));
             CKC(cudaMemcpy(e->d_tw_step, t.data(), t.size() * sizeof(float2), cudaMemcpyHostToDevice));
+            // Rounds: by default the whole batch is one round.  Measured on B200 (tools/bench_configs.py --only large):
+            // rounds small enough to keep the intermediate (8N) and the dB spectrum (4N bytes per block) L2-resident
+            // (SDR_LARGE_ROUND_MB=32..96) cost more in per-launch ramp and tail than they save in HBM traffic.
+            const char *mb = getenv("SDR_LARGE_ROUND_MB");
+            if (mb && atoi(mb) > 0) {
+                e->round_blocks = (int)(((long long)atoi(mb) << 20) / ((long long)12 * e->N));
+                if (e->round_blocks < 16) e->round_blocks = 16;
+            } else {
+                e->round_blocks = cfg->max_blocks_per_batch > 16 ? cfg->max_blocks_per_batch : 16;
+            }
         }
     }
     if (cfg->window) {
@@ -902,7 +979,11 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
         s.work_flush_offset[w] = n_flushes;
         int c = si.cum_count, pos = 0, rem = wk.n_blocks;
         while (rem > 0) {
-            const int take = rem < SDR_CUMULATION_SIZE - c ? rem : SDR_CUMULATION_SIZE - c;
+            int take = rem < SDR_CUMULATION_SIZE - c ? rem : SDR_CUMULATION_SIZE - c;
+            if (e->round_blocks > 0) {  // register-resident large path: a segment never straddles a round
+                const int room = e->round_blocks - (block_off + pos) % e->round_blocks;
+                if (take > room) take = room;
+            }
             if (n_segs >= e->max_segs || n_flushes >= e->max_flushes) {
                 e->err = "internal: descriptor capacity exceeded";
                 return SDR_ESTATE;
@@ -923,7 +1004,7 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
             sg.state_in = c > 0 ? 2 * wk.stream + si.state_row : -1;
             sg.flush_idx = (c + take == SDR_CUMULATION_SIZE) ? n_flushes++ : -1;
             sg.state_out = 2 * wk.stream + (si.state_row ^ 1);
-            if (sg.flush_idx < 0) si.state_row ^= 1;  // only the last segment of a work can leave a window open
+            if (sg.flush_idx < 0) si.state_row ^= 1;  // the next segment of the stream reads what this one saves
             if (sg.flush_idx >= 0) pw.n_flushes++;
             c = (c + take) % SDR_CUMULATION_SIZE;
             pos += take;
@@ -968,6 +1049,22 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     int k1_launches = 1;
     if (!e->large) {
         CK(e, launch_k1(e, a1, dbg, e->s_compute, i16, pair_ok));
+    } else if (e->round_blocks > 0) {
+        // rounds of consecutive blocks; the segment table is in block order and no segment straddles a round
+        std::vector<LargeRound> rounds;
+        int sgi = 0;
+        for (int b0 = 0; b0 < block_off; b0 += e->round_blocks) {
+            LargeRound r;
+            r.blk0 = b0;
+            r.n_blocks = block_off - b0 < e->round_blocks ? block_off - b0 : e->round_blocks;
+            r.seg0 = sgi;
+            while (sgi < n_segs && segs[sgi].block_out < b0 + r.n_blocks) sgi++;
+            r.n_segs = sgi - r.seg0;
+            rounds.push_back(r);
+        }
+        const LargeFastBufs lb{s.d_tmp, s.d_spec_round, s.d_nf_part, s.d_xto, s.d_nf_edge};
+        CK(e, launch_large_fast(e, a1, lb, reinterpret_cast<const int *>(s.d_desc + dl.block_seg), rounds, block_off, dbg, e->s_compute,
+                                &k1_launches));
     } else {
         CK(e, launch_large(e, a1, s.d_tmp, reinterpret_cast<const int *>(s.d_desc + dl.block_seg), block_off, n_segs, e->s_compute));
         k1_launches = 4;
@@ -1113,7 +1210,11 @@ int sdr_dsp_iq_to_spectrum_and_psd(sdr_engine *e, const float *iq, int n_blocks,
     const size_t out_bytes = (size_t)n_blocks * N * sizeof(float);
     const size_t seg_bytes = align_up(sizeof(Segment) * (size_t)n_blocks, 256);
     const size_t misc = 4096;
-    const size_t large_bytes = e->large ? align_up(iq_bytes, 256) + align_up((size_t)n_blocks * sizeof(int), 256) : 0;
+    const size_t nf_part_bytes = e->round_blocks > 0 ? align_up((size_t)n_blocks * (size_t)(e->lg.n1 / 16) * 10 * sizeof(double2), 256) : 0;
+    const size_t fast_bytes = e->round_blocks > 0 ? align_up(out_bytes, 256) + nf_part_bytes + align_up((size_t)n_blocks * 10 * sizeof(float), 256) +
+                                                        align_up((size_t)n_blocks * sizeof(int), 256)
+                                                  : 0;
+    const size_t large_bytes = e->large ? align_up(iq_bytes, 256) + align_up((size_t)n_blocks * sizeof(int), 256) + fast_bytes : 0;
     size_t need = align_up(iq_bytes, 256) + 2 * align_up(out_bytes, 256) + seg_bytes + misc +
                   align_up((size_t)n_blocks * 16, 256) * 2 + align_up((size_t)N * sizeof(float), 256) + large_bytes;
     int rc = ensure_scratch(e, need);
@@ -1140,6 +1241,14 @@ int sdr_dsp_iq_to_spectrum_and_psd(sdr_engine *e, const float *iq, int n_blocks,
     float2 *d_tmp = reinterpret_cast<float2 *>(p);  // large-block path only
     p += e->large ? align_up(iq_bytes, 256) : 0;
     int *d_block_seg = reinterpret_cast<int *>(p);
+    p += e->large ? align_up((size_t)n_blocks * sizeof(int), 256) : 0;
+    float *d_spec_round = reinterpret_cast<float *>(p);
+    p += e->round_blocks > 0 ? align_up(out_bytes, 256) : 0;
+    double2 *d_nf_part = reinterpret_cast<double2 *>(p);
+    p += nf_part_bytes;
+    float *d_xto = reinterpret_cast<float *>(p);
+    p += e->round_blocks > 0 ? align_up((size_t)n_blocks * 10 * sizeof(float), 256) : 0;
+    int *d_nf_edge = reinterpret_cast<int *>(p);
     std::vector<Segment> segs(n_blocks);
     for (int b = 0; b < n_blocks; b++) {
         Segment &sg = segs[b];
@@ -1186,8 +1295,16 @@ int sdr_dsp_iq_to_spectrum_and_psd(sdr_engine *e, const float *iq, int n_blocks,
         for (int b = 0; b < n_blocks; b++) bs[b] = b;
         CK(e, cudaMemcpyAsync(d_block_seg, bs.data(), sizeof(int) * (size_t)n_blocks, cudaMemcpyHostToDevice, e->s_compute));
         CK(e, cudaStreamSynchronize(e->s_compute));  // bs is a stack-lifetime buffer
-        CK(e, launch_large(e, a, d_tmp, d_block_seg, n_blocks, n_blocks, e->s_compute));
-        e->launches += 4;
+        if (e->round_blocks > 0) {  // one round: the scratch holds the whole call
+            const LargeFastBufs lb{d_tmp, d_spec_round, d_nf_part, d_xto, d_nf_edge};
+            const std::vector<LargeRound> rounds{LargeRound{0, n_blocks, 0, n_blocks}};
+            int nl = 0;
+            CK(e, launch_large_fast(e, a, lb, d_block_seg, rounds, n_blocks, true, e->s_compute, &nl));
+            e->launches += nl;
+        } else {
+            CK(e, launch_large(e, a, d_tmp, d_block_seg, n_blocks, n_blocks, e->s_compute));
+            e->launches += 4;
+        }
     }
     CK(e, cudaMemcpyAsync(spectrum, d_spec, out_bytes, cudaMemcpyDeviceToHost, e->s_compute));
     CK(e, cudaMemcpyAsync(psd, d_psd, out_bytes, cudaMemcpyDeviceToHost, e->s_compute));

@@ -204,24 +204,45 @@ __device__ __forceinline__ void fft256_halfwarp(float2 (&v)[16], float2 *col, co
     dft16(v);
 }
 
+// The register-resident path runs in ROUNDS of consecutive blocks [blk0, blk0 + round blocks): the four-step
+// intermediate and the dB spectrum of a round are addressed relative to blk0 and sized to stay L2-resident, so HBM
+// sees the IQ once; everything a block contributes per block (noise-window partial sums, taps) is produced by the
+// row kernel, the cumulation by large_round_cum_kernel over the round's segments.
 struct FastStepArgs {
-    float2 *tmp;            // [blocks][N] four-step intermediate
-    float *spectrum, *psd;  // step 2 outputs [blocks][N]
+    float2 *tmp;            // [round blocks][N] four-step intermediate
+    float *spec_round;      // [round blocks][N] dB spectrum of the round (cumulation input)
+    float *spectrum, *psd;  // [blocks][N] or nullptr (parity / scope)
     const float2 *tw256;    // W_256^m
     const float2 *tw_step;  // [k1][c] = W_N^(c k1), k1 < N1, c < N2 (step 1)
     const float *window;
-    const Segment *segs;
-    const int *block_seg;
+    const Segment *segs;    // all segments of the batch
+    const int *block_seg;   // [blocks] segment of each block
+    const WorkParams *works;
+    const int *listener_bins;
+    double2 *nf_part;       // [blocks][N1/16][10] (sum x, sum x^2) over this CTA's bins per noise window
+    float *xto;             // [blocks][10] psd[first bin of the next window]
+    int *nf_edge;           // [blocks] edge width (for the finish kernel)
+    float *taps;
+    int tap_stride;
+    int blk0;               // first block of the round
     int n, n1, n2;
     float db_offset;
 };
+
+// number of tile elements (row k2' < rows, column f < 16; bin kk = r0 + f + n1*k2') whose bin is below `bin`
+__device__ __forceinline__ int tile_count_below(int bin, int r0, int n1, int rows) {
+    if (bin <= r0) return 0;
+    const int d = bin - r0, q = d / n1, rem = d - q * n1;
+    if (q >= rows) return rows * 16;
+    return q * 16 + (rem < 16 ? rem : 16);
+}
 
 // step 1, N1 = 256: grid (N2 / 16, blocks), 256 threads; half-warp f owns column c0 + f
 __global__ void __launch_bounds__(256) fast_cols256_kernel(const FastStepArgs a) {
     extern __shared__ __align__(16) unsigned char sub_smem[];
     float2 *cols = reinterpret_cast<float2 *>(sub_smem);  // [16][HW_PITCH]
     const int tid = threadIdx.x, hl = tid & 15, f = tid >> 4;
-    const int blk = blockIdx.y, c0 = blockIdx.x * 16;
+    const int blk = a.blk0 + blockIdx.y, c0 = blockIdx.x * 16;
     const int N = a.n, N2 = a.n2;
     const Segment sg = a.segs[a.block_seg[blk]];
     const float2 *src = reinterpret_cast<const float2 *>(sg.iq) + (size_t)(blk - sg.block_out) * N + c0;
@@ -247,7 +268,7 @@ __global__ void __launch_bounds__(256) fast_cols256_kernel(const FastStepArgs a)
     for (int p = 0; p < 16; p++) col[hl + 16 * OutIdx<16>::of(p)] = v[p];  // natural order k = hl + 16 k2
     __syncthreads();
     // A_c[k] * W_N^(c k) -> tmp[k*N2 + c]: half-warp = 128 contiguous bytes
-    float2 *dst = a.tmp + (size_t)blk * N + c0;
+    float2 *dst = a.tmp + (size_t)blockIdx.y * N + c0;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
         const int k = f + 16 * i;
@@ -259,7 +280,7 @@ __global__ void __launch_bounds__(256) fast_cols256_kernel(const FastStepArgs a)
 // step 1, N1 = 32: one thread per column, the whole 32-point transform in registers; grid (N2 / 256, blocks)
 __global__ void __launch_bounds__(256) fast_cols32_kernel(const FastStepArgs a) {
     const int c = blockIdx.x * 256 + threadIdx.x;
-    const int blk = blockIdx.y;
+    const int blk = a.blk0 + blockIdx.y;
     const int N = a.n, N2 = a.n2;
     const Segment sg = a.segs[a.block_seg[blk]];
     const float2 *src = reinterpret_cast<const float2 *>(sg.iq) + (size_t)(blk - sg.block_out) * N + c;
@@ -274,7 +295,7 @@ __global__ void __launch_bounds__(256) fast_cols32_kernel(const FastStepArgs a) 
         }
     }
     dft32(v);
-    float2 *dst = a.tmp + (size_t)blk * N + c;
+    float2 *dst = a.tmp + (size_t)blockIdx.y * N + c;
 #pragma unroll
     for (int p = 0; p < 32; p++) {
         const int k1 = OutIdx<32>::of(p);
@@ -284,16 +305,24 @@ __global__ void __launch_bounds__(256) fast_cols32_kernel(const FastStepArgs a) 
     }
 }
 
-// step 2, N2 = 256: grid (N1 / 16, blocks), 256 threads; half-warp f owns row r0 + f (bins r0 + f + N1*k2)
+// step 2 + epilogue, N2 = 256: grid (N1 / 16, round blocks), 256 threads; half-warp f owns row r0 + f, i.e. the bins
+// r0 + f + N1*k2.  Fused in: |X|^2 (dsp/fft.go:71-73), dB + 120 (rx/receiver.go:376-378), this CTA's share of the ten
+// noise-window sums of dsp.FindNoiseFloor (dsp/fft.go:215-252), the listener taps on bins it owns (rx/receiver.go:393).
 __global__ void __launch_bounds__(256) fast_rows256_kernel(const FastStepArgs a) {
     extern __shared__ __align__(16) unsigned char sub_smem[];
     float2 *cols = reinterpret_cast<float2 *>(sub_smem);  // [16][HW_PITCH]; reused as the (psd, dB) output tile
-    const int tid = threadIdx.x, hl = tid & 15, f = tid >> 4;
-    const int blk = blockIdx.y, r0 = blockIdx.x * 16;
+    __shared__ int cnt[11];
+    const int tid = threadIdx.x, hl = tid & 15, f = tid >> 4, lane = tid & 31, warp = tid >> 5;
+    const int blk = a.blk0 + blockIdx.y, r0 = blockIdx.x * 16;
     const int N = a.n, N1 = a.n1;
+    const Segment sg = a.segs[a.block_seg[blk]];
+    const WorkParams wp = a.works[sg.work];
+    const int e = wp.edge_width;
+    const int ws = nf_window_size(N, e), n_win = nf_window_count(N, e);
+    if (tid < 11) cnt[tid] = tile_count_below(e + tid * ws, r0, N1, 256);
     HwTwiddle t;
     hw_twiddle_load(t, a.tw256, hl);
-    const float2 *src = a.tmp + (size_t)blk * N + (size_t)r0 * 256;  // 16 contiguous rows
+    const float2 *src = a.tmp + (size_t)blockIdx.y * N + (size_t)r0 * 256;  // 16 contiguous rows
 #pragma unroll
     for (int i = 0; i < 16; i++) cols[i * HW_PITCH + tid] = src[i * 256 + tid];
     __syncthreads();
@@ -301,7 +330,7 @@ __global__ void __launch_bounds__(256) fast_rows256_kernel(const FastStepArgs a)
     float2 *col = cols + f * HW_PITCH;
     fft256_halfwarp(v, col, t, hl);
     __syncwarp();
-    // |X|^2 (dsp/fft.go:71-73) and dB + 120 (rx/receiver.go:376-378) of X[k1 + N1*k2], k2 = hl + 16*OutIdx<16>(p)
+    // X[k1 + N1*k2], k2 = hl + 16*OutIdx<16>(p)
 #pragma unroll
     for (int p = 0; p < 16; p++) {
         const float psd = fmaf(v[p].x, v[p].x, v[p].y * v[p].y);
@@ -310,14 +339,89 @@ __global__ void __launch_bounds__(256) fast_rows256_kernel(const FastStepArgs a)
     }
     __syncthreads();
     // fftshifted stores (dsp/fft.go:54-57): half-warp = 16 consecutive bins
+    float *spec = a.spec_round + (size_t)blockIdx.y * N;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
         const int k2 = f + 16 * i;
         const float2 o = cols[hl * HW_PITCH + k2];
         const int kk = ((r0 + hl) + N1 * k2 + N / 2) & (N - 1);
-        a.psd[(size_t)blk * N + kk] = o.x;
-        a.spectrum[(size_t)blk * N + kk] = o.y;
+        spec[kk] = o.y;
+        if (a.psd) {
+            a.psd[(size_t)blk * N + kk] = o.x;
+            a.spectrum[(size_t)blk * N + kk] = o.y;
+        }
     }
+    // noise-window sums over this CTA's bins in ascending bin order t = 16*k2' + f (k2' = fftshifted k2):
+    // float64 sums of float32 values as in the reference
+    for (int w = warp; w < 10; w += 8) {
+        double a1 = 0.0, a2 = 0.0;
+        for (int i = cnt[w] + lane; i < cnt[w + 1]; i += 32) {
+            const double x = (double)cols[(i & 15) * HW_PITCH + (((i >> 4) + 128) & 255)].x;
+            a1 += x;
+            a2 = fma(x, x, a2);
+        }
+        a1 = warp_sum(a1);
+        a2 = warp_sum(a2);
+        if (lane == 0) a.nf_part[((size_t)blk * gridDim.x + blockIdx.x) * 10 + w] = make_double2(a1, a2);
+    }
+    if (tid < n_win) {  // x_to = psd[e + (w+1)*ws] (dsp/fft.go:238-243) if this CTA owns that bin
+        const int k = (e + (tid + 1) * ws - N / 2) & (N - 1);
+        const int k1 = k & (N1 - 1);
+        if (k1 >= r0 && k1 < r0 + 16) a.xto[(size_t)blk * 10 + tid] = cols[(k1 - r0) * HW_PITCH + k / N1].x;
+    }
+    if (blockIdx.x == 0 && tid == 0) a.nf_edge[blk] = e;
+    const int *lbins = a.listener_bins + wp.listener_off;
+    for (int l = tid; l < wp.n_listeners; l += 256) {
+        const int k = (__ldg(&lbins[l]) - N / 2) & (N - 1);
+        const int k1 = k & (N1 - 1);
+        if (k1 >= r0 && k1 < r0 + 16) a.taps[(size_t)blk * a.tap_stride + l] = cols[(k1 - r0) * HW_PITCH + k / N1].y;
+    }
+}
+
+struct LargeFinishArgs {
+    const double2 *nf_part;
+    const float *xto;
+    const int *nf_edge;
+    float *psd_floor;
+    double *variance;
+    int n_blocks, n_cta, n;
+};
+
+// one warp per block: fixed-order sum of the per-CTA window sums, then dsp.FindNoiseFloor's selection
+__global__ void __launch_bounds__(128) large_nf_finish_kernel(const LargeFinishArgs a) {
+    const int blk = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (blk >= a.n_blocks) return;
+    const int e = a.nf_edge[blk];
+    const int ws = nf_window_size(a.n, e), n_win = nf_window_count(a.n, e);
+    double s1 = 0.0, s2 = 0.0, xt = 0.0;
+    if (lane < n_win) {
+        for (int c = 0; c < a.n_cta; c++) {
+            const double2 p = a.nf_part[((size_t)blk * a.n_cta + c) * 10 + lane];
+            s1 += p.x;
+            s2 += p.y;
+        }
+        xt = (double)a.xto[(size_t)blk * 10 + lane];
+    }
+    nf_select_variance(s1, s2, xt, ws, n_win, lane, &a.psd_floor[blk], &a.variance[blk]);
+}
+
+struct RoundCumArgs {
+    const float *spec_round;  // [round blocks][N]
+    const Segment *segs;      // segments of this round
+    float *cum_state;
+    float *flush_cum;
+    int blk0, n;
+};
+
+// grid (N / 256, segments of the round): thread = bin, blocks added in order (sequential float32, rx/receiver.go:404-407)
+__global__ void __launch_bounds__(256) large_round_cum_kernel(const RoundCumArgs a) {
+    const Segment sg = a.segs[blockIdx.y];
+    const int bin = blockIdx.x * 256 + threadIdx.x;
+    float cum = sg.state_in >= 0 ? a.cum_state[(size_t)sg.state_in * a.n + bin] : 0.f;
+    const float *sp = a.spec_round + (size_t)(sg.block_out - a.blk0) * a.n + bin;
+    for (int b = 0; b < sg.n_blocks; b++) cum = __fadd_rn(cum, sp[(size_t)b * a.n]);
+    float *dst = (sg.flush_idx >= 0) ? a.flush_cum + (size_t)sg.flush_idx * a.n : a.cum_state + (size_t)sg.state_out * a.n;
+    dst[bin] = cum;
 }
 
 struct LargePostArgs {

@@ -406,9 +406,15 @@ def test_stream_reset_close_reopen_and_flags(capi):
             eng.submit([dict(stream=s + 1, iq=iq)])  # never opened
 
 
-def test_large_block_ragged_multi_stream_bit_identical_and_oracle(capi, oracle):
-    """large-block path (N=8192): rounds of capped segments chained through cum_state must not change a bit, whatever
-    the batching; three streams in one submit; noise floor / keys / peaks against the oracle"""
+@pytest.mark.parametrize("round_mb", [None, "1"])
+def test_large_block_ragged_multi_stream_bit_identical_and_oracle(capi, oracle, round_mb, monkeypatch):
+    """large-block path (N=8192): the cumulation carried through cum_state must not change a bit, whatever the
+    batching -- also when the batch runs as many small rounds (SDR_LARGE_ROUND_MB=1: 16 blocks per round, segments cut
+    at round boundaries); three streams in one submit; noise floor / keys / cumulation against the oracle"""
+    if round_mb is None:
+        monkeypatch.delenv("SDR_LARGE_ROUND_MB", raising=False)
+    else:
+        monkeypatch.setenv("SDR_LARGE_ROUND_MB", round_mb)
     n, fs, nb = 8192, 768000, 230
     rng = np.random.default_rng(81)
     specs = [synth.StreamSpec(sample_rate=fs, block_size=n, n_blocks=nb, seed=810 + i,
