@@ -243,7 +243,9 @@ int sdr_goertzel_process_iq(sdr_goertzel_bank *b, const float *iq, int mem, int 
         GCK(b, cudaMalloc((void **)&b->d_twiddle, (size_t)N * sizeof(float2)));
         GCK(b, cudaMemcpy(b->d_twiddle, tw.data(), (size_t)N * sizeof(float2), cudaMemcpyHostToDevice));
         b->twiddle_n = N;
-        GCK(b, cudaFuncSetAttribute(goertzel_iq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        GCK(b, cudaFuncSetAttribute(goertzel_iq_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+        GCK(b, cudaFuncSetAttribute(goertzel_iq_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+        GCK(b, cudaFuncSetAttribute(goertzel_iq_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
     }
     const float *d_iq = iq;
     const size_t iq_floats = (size_t)n_blocks * 2 * N;
@@ -286,8 +288,16 @@ int sdr_goertzel_process_iq(sdr_goertzel_bank *b, const float *iq, int mem, int 
     a.n_blocks = n_blocks;
     a.n_bins = n_bins;
     a.db_offset = (float)(10.0 * log10(20.0 / ((double)N * (double)N)));
-    int grid = n_blocks < 4 * b->sm_count ? n_blocks : 4 * b->sm_count;
-    goertzel_iq_kernel<<<grid, K3_THREADS, (size_t)N * 8, b->stream>>>(a);
+    // listeners per lane: 32 * LPT listeners per pass over the staged block
+    const int lpt = n_bins <= 32 ? 1 : n_bins <= 64 ? 2 : 4;
+    const size_t smem = (size_t)N * 8 + (size_t)(K3_THREADS / 32) * 32 * lpt * sizeof(float2);
+    int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    const int grid = n_blocks < per_sm * b->sm_count ? n_blocks : per_sm * b->sm_count;
+    if (lpt == 1) goertzel_iq_kernel<1><<<grid, K3_THREADS, smem, b->stream>>>(a);
+    else if (lpt == 2) goertzel_iq_kernel<2><<<grid, K3_THREADS, smem, b->stream>>>(a);
+    else goertzel_iq_kernel<4><<<grid, K3_THREADS, smem, b->stream>>>(a);
     GCK(b, cudaGetLastError());
     GCK(b, cudaMemcpyAsync(out_db, b->d_out, out_n * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
     GCK(b, cudaStreamSynchronize(b->stream));

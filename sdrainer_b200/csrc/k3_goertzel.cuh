@@ -12,7 +12,8 @@
 //     bin-centre frequency equals that DFT bin, so each (block, listener) evaluates
 //     X[k] = sum_n x[n] W_N^(nk) directly with table twiddles (an fp32 Goertzel recurrence is numerically
 //     unsafe at long N / low omega) and projects it to dB exactly like K1 (rx/receiver.go:376-378,393).
-//     The block is staged once in shared memory by a TMA bulk copy and shared by all listeners.
+//     The block is staged once in shared memory by a TMA bulk copy and shared by all listeners; the twiddle is a
+//     rotating phasor re-synchronised from the table every 32 samples (see goertzel_iq_kernel).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -112,13 +113,44 @@ struct GoertzelIqArgs {
 };
 
 constexpr int K3_THREADS = 256;
+constexpr int K3_CHUNK = 32;  // samples between two table re-synchronisations of the rotating twiddle
 
-// one CTA per block; dynamic smem = 8N bytes (block) ; twiddles come from global/L1
+// One CTA per block (persistent over blocks); the block is staged ONCE in shared memory by a TMA bulk copy and
+// shared by all listeners.  Work split: lane = listener (LPT listeners per lane, 32*LPT per pass), warp = sample
+// chunk.  Per sample the lane reads x[n] as a shared-memory broadcast and, per listener, does acc += x * w and
+// w *= W_N^k in packed f32x2 arithmetic (4 instructions); w is re-read from the fp64-rounded table every K3_CHUNK
+// samples, which bounds the drift of the recurrence at ~K3_CHUNK * 2^-24 (a free-running fp32 Goertzel / phasor
+// recurrence is numerically unsafe at long N).  Dynamic smem = 8N bytes (block) + 8 * 32 * LPT * 8 (warp partials).
+// ACT of the lane's LPT listener chains are live: acc[i] += x[n] * W_N^(k_i n) over this warp's sample chunks
+template <int LPT, int ACT>
+__device__ __forceinline__ void k3_accumulate(const float2 *X, const float2 *__restrict__ twiddle, const int (&k)[LPT],
+                                              const float2 (&step)[LPT], float2 (&acc)[LPT], int warp, int n_chunks, int N) {
+    for (int c = warp; c < n_chunks; c += K3_THREADS / 32) {
+        const int n0 = c * K3_CHUNK;
+        float2 w[ACT];
+#pragma unroll
+        for (int i = 0; i < ACT; i++) w[i] = __ldg(&twiddle[(k[i] * n0) & (N - 1)]);
+#pragma unroll
+        for (int j = 0; j < K3_CHUNK; j++) {
+            const float2 x = X[n0 + j];  // broadcast
+#pragma unroll
+            for (int i = 0; i < ACT; i++) {
+                // acc += x * w ; w *= step
+                acc[i] = __ffma2_rn(make_float2(x.x, x.x), w[i], acc[i]);
+                acc[i] = __ffma2_rn(make_float2(x.y, x.y), make_float2(-w[i].y, w[i].x), acc[i]);
+                w[i] = cmul(w[i], step[i]);
+            }
+        }
+    }
+}
+
+template <int LPT>
 __global__ void __launch_bounds__(K3_THREADS) goertzel_iq_kernel(const GoertzelIqArgs a) {
     extern __shared__ __align__(128) unsigned char k3_smem[];
     __shared__ __align__(8) uint64_t bar;
     float2 *X = reinterpret_cast<float2 *>(k3_smem);
     const int N = a.n;
+    float2 *RED = reinterpret_cast<float2 *>(k3_smem + (size_t)8 * N);  // [warp][32 * LPT]
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     constexpr int NW = K3_THREADS / 32;
     if (threadIdx.x == 0) {
@@ -127,6 +159,7 @@ __global__ void __launch_bounds__(K3_THREADS) goertzel_iq_kernel(const GoertzelI
     }
     __syncthreads();
     uint32_t phase = 0;
+    const int n_chunks = N / K3_CHUNK;
     for (int blk = blockIdx.x; blk < a.n_blocks; blk += gridDim.x) {
         if (threadIdx.x == 0) {
             fence_proxy_async();
@@ -135,33 +168,45 @@ __global__ void __launch_bounds__(K3_THREADS) goertzel_iq_kernel(const GoertzelI
         }
         mbar_wait(&bar, phase);
         phase ^= 1u;
-        for (int l = warp; l < a.n_bins; l += NW) {
-            const int kk = a.bins[l];
-            const int k = (kk + N / 2) & (N - 1);  // undo dsp/fft.go:54-57
-            float re = 0.f, im = 0.f;
-            int idx = (lane * k) & (N - 1);
-            const int step = (32 * k) & (N - 1);
-            for (int n = lane; n < N; n += 32) {
-                const float2 x = X[n];
-                const float2 w = __ldg(&a.twiddle[idx]);
-                re = fmaf(x.x, w.x, re);
-                re = fmaf(-x.y, w.y, re);
-                im = fmaf(x.x, w.y, im);
-                im = fmaf(x.y, w.x, im);
-                idx = (idx + step) & (N - 1);
+        for (int g0 = 0; g0 < a.n_bins; g0 += 32 * LPT) {
+            // listeners per lane in this pass (uniform): the last pass runs only as many chains as it has listeners
+            const int lpt_here = (a.n_bins - g0 + 31) / 32 < LPT ? (a.n_bins - g0 + 31) / 32 : LPT;
+            int k[LPT];
+            float2 step[LPT], acc[LPT];
+#pragma unroll
+            for (int i = 0; i < LPT; i++) {
+                const int l = g0 + lane + 32 * i;
+                const int kk = l < a.n_bins ? __ldg(&a.bins[l]) : 0;
+                k[i] = (kk + N / 2) & (N - 1);  // undo dsp/fft.go:54-57
+                step[i] = __ldg(&a.twiddle[k[i]]);
+                acc[i] = make_float2(0.f, 0.f);
+            }
+            // chunk loop specialised on the number of active chains (uniform per pass)
+            switch (lpt_here) {
+                case 1: k3_accumulate<LPT, 1>(X, a.twiddle, k, step, acc, warp, n_chunks, N); break;
+                case 2: k3_accumulate<LPT, (LPT >= 2 ? 2 : LPT)>(X, a.twiddle, k, step, acc, warp, n_chunks, N); break;
+                case 3: k3_accumulate<LPT, (LPT >= 3 ? 3 : LPT)>(X, a.twiddle, k, step, acc, warp, n_chunks, N); break;
+                default: k3_accumulate<LPT, LPT>(X, a.twiddle, k, step, acc, warp, n_chunks, N); break;
             }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                re += __shfl_xor_sync(0xffffffffu, re, o);
-                im += __shfl_xor_sync(0xffffffffu, im, o);
+            for (int i = 0; i < LPT; i++) RED[warp * 32 * LPT + lane + 32 * i] = acc[i];
+            __syncthreads();
+            for (int q = threadIdx.x; q < 32 * LPT; q += K3_THREADS) {
+                const int l = g0 + q;
+                if (l < a.n_bins) {
+                    float re = 0.f, im = 0.f;
+#pragma unroll
+                    for (int wq = 0; wq < NW; wq++) {
+                        re += RED[wq * 32 * LPT + q].x;
+                        im += RED[wq * 32 * LPT + q].y;
+                    }
+                    const float psd = fmaf(re, re, im * im);
+                    const float t = fmaf(3.01029995663981195f, __log2f(psd), a.db_offset);
+                    a.out_db[(size_t)blk * a.n_bins + l] = __fadd_rn(t, 120.0f);
+                }
             }
-            if (lane == 0) {
-                const float psd = fmaf(re, re, im * im);
-                const float t = fmaf(3.01029995663981195f, __log2f(psd), a.db_offset);
-                a.out_db[(size_t)blk * a.n_bins + l] = __fadd_rn(t, 120.0f);
-            }
+            __syncthreads();  // RED is rewritten by the next listener group; X by the next bulk copy
         }
-        __syncthreads();  // all warps done with X before the next bulk copy lands
     }
 }
 

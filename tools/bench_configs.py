@@ -109,20 +109,24 @@ def goertzel_stress():
     """config 3 'Goertzel bank stress': 200 listeners on 768 kS/s, N=8192 blocks through the IQ Goertzel bank (K3)
     next to the FFT-tap path that serves the same listeners."""
     import time
-    n, nl, nb = 8192, 200, 2048
+    n, nl, nb = 8192, 200, 16384
     dev = torch.device("cuda", 0)
     iq = torch.randn(nb * n * 2, device=dev, dtype=torch.float32) * 1e-4
     bins = np.sort(np.random.default_rng(3).choice(np.arange(80, n - 80), size=nl, replace=False)).astype(np.int32)
     bank = capi.GoertzelBank([700.0], 48000)
-    bank.process_iq(iq.data_ptr(), n, bins, n_blocks=64)  # warm-up (table upload)
+    bank.process_iq(iq.data_ptr(), n, bins, n_blocks=nb)  # warm-up (table upload, output buffers)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    bank.process_iq(iq.data_ptr(), n, bins, n_blocks=nb)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    dts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        bank.process_iq(iq.data_ptr(), n, bins, n_blocks=nb)
+        torch.cuda.synchronize()
+        dts.append(time.perf_counter() - t0)
+    dt = min(dts)
     row = {"config": "cfg3 Goertzel bank stress (K3 IQ bank, 200 listeners, N=8192)", "blocks": nb,
            "msamples_per_s": nb * n / dt / 1e6, "listener_msamples_per_s": nb * n * nl / dt / 1e6,
-           "gflops": 8.0 * nb * n * nl / dt / 1e9, "note": "includes the D2H of the 200 dB values per block; "
+           "gflops": 8.0 * nb * n * nl / dt / 1e9, "fp32_peak_frac": 8.0 * nb * n * nl / dt / 72e12,
+           "note": "wall clock of one call, includes the D2H of the 200 dB values per block; "
            "compute-bound (200 flop/byte): reported against fp32 throughput, not HBM"}
     print(json.dumps(row))
     return row
