@@ -238,7 +238,7 @@ __device__ __forceinline__ int tile_count_below(int bin, int r0, int n1, int row
 }
 
 // step 1, N1 = 256: grid (N2 / 16, blocks), 256 threads; half-warp f owns column c0 + f
-__global__ void __launch_bounds__(256) fast_cols256_kernel(const FastStepArgs a) {
+__global__ void __launch_bounds__(256, 3) fast_cols256_kernel(const FastStepArgs a) {
     extern __shared__ __align__(16) unsigned char sub_smem[];
     float2 *cols = reinterpret_cast<float2 *>(sub_smem);  // [16][HW_PITCH]
     const int tid = threadIdx.x, hl = tid & 15, f = tid >> 4;
