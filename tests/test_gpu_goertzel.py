@@ -105,3 +105,23 @@ def test_iq_bank_equals_fft_bin(capi, oracle, n):
             s = eng.open_stream(spec.sample_rate)
             k1 = eng.collect(eng.submit([dict(stream=s, iq=iq, listener_bins=bins)]))
         assert np.abs(got[strong] - k1.taps[:, :len(bins)][strong]).max() < 1e-3
+
+
+@pytest.mark.parametrize("n_bins", [1, 31, 32, 33, 64, 65, 96, 97, 128, 129, 200, 257])
+def test_iq_bank_listener_counts_around_the_pass_boundaries(capi, n_bins):
+    """goertzel_iq_kernel<LPT>: 32*LPT listeners per pass, the last pass runs 1..LPT chains -- every listener must get the
+    DFT bin of ITS frequency whatever the count (checked against numpy's float64 FFT of the same float32 block)"""
+    n, nb = 1024, 3
+    rng = np.random.default_rng(n_bins)
+    iq = (rng.standard_normal(nb * 2 * n) * 1e-2).astype(np.float32)
+    bins = rng.choice(np.arange(n), size=n_bins, replace=False).astype(np.int32)
+    bank = capi.GoertzelBank([700.0], 48000)
+    got = bank.process_iq(iq, n, bins)
+    x = iq.astype(np.float64).reshape(nb, n, 2)
+    spec = np.fft.fftshift(np.fft.fft(x[..., 0] + 1j * x[..., 1], axis=1), axes=1)
+    psd = np.abs(spec) ** 2
+    want = 10 * np.log10(20 * psd[:, bins] / n ** 2) + 120
+    assert got.shape == want.shape
+    lin_g, lin_w = 10 ** (got.astype(np.float64) / 10), 10 ** (want / 10)
+    assert (np.abs(lin_g - lin_w) <= 2e-5 * lin_w.max(axis=1, keepdims=True)).all()
+    assert np.abs(got - want)[lin_w > 0.05 * lin_w.max()].max() < 2e-3

@@ -463,3 +463,28 @@ def test_large_block_ragged_multi_stream_bit_identical_and_oracle(capi, oracle, 
         pu.check_keys(keys, r.taps, r.thresholds[:, 0] + r.thresholds[:, 1])
         fc = per_stream(one, i, "flush_cum")
         assert fc.shape == r.flush_cum.shape and np.abs(fc - r.flush_cum).max() < 0.5
+
+
+@pytest.mark.parametrize("n", [8192, 16384, 32768, 65536])
+def test_large_block_parseval_linearity_and_tone(capi, n):
+    """size-independent properties of every large-block shape (register-resident 32x256 / 256x256 kernels and the
+    Stockham kernels for 16384 / 32768): sum(psd) = N*sum|x|^2, psd(4x) = 16 psd(x) exactly, a bin-centred tone lands
+    on its fftshifted bin (dsp/fft.go:54-57)"""
+    rng = np.random.default_rng(n)
+    nb = 3
+    iq = (rng.standard_normal(nb * 2 * n).astype(np.float32) * np.float32(1e-3))
+    k = n // 3 + 7
+    t = np.arange(n)
+    tone = np.exp(2j * np.pi * k * t / n)
+    iq[0:2 * n:2] = tone.real.astype(np.float32)
+    iq[1:2 * n:2] = tone.imag.astype(np.float32)
+    with capi.Engine(n, max_blocks_per_batch=4) as eng:
+        _, psd = eng.iq_to_spectrum_and_psd(iq)
+        _, psd4 = eng.iq_to_spectrum_and_psd(iq * np.float32(4.0))
+    energy = (iq.astype(np.float64) ** 2).reshape(nb, -1).sum(axis=1)
+    assert np.abs(psd.astype(np.float64).sum(axis=1) / (n * energy) - 1).max() < 1e-5
+    assert np.array_equal(psd4, psd * np.float32(16.0))
+    kk = (k + n // 2) % n
+    assert int(np.argmax(psd[0])) == kk
+    assert abs(psd[0, kk] / float(n) ** 2 - 1.0) < 1e-5
+    assert np.delete(psd[0], kk).max() < 1e-6 * psd[0, kk]
