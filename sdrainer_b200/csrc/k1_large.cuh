@@ -179,13 +179,9 @@ __device__ __forceinline__ void hw_twiddle_load(HwTwiddle &t, const float2 *__re
 #pragma unroll
     for (int k = 1; k < 16; k++) t.w[k - 1] = __ldg(&tw256[(hl * k) & 255]);
 }
-// col: this FFT's 256 inputs in natural order (pitch HW_PITCH); all 32 lanes of the warp call it (two FFTs per warp)
-__device__ __forceinline__ void fft256_halfwarp(float2 (&v)[16], float2 *col, const HwTwiddle &t, int hl) {
-#pragma unroll
-    for (int q = 0; q < 16; q++) {
-        const int n1 = (q & 3) * 4 + (q >> 2);
-        v[n1] = col[16 * n1 + hl];
-    }
+// v[n1] = x[16 n1 + hl] on entry; col: 16*17 complex slots of scratch for the transpose; all 32 lanes of the warp
+// call it (two FFTs per warp)
+__device__ __forceinline__ void fft256_halfwarp_regs(float2 (&v)[16], float2 *col, const HwTwiddle &t, int hl) {
     dft16(v);
 #pragma unroll
     for (int p = 0; p < 16; p++) {
@@ -208,6 +204,17 @@ __device__ __forceinline__ void fft256_halfwarp(float2 (&v)[16], float2 *col, co
 // intermediate and the dB spectrum of a round are addressed relative to blk0 and sized to stay L2-resident, so HBM
 // sees the IQ once; everything a block contributes per block (noise-window partial sums, taps) is produced by the
 // row kernel, the cumulation by large_round_cum_kernel over the round's segments.
+// col: this FFT's 256 inputs in natural order (pitch HW_PITCH), overwritten by the transpose
+__device__ __forceinline__ void fft256_halfwarp(float2 (&v)[16], float2 *col, const HwTwiddle &t, int hl) {
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        const int n1 = (q & 3) * 4 + (q >> 2);
+        v[n1] = col[16 * n1 + hl];
+    }
+    __syncwarp();  // every lane has read its inputs: the column may be overwritten by the transpose
+    fft256_halfwarp_regs(v, col, t, hl);
+}
+
 struct FastStepArgs {
     float2 *tmp;            // [round blocks][N] four-step intermediate
     float *spec_round;      // [round blocks][N] dB spectrum of the round (cumulation input)
@@ -322,13 +329,17 @@ __global__ void __launch_bounds__(256) fast_rows256_kernel(const FastStepArgs a)
     if (tid < 11) cnt[tid] = tile_count_below(e + tid * ws, r0, N1, 256);
     HwTwiddle t;
     hw_twiddle_load(t, a.tw256, hl);
-    const float2 *src = a.tmp + (size_t)blockIdx.y * N + (size_t)r0 * 256;  // 16 contiguous rows
-#pragma unroll
-    for (int i = 0; i < 16; i++) cols[i * HW_PITCH + tid] = src[i * 256 + tid];
-    __syncthreads();
+    // row r0 + f straight into the registers of its half-warp: lane hl takes x[16 n1 + hl], 128 contiguous bytes
+    // per half-warp and n1 (no shared-memory staging of the input)
+    const float2 *src = a.tmp + (size_t)blockIdx.y * N + (size_t)(r0 + f) * 256 + hl;
     float2 v[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        const int n1 = (q & 3) * 4 + (q >> 2);
+        v[n1] = src[16 * n1];
+    }
     float2 *col = cols + f * HW_PITCH;
-    fft256_halfwarp(v, col, t, hl);
+    fft256_halfwarp_regs(v, col, t, hl);
     __syncwarp();
     // X[k1 + N1*k2], k2 = hl + 16*OutIdx<16>(p)
 #pragma unroll
