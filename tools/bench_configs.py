@@ -4,6 +4,8 @@
 Not the contract bench (that is bench.py on configs[1]); this reports Msamples/s and the HBM-roofline fraction of
 the dominant kernel stage for the other block sizes so that DESIGN.md can quote them.
 Usage: python tools/bench_configs.py [--out profiles/r1_all_configs.json]
+Multi-GPU (streams sharded by rank, no collective on the data path; barrier + max-over-ranks time only):
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/bench_configs.py --only cfg5
 """
 import argparse
 import json
@@ -36,7 +38,14 @@ def main():
     ap.add_argument("--stream-scale", type=int, default=1, help="multiply the stream count of the selected cases")
     args = ap.parse_args()
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
-    dev = torch.device("cuda", 0)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.Stream(device=dev)
     rows = []
     for name, n, fs, nl, n_streams, nb in CASES:
@@ -44,7 +53,7 @@ def main():
             continue
         n_streams *= args.stream_scale
         g = torch.Generator(device=dev)
-        g.manual_seed(n)
+        g.manual_seed(n + 7919 * rank)
         iq = torch.randn((n_streams, nb * n * 2), generator=g, device=dev, dtype=torch.float32) * 1e-4
         rng = np.random.default_rng(n)
         bins = [np.sort(rng.choice(np.arange(80, n - 80), size=nl, replace=False)).astype(np.int32) for _ in range(n_streams)]
@@ -57,7 +66,7 @@ def main():
                 v[:, :, 0] += 0.01 * torch.cos(ph * t)
                 v[:, :, 1] += 0.01 * torch.sin(ph * t)
         eng = capi.Engine(n, max_streams=n_streams, max_listeners=max(nl, 1), max_blocks_per_batch=n_streams * nb,
-                          max_peaks_per_flush=128, n_slots=2, cuda_stream=stream.cuda_stream)
+                          max_peaks_per_flush=128, n_slots=2, device=local_rank, cuda_stream=stream.cuda_stream)
         sids = [eng.open_stream(fs) for _ in range(n_streams)]
         per = nb * 2 * n * 4
         prepared = eng.prepare([dict(stream=sids[i], iq=iq.data_ptr() + i * per, n_blocks=nb, listener_bins=bins[i])
@@ -67,6 +76,8 @@ def main():
             eng.collect_raw(tk)
             eng.release(tk)
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k1 = []
         e0.record(stream)
@@ -84,21 +95,29 @@ def main():
             eng.release(tk)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.steps
+        if world > 1:  # whole-job time = slowest rank
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
         samples = n_streams * nb * n
         alg = (8 * n + 4 * n / 100.0 + 4 * nl + 16) * n_streams * nb
         k1_ms = float(np.mean(k1))
-        rows.append({"config": name, "block_size": n, "streams": n_streams, "listeners": nl,
-                     "batch_bytes": samples * 8, "msamples_per_s": samples / (ms * 1e-3) / 1e6, "ms_per_step": ms,
+        rows.append({"config": name, "n_gpus": world, "block_size": n, "streams_per_gpu": n_streams, "streams": n_streams * world,
+                     "listeners": nl, "batch_bytes": samples * 8, "msamples_per_s": world * samples / (ms * 1e-3) / 1e6,
+                     "ms_per_step": ms,
                      "spectral_stage_ms": k1_ms, "spectral_stage_gbs": alg / (k1_ms * 1e-3) / 1e9,
                      "hbm_roofline_frac": alg / (k1_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                     "realtime_streams": samples / (ms * 1e-3) / fs})
-        print(json.dumps(rows[-1]))
+                     "realtime_streams": world * samples / (ms * 1e-3) / fs})
+        if rank == 0:
+            print(json.dumps(rows[-1]))
         eng.close()
         del iq
         torch.cuda.empty_cache()
-    if args.out:
+    if args.out and rank == 0:
         with open(args.out, "w") as f:
             json.dump({"peak_hbm_gbs": peaks["hbm_gbs"], "rows": rows}, f, indent=1)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__" and "--goertzel" not in sys.argv:
