@@ -25,6 +25,7 @@
 #include "k1_pair.cuh"
 #include "k2_post.cuh"
 #include "k1_large.cuh"
+#include "k1_mid.cuh"
 
 using namespace sdr;
 
@@ -96,6 +97,10 @@ struct sdr_engine {
     float2 *d_tw_sub1 = nullptr, *d_tw_sub2 = nullptr, *d_tw_n = nullptr;
     float2 *d_tw_step = nullptr;  // [k1][c] = W_N^(c k1): step-1 twiddles of the register-resident kernels
     int round_blocks = 0;         // register-resident large path: blocks per L2-resident round (SDR_LARGE_ROUND_MB)
+    // N = 4096 / 8192: fused single-pass kernel (k1_mid.cuh), SDR_K1_MID=0 disables it
+    float2 *d_tw_mid = nullptr, *d_tw256m = nullptr;
+    bool k1_mid = false;
+    int k1m_grid_cap = 0;
     float *d_window = nullptr;
     float *d_cum_state = nullptr;
     RollingState *d_rolling = nullptr;
@@ -378,9 +383,42 @@ cudaError_t launch_k1_pair(const sdr_engine *e, const K1Args &a, bool dbg, cudaS
                             K1PairGeom::smem_bytes(e->k1p_stages), st);
 }
 
+template <int R1>
+const void *k1m_fn(bool dbg, bool win) {
+    if (dbg) return win ? (const void *)k1_mid_kernel<R1, true, true> : (const void *)k1_mid_kernel<R1, true, false>;
+    return win ? (const void *)k1_mid_kernel<R1, false, true> : (const void *)k1_mid_kernel<R1, false, false>;
+}
+const void *k1m_fn(int n, bool dbg, bool win) { return n == 4096 ? k1m_fn<16>(dbg, win) : k1m_fn<32>(dbg, win); }
+int k1m_smem(int n) { return n == 4096 ? K1MidGeom<16>::SMEM_BYTES : K1MidGeom<32>::SMEM_BYTES; }
+
+int k1m_grid_cap_for(int n, bool win, int sm_count) {
+    int occ = 0;
+    for (int dbg = 0; dbg < 2; dbg++) {
+        const void *fn = k1m_fn(n, dbg != 0, win);
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k1m_smem(n));
+        if (!dbg) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 256, k1m_smem(n));
+    }
+    if (occ < 1) occ = 1;
+    return occ * sm_count;
+}
+
+cudaError_t launch_k1_mid(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st) {
+    int grid = a.n_segs;
+    if (grid > e->k1m_grid_cap) {
+        const int rounds = (grid + e->k1m_grid_cap - 1) / e->k1m_grid_cap;
+        grid = (a.n_segs + rounds - 1) / rounds;
+    }
+    if (grid < 1) grid = 1;
+    K1Args args = a;
+    const float2 *tws = e->d_tw_mid, *tw256 = e->d_tw256m;
+    void *params[] = {&args, &tws, &tw256};
+    return cudaLaunchKernel(k1m_fn(e->N, dbg, a.window != nullptr), dim3(grid), dim3(256), params, k1m_smem(e->N), st);
+}
+
 // pair_ok: every work of the launch has noise windows of at least K1PairGeom::MIN_WS bins
 cudaError_t launch_k1(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st, bool i16 = false, bool pair_ok = true) {
     if (e->k1_pair && pair_ok) return launch_k1_pair(e, a, dbg, st, i16);
+    if (e->k1_mid && e->N == 4096 && !i16) return launch_k1_mid(e, a, dbg, st);
     switch (e->N) {
         case 512: return launch_k1_n<512>(e, a, dbg, st, i16);
         case 1024: return launch_k1_n<1024>(e, a, dbg, st, i16);
@@ -731,6 +769,27 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
     }
     CKC(cudaMalloc((void **)&e->d_cum_state, (size_t)2 * cfg->max_streams * e->N * sizeof(float)));
     CKC(cudaMemset(e->d_cum_state, 0, (size_t)2 * cfg->max_streams * e->N * sizeof(float)));
+    if (e->N == 4096 || e->N == 8192) {
+        const int r1 = e->N / 256;
+        std::vector<float2> t((size_t)r1 * 256), t256(256);
+        const double two_pi = 6.283185307179586476925286766559;
+        for (int k = 0; k < r1; k++)
+            for (int c = 0; c < 256; c++) {
+                const double ang = -two_pi * (double)((c * k) % e->N) / (double)e->N;
+                t[(size_t)k * 256 + c] = make_float2((float)cos(ang), (float)sin(ang));
+            }
+        for (int m = 0; m < 256; m++) {
+            const double ang = -two_pi * (double)m / 256.0;
+            t256[m] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+        CKC(cudaMalloc((void **)&e->d_tw_mid, t.size() * sizeof(float2)));
+        CKC(cudaMemcpy(e->d_tw_mid, t.data(), t.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        CKC(cudaMalloc((void **)&e->d_tw256m, t256.size() * sizeof(float2)));
+        CKC(cudaMemcpy(e->d_tw256m, t256.data(), t256.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        const char *v = getenv("SDR_K1_MID");
+        e->k1_mid = !(v && v[0] == '0');
+        if (e->k1_mid) e->k1m_grid_cap = k1m_grid_cap_for(e->N, e->d_window != nullptr, e->sm_count);
+    }
     CKC(cudaMalloc((void **)&e->d_rolling, (size_t)cfg->max_streams * sizeof(RollingState)));
     CKC(cudaMemset(e->d_rolling, 0, (size_t)cfg->max_streams * sizeof(RollingState)));
     e->streams.resize(cfg->max_streams);
@@ -768,6 +827,8 @@ void sdr_engine_destroy(sdr_engine *e) {
     cudaFree(e->d_tw2);
     cudaFree(e->d_twp);
     cudaFree(e->d_tw_step);
+    cudaFree(e->d_tw_mid);
+    cudaFree(e->d_tw256m);
     cudaFree(e->d_tw_sub1);
     cudaFree(e->d_tw_sub2);
     cudaFree(e->d_tw_n);
@@ -1049,6 +1110,9 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     int k1_launches = 1;
     if (!e->large) {
         CK(e, launch_k1(e, a1, dbg, e->s_compute, i16, pair_ok));
+    } else if (e->k1_mid && e->N == 8192 && block_off <= e->round_blocks && n_segs >= 2 * e->sm_count) {
+        // enough segments to fill the GPU with segment-sequential CTAs: fused single pass (k1_mid.cuh)
+        CK(e, launch_k1_mid(e, a1, dbg, e->s_compute));
     } else if (e->round_blocks > 0) {
         // rounds of consecutive blocks; the segment table is in block order and no segment straddles a round
         std::vector<LargeRound> rounds;

@@ -25,8 +25,11 @@ CASES = [
     ("N=1024 L=25", 1024, 96000, 25, 2 * 148 * 12, 100),
     ("cfg2/cfg4 192 kS/s N=2048 L=50", 2048, 192000, 50, 148 * 12, 100),
     ("N=4096 L=100", 4096, 384000, 100, 148 * 4, 100),
-    ("cfg3 768 kS/s N=8192 L=200 (large-block path)", 8192, 768000, 200, 64, 100),
-    ("cfg5 24.576 MS/s N=65536 peak scan (large-block path)", 65536, 24576000, 0, 8, 100),
+    # >= 2 GiB of blocks per batch like the other shapes; 512 streams also give the fused N = 8192
+    # kernel (k1_mid.cuh) its >= 2 segments per SM, below that the engine takes the block-parallel two-kernel path
+    ("cfg3 768 kS/s N=8192 L=200 (fused k1_mid)", 8192, 768000, 200, 512, 100),
+    ("cfg3 768 kS/s N=8192 L=200, 64 streams (two-kernel large-block path)", 8192, 768000, 200, 64, 100),
+    ("cfg5 24.576 MS/s N=65536 peak scan (large-block path)", 65536, 24576000, 0, 64, 100),
 ]
 
 
