@@ -26,6 +26,7 @@
 #include "k2_post.cuh"
 #include "k1_large.cuh"
 #include "k1_mid.cuh"
+#include "k1_warp.cuh"
 
 using namespace sdr;
 
@@ -97,6 +98,10 @@ struct sdr_engine {
     float2 *d_tw_sub1 = nullptr, *d_tw_sub2 = nullptr, *d_tw_n = nullptr;
     float2 *d_tw_step = nullptr;  // [k1][c] = W_N^(c k1): step-1 twiddles of the register-resident kernels
     int round_blocks = 0;         // register-resident large path: blocks per L2-resident round (SDR_LARGE_ROUND_MB)
+    // N = 512: warp-per-block kernel (k1_warp.cuh), SDR_K1_WARP=0 selects the three-pass kernel
+    float2 *d_tw512 = nullptr, *d_tw256w = nullptr;
+    bool k1_warp = false;
+    int k1w_grid_cap = 0;
     // N = 4096 / 8192: fused single-pass kernel (k1_mid.cuh), SDR_K1_MID=0 disables it
     float2 *d_tw_mid = nullptr, *d_tw256m = nullptr;
     bool k1_mid = false;
@@ -383,6 +388,33 @@ cudaError_t launch_k1_pair(const sdr_engine *e, const K1Args &a, bool dbg, cudaS
                             K1PairGeom::smem_bytes(e->k1p_stages), st);
 }
 
+const void *k1w_fn(bool dbg, bool win, bool i16) {
+    if (i16) return dbg ? (const void *)k1_warp_kernel<true, false, true> : (const void *)k1_warp_kernel<false, false, true>;
+    if (dbg) return win ? (const void *)k1_warp_kernel<true, true, false> : (const void *)k1_warp_kernel<true, false, false>;
+    return win ? (const void *)k1_warp_kernel<false, true, false> : (const void *)k1_warp_kernel<false, false, false>;
+}
+int k1w_grid_cap_for(bool win, int sm_count) {
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1w_fn(false, win, false), 32 * K1WarpGeom::WARPS, K1WarpGeom::SMEM_BYTES);
+    if (occ < 1) occ = 1;
+    return occ * sm_count;
+}
+cudaError_t launch_k1_warp(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st, bool i16) {
+    // one warp per segment, WARPS warps per CTA; whole rounds of the resident grid
+    const int need = (a.n_segs + K1WarpGeom::WARPS - 1) / K1WarpGeom::WARPS;
+    int grid = need;
+    if (need > e->k1w_grid_cap) {
+        const int rounds = (need + e->k1w_grid_cap - 1) / e->k1w_grid_cap;
+        grid = (need + rounds - 1) / rounds;
+    }
+    if (grid < 1) grid = 1;
+    K1Args args = a;
+    const float2 *t512 = e->d_tw512, *t256 = e->d_tw256w;
+    void *params[] = {&args, &t512, &t256};
+    return cudaLaunchKernel(k1w_fn(dbg, a.window != nullptr, i16), dim3(grid), dim3(32 * K1WarpGeom::WARPS), params,
+                            K1WarpGeom::SMEM_BYTES, st);
+}
+
 template <int R1>
 const void *k1m_fn(bool dbg, bool win) {
     if (dbg) return win ? (const void *)k1_mid_kernel<R1, true, true> : (const void *)k1_mid_kernel<R1, true, false>;
@@ -416,9 +448,12 @@ cudaError_t launch_k1_mid(const sdr_engine *e, const K1Args &a, bool dbg, cudaSt
 }
 
 // pair_ok: every work of the launch has noise windows of at least K1PairGeom::MIN_WS bins
-cudaError_t launch_k1(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st, bool i16 = false, bool pair_ok = true) {
+// warp_ok: N = 512 and every work has noise windows of at least K1WarpGeom::MIN_WS bins
+cudaError_t launch_k1(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st, bool i16 = false, bool pair_ok = true,
+                      bool warp_ok = true) {
     if (e->k1_pair && pair_ok) return launch_k1_pair(e, a, dbg, st, i16);
     if (e->k1_mid && e->N == 4096 && !i16) return launch_k1_mid(e, a, dbg, st);
+    if (e->k1_warp && warp_ok) return launch_k1_warp(e, a, dbg, st, i16);
     switch (e->N) {
         case 512: return launch_k1_n<512>(e, a, dbg, st, i16);
         case 1024: return launch_k1_n<1024>(e, a, dbg, st, i16);
@@ -769,6 +804,21 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
     }
     CKC(cudaMalloc((void **)&e->d_cum_state, (size_t)2 * cfg->max_streams * e->N * sizeof(float)));
     CKC(cudaMemset(e->d_cum_state, 0, (size_t)2 * cfg->max_streams * e->N * sizeof(float)));
+    if (e->N == 512) {
+        std::vector<float2> t512(256), t256(256);
+        const double two_pi = 6.283185307179586476925286766559;
+        for (int m = 0; m < 256; m++) {
+            t512[m] = make_float2((float)cos(-two_pi * m / 512.0), (float)sin(-two_pi * m / 512.0));
+            t256[m] = make_float2((float)cos(-two_pi * m / 256.0), (float)sin(-two_pi * m / 256.0));
+        }
+        CKC(cudaMalloc((void **)&e->d_tw512, 256 * sizeof(float2)));
+        CKC(cudaMemcpy(e->d_tw512, t512.data(), 256 * sizeof(float2), cudaMemcpyHostToDevice));
+        CKC(cudaMalloc((void **)&e->d_tw256w, 256 * sizeof(float2)));
+        CKC(cudaMemcpy(e->d_tw256w, t256.data(), 256 * sizeof(float2), cudaMemcpyHostToDevice));
+        const char *v = getenv("SDR_K1_WARP");
+        e->k1_warp = !(v && v[0] == '0');
+        if (e->k1_warp) e->k1w_grid_cap = k1w_grid_cap_for(e->d_window != nullptr, e->sm_count);
+    }
     if (e->N == 4096 || e->N == 8192) {
         const int r1 = e->N / 256;
         std::vector<float2> t((size_t)r1 * 256), t256(256);
@@ -828,6 +878,8 @@ void sdr_engine_destroy(sdr_engine *e) {
     cudaFree(e->d_twp);
     cudaFree(e->d_tw_step);
     cudaFree(e->d_tw_mid);
+    cudaFree(e->d_tw512);
+    cudaFree(e->d_tw256w);
     cudaFree(e->d_tw256m);
     cudaFree(e->d_tw_sub1);
     cudaFree(e->d_tw_sub2);
@@ -991,6 +1043,7 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     int n_segs = 0, n_flushes = 0, block_off = 0, lb_off = 0;
     size_t iq_off = 0;  // floats into d_iq
     bool pair_ok = true;              // every work's noise windows are wide enough for k1_pair_kernel
+    bool warp_ok = (N == 512);        // ... and for k1_warp_kernel
     const float *pend_src = nullptr;  // pending coalesced H2D copy
     float *pend_dst = nullptr;
     size_t pend_n = 0;
@@ -1015,6 +1068,7 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
         }
         wps[w].edge_width = wk.edge_width;
         if (nf_window_size(N, wk.edge_width) < K1PairGeom::MIN_WS) pair_ok = false;
+        if (N != 512 || nf_window_size(N, wk.edge_width) < K1WarpGeom::MIN_WS) warp_ok = false;
         wps[w].n_listeners = wk.n_listeners;
         wps[w].listener_off = lb_off;
         wps[w].pad = 0;
@@ -1109,7 +1163,7 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     CK(e, cudaEventRecord(s.ev_k0, e->s_compute));
     int k1_launches = 1;
     if (!e->large) {
-        CK(e, launch_k1(e, a1, dbg, e->s_compute, i16, pair_ok));
+        CK(e, launch_k1(e, a1, dbg, e->s_compute, i16, pair_ok, warp_ok));
     } else if (e->k1_mid && e->N == 8192 && block_off <= e->round_blocks && n_segs >= 2 * e->sm_count) {
         // enough segments to fill the GPU with segment-sequential CTAs: fused single pass (k1_mid.cuh)
         CK(e, launch_k1_mid(e, a1, dbg, e->s_compute));
