@@ -420,15 +420,16 @@ const void *k1m_fn(bool dbg, bool win) {
     if (dbg) return win ? (const void *)k1_mid_kernel<R1, true, true> : (const void *)k1_mid_kernel<R1, true, false>;
     return win ? (const void *)k1_mid_kernel<R1, false, true> : (const void *)k1_mid_kernel<R1, false, false>;
 }
-const void *k1m_fn(int n, bool dbg, bool win) { return n == 4096 ? k1m_fn<16>(dbg, win) : k1m_fn<32>(dbg, win); }
-int k1m_smem(int n) { return n == 4096 ? K1MidGeom<16>::SMEM_BYTES : K1MidGeom<32>::SMEM_BYTES; }
+const void *k1m_fn(int n, bool dbg, bool win) { return n == 2048 ? k1m_fn<8>(dbg, win) : n == 4096 ? k1m_fn<16>(dbg, win) : k1m_fn<32>(dbg, win); }
+int k1m_smem(int n) { return n == 2048 ? K1MidGeom<8>::SMEM_BYTES : n == 4096 ? K1MidGeom<16>::SMEM_BYTES : K1MidGeom<32>::SMEM_BYTES; }
+int k1m_threads(int n) { return n == 2048 ? K1MidGeom<8>::T : 256; }
 
 int k1m_grid_cap_for(int n, bool win, int sm_count) {
     int occ = 0;
     for (int dbg = 0; dbg < 2; dbg++) {
         const void *fn = k1m_fn(n, dbg != 0, win);
         cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k1m_smem(n));
-        if (!dbg) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 256, k1m_smem(n));
+        if (!dbg) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, k1m_threads(n), k1m_smem(n));
     }
     if (occ < 1) occ = 1;
     return occ * sm_count;
@@ -444,15 +445,15 @@ cudaError_t launch_k1_mid(const sdr_engine *e, const K1Args &a, bool dbg, cudaSt
     K1Args args = a;
     const float2 *tws = e->d_tw_mid, *tw256 = e->d_tw256m;
     void *params[] = {&args, &tws, &tw256};
-    return cudaLaunchKernel(k1m_fn(e->N, dbg, a.window != nullptr), dim3(grid), dim3(256), params, k1m_smem(e->N), st);
+    return cudaLaunchKernel(k1m_fn(e->N, dbg, a.window != nullptr), dim3(grid), dim3(k1m_threads(e->N)), params, k1m_smem(e->N), st);
 }
 
 // pair_ok: every work of the launch has noise windows of at least K1PairGeom::MIN_WS bins
 // warp_ok: N = 512 and every work has noise windows of at least K1WarpGeom::MIN_WS bins
 cudaError_t launch_k1(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st, bool i16 = false, bool pair_ok = true,
                       bool warp_ok = true) {
+    if (e->k1_mid && (e->N == 4096 || e->N == 2048) && !i16) return launch_k1_mid(e, a, dbg, st);
     if (e->k1_pair && pair_ok) return launch_k1_pair(e, a, dbg, st, i16);
-    if (e->k1_mid && e->N == 4096 && !i16) return launch_k1_mid(e, a, dbg, st);
     if (e->k1_warp && warp_ok) return launch_k1_warp(e, a, dbg, st, i16);
     switch (e->N) {
         case 512: return launch_k1_n<512>(e, a, dbg, st, i16);
@@ -819,7 +820,7 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
         e->k1_warp = !(v && v[0] == '0');
         if (e->k1_warp) e->k1w_grid_cap = k1w_grid_cap_for(e->d_window != nullptr, e->sm_count);
     }
-    if (e->N == 4096 || e->N == 8192) {
+    if (e->N == 2048 || e->N == 4096 || e->N == 8192) {
         const int r1 = e->N / 256;
         std::vector<float2> t((size_t)r1 * 256), t256(256);
         const double two_pi = 6.283185307179586476925286766559;
@@ -838,6 +839,10 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
         CKC(cudaMemcpy(e->d_tw256m, t256.data(), t256.size() * sizeof(float2), cudaMemcpyHostToDevice));
         const char *v = getenv("SDR_K1_MID");
         e->k1_mid = !(v && v[0] == '0');
+        if (e->N == 2048) {  // N = 2048: opt-in (SDR_K1_MID2048=1); the three-pass kernel is the default
+            const char *v2 = getenv("SDR_K1_MID2048");
+            e->k1_mid = e->k1_mid && v2 && v2[0] == '1';
+        }
         if (e->k1_mid) e->k1m_grid_cap = k1m_grid_cap_for(e->N, e->d_window != nullptr, e->sm_count);
     }
     CKC(cudaMalloc((void **)&e->d_rolling, (size_t)cfg->max_streams * sizeof(RollingState)));

@@ -1,4 +1,4 @@
-// k1_mid.cuh -- fused spectral front end for N = 4096 and N = 8192 (N = R1 x 256, R1 = 16 | 32): one pass over the IQ,
+// k1_mid.cuh -- fused spectral front end for N = R1 x 256, R1 = 8 | 16 | 32 (N = 2048, 4096, 8192): one pass over the IQ,
 // one launch, the cumulation in registers -- the K1 contract (k1_spectral.cuh) at block sizes whose exchange no
 // longer fits the three-pass kernel's register/shared-memory budget.
 //
@@ -24,35 +24,43 @@
 #ifndef SDR_K1M_MINB16
 #define SDR_K1M_MINB16 2
 #endif
+#ifndef SDR_K1M_MINB8
+#define SDR_K1M_MINB8 4
+#endif
 
 namespace sdr {
 
 template <int R1>
 struct K1MidGeom {
     static constexpr int N = R1 * 256;
-    static constexpr int JR = R1 / 16;                 // rows per half-warp
-    static constexpr int LOG_R1 = (R1 == 16) ? 4 : 5;
+    static constexpr int T = (R1 >= 16) ? 256 : 16 * R1;  // threads per CTA: one half-warp per row (two rows at R1 = 32)
+    static constexpr int CPT = 256 / T;                // columns per thread in pass A
+    static constexpr int JR = (R1 + 15) / 16;          // rows per half-warp
+    static constexpr int LOG_R1 = (R1 == 8) ? 3 : (R1 == 16) ? 4 : 5;
+    static constexpr int MINB = (R1 == 8) ? SDR_K1M_MINB8 : (R1 == 16) ? SDR_K1M_MINB16 : 2;
     static constexpr int E_BYTES = R1 * HW_PITCH * 8;  // 34 944 / 69 888
-    static constexpr int TPW = 24;                     // noise floor: threads per window (3 lanes x 8 partials combine)
+    static constexpr int TPW = (T / 10) / 3 * 3;       // noise floor: threads per window (3 lanes x TPW/3 partials combine)
     static constexpr int NFB = 8;                      // noise floor: blocks per batched selection
-    static constexpr int PART_BYTES = 256 * 8;
+    static constexpr int PART_BYTES = T * 8;
     static constexpr int NF_BYTES = NFB * 10 * (8 + 8 + 4);
     static constexpr int SMEM_BYTES = E_BYTES + PART_BYTES + NF_BYTES + 64;
-    static_assert(R1 == 16 || R1 == 32, "N = 4096 or 8192");
+    static_assert(R1 == 8 || R1 == 16 || R1 == 32, "N = 2048, 4096 or 8192");
 };
 
 template <int R1>
 __device__ __forceinline__ void dft_r1(float2 (&v)[R1]);
+template <>
+__device__ __forceinline__ void dft_r1<8>(float2 (&v)[8]) { dft8(v); }
 template <>
 __device__ __forceinline__ void dft_r1<16>(float2 (&v)[16]) { dft16(v); }
 template <>
 __device__ __forceinline__ void dft_r1<32>(float2 (&v)[32]) { dft32(v); }
 
 template <int R1, bool DEBUG_STORE, bool HAS_WINDOW>
-__global__ void __launch_bounds__(256, (R1 == 16) ? SDR_K1M_MINB16 : 2) k1_mid_kernel(const K1Args a, const float2 *__restrict__ tw_step,
+__global__ void __launch_bounds__(K1MidGeom<R1>::T, K1MidGeom<R1>::MINB) k1_mid_kernel(const K1Args a, const float2 *__restrict__ tw_step,
                                                         const float2 *__restrict__ tw256) {
     using Gm = K1MidGeom<R1>;
-    constexpr int N = Gm::N, JR = Gm::JR;
+    constexpr int N = Gm::N, JR = Gm::JR, T = Gm::T, CPT = Gm::CPT;
     extern __shared__ __align__(16) unsigned char mid_smem[];
     float2 *E = reinterpret_cast<float2 *>(mid_smem);  // [R1][HW_PITCH]
     float *Ef = reinterpret_cast<float *>(mid_smem);   // |X|^2 of bin kk lives at Ef[(kk % R1) * 2*HW_PITCH + kk / R1]
@@ -62,13 +70,12 @@ __global__ void __launch_bounds__(256, (R1 == 16) ? SDR_K1M_MINB16 : 2) k1_mid_k
     float *NFX = reinterpret_cast<float *>(NFS2 + Gm::NFB * 10);
     constexpr int TPW = Gm::TPW, NFB = Gm::NFB;
     const int tid = threadIdx.x, hl = tid & 15, f = tid >> 4, lane = tid & 31, warp = tid >> 5;
-    const float db_offset = (R1 == 16) ? (float)(13.0102999566398120 - 20.0 * 12.0 * 0.30102999566398120)
-                                       : (float)(13.0102999566398120 - 20.0 * 13.0 * 0.30102999566398120);
+    const float db_offset = (float)(13.0102999566398120 - 20.0 * (double)(8 + Gm::LOG_R1) * 0.30102999566398120);
     auto psd_at = [&](int kk) -> float { return Ef[(kk & (R1 - 1)) * (2 * HW_PITCH) + (kk >> Gm::LOG_R1)]; };
     auto to_db = [&](float psd) -> float { return __fadd_rn(fmaf(3.01029995663981195f, fast_log2(psd), db_offset), 120.0f); };
 
     HwTwiddle t;
-    if (R1 == 16) hw_twiddle_load(t, tw256, hl);
+    if (R1 != 32) hw_twiddle_load(t, tw256, hl);
 
     for (int seg = blockIdx.x; seg < a.n_segs; seg += gridDim.x) {
         const Segment sg = a.segs[seg];
@@ -108,35 +115,45 @@ __global__ void __launch_bounds__(256, (R1 == 16) ? SDR_K1M_MINB16 : 2) k1_mid_k
         const float2 *iq = reinterpret_cast<const float2 *>(sg.iq);
         for (int blk = 0; blk < sg.n_blocks; blk++) {
             const int ob = sg.block_out + blk;
-            // ---------------- pass A: column c = tid ----------------
-            {
-                const float2 *src = iq + (size_t)blk * N + tid;
-                float2 v[R1];
+            // ---------------- pass A: columns c = tid + T*cc ----------------
+            if (blk + 1 < sg.n_blocks) {  // next block -> L2 (N*8/128 lines, 1 or 2 per thread)
+#pragma unroll
+                for (int i = 0; i < (N * 8 / 128 + T - 1) / T; i++)
+                    if (tid + T * i < N * 8 / 128)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(iq + (size_t)(blk + 1) * N) +
+                                                                      (size_t)(tid + T * i) * 128));
+            }
+            float2 v[CPT][R1];
+#pragma unroll
+            for (int cc = 0; cc < CPT; cc++) {  // all loads of the block in flight before the first butterfly
+                const int c = tid + T * cc;
+                const float2 *src = iq + (size_t)blk * N + c;
 #pragma unroll
                 for (int q = 0; q < R1; q++) {
-                    const int r = (R1 == 32) ? (q & 3) * 8 + (q >> 2) : (q & 3) * 4 + (q >> 2);  // first-layer order
-                    v[r] = __ldg(&src[(size_t)r * 256]);
+                    // issue order = consumption order of the first butterfly layer
+                    const int r = (R1 == 32) ? (q & 3) * 8 + (q >> 2) : (R1 == 16) ? (q & 3) * 4 + (q >> 2) : (q & 1) * 4 + (q >> 1);
+                    v[cc][r] = __ldg(&src[(size_t)r * 256]);
                     if (HAS_WINDOW) {
-                        const float w = __ldg(&a.window[r * 256 + tid]);
-                        v[r] = __fmul2_rn(v[r], make_float2(w, w));
+                        const float w = __ldg(&a.window[r * 256 + c]);
+                        v[cc][r] = __fmul2_rn(v[cc][r], make_float2(w, w));
                     }
                 }
-                if (blk + 1 < sg.n_blocks) {  // next block -> L2 (N*8/128 lines, 2 or 4 per thread)
+            }
 #pragma unroll
-                    for (int i = 0; i < N * 8 / 128 / 256; i++)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(iq + (size_t)(blk + 1) * N) +
-                                                                      (size_t)(tid + 256 * i) * 128));
-                }
-                dft_r1<R1>(v);
+            for (int cc = 0; cc < CPT; cc++) {
+                const int c = tid + T * cc;
+                dft_r1<R1>(v[cc]);
 #pragma unroll
                 for (int p = 1; p < R1; p++) {
                     const int k1 = OutIdx<R1>::of(p);
-                    if (k1 > 0) v[p] = cmul(v[p], __ldg(&tw_step[k1 * 256 + tid]));
+                    if (k1 > 0) v[cc][p] = cmul(v[cc][p], __ldg(&tw_step[k1 * 256 + c]));
                 }
-                if (blk > 0) __syncthreads();  // the previous block's noise-floor / tap reads of E are done
-#pragma unroll
-                for (int p = 0; p < R1; p++) E[OutIdx<R1>::of(p) * HW_PITCH + tid] = v[p];
             }
+            if (blk > 0) __syncthreads();  // the previous block's noise-floor / tap reads of E are done
+#pragma unroll
+            for (int cc = 0; cc < CPT; cc++)
+#pragma unroll
+                for (int p = 0; p < R1; p++) E[OutIdx<R1>::of(p) * HW_PITCH + tid + T * cc] = v[cc][p];
             __syncthreads();
             // ---------------- pass B: half-warp f = rows f, f + 16 ----------------
             if (R1 == 32) {
@@ -185,7 +202,7 @@ __global__ void __launch_bounds__(256, (R1 == 16) ? SDR_K1M_MINB16 : 2) k1_mid_k
                 PART[tid] = make_float2(s1, s2);
             }
             // listener taps (rx/receiver.go:393)
-            for (int l = tid; l < L; l += 256) a.taps[(size_t)ob * a.tap_stride + l] = to_db(psd_at(__ldg(&lbins[l])));
+            for (int l = tid; l < L; l += T) a.taps[(size_t)ob * a.tap_stride + l] = to_db(psd_at(__ldg(&lbins[l])));
             __syncthreads();
             if (warp == 0) {  // phase 2 + batched selection: warp 0 only, everything else moves on to the next block
                 const int w = lane / 3, j = lane - 3 * w;
