@@ -77,6 +77,7 @@ struct Slot {
     float *h_spectrum = nullptr, *h_psd = nullptr;  // lazy
     std::vector<int> work_block_offset, work_flush_offset;
     int n_works = 0, n_blocks = 0, n_flushes = 0, launches = 0;
+    cudaEvent_t ev_desc = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_k0 = nullptr, ev_km = nullptr, ev_k1 = nullptr, ev_done = nullptr;
 };
 
@@ -90,6 +91,10 @@ struct sdr_engine {
     int sm_count = 148;
     std::string err;
     cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    // descriptor uploads always go through an internal stream (also when the caller supplied the compute stream): a
+    // slot's descriptor block is only rewritten after its ticket was released, so the copy of batch i+1 overlaps the
+    // kernels of batch i instead of sitting between them on the compute stream
+    cudaStream_t s_desc = nullptr;
     bool own_streams = true;
     float2 *d_tw1 = nullptr, *d_tw2 = nullptr;
     // large-block path (N >= 8192): four-step split N = n1 * n2
@@ -582,6 +587,7 @@ void free_slot(Slot &s) {
     cudaFreeHost(s.h_spectrum);
     cudaFreeHost(s.h_psd);
     if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+    if (s.ev_desc) cudaEventDestroy(s.ev_desc);
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
     if (s.ev_km) cudaEventDestroy(s.ev_km);
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
@@ -628,6 +634,7 @@ int alloc_slot(sdr_engine *e, Slot &s) {
         CK(e, cudaMalloc((void **)&s.d_psd, MB * N * sizeof(float)));
     }
     CK(e, cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+    CK(e, cudaEventCreateWithFlags(&s.ev_desc, cudaEventDisableTiming));
     CK(e, cudaEventCreate(&s.ev_k0));
     CK(e, cudaEventCreate(&s.ev_km));
     CK(e, cudaEventCreate(&s.ev_k1));
@@ -730,6 +737,7 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
                  std::to_string(prop.minor);
         return fail(SDR_ECUDA);
     }
+    CKC(cudaStreamCreateWithFlags(&e->s_desc, cudaStreamNonBlocking));
     if (cfg->cuda_stream) {
         e->own_streams = false;
         e->s_compute = e->s_h2d = e->s_d2h = (cudaStream_t)cfg->cuda_stream;
@@ -893,6 +901,7 @@ void sdr_engine_destroy(sdr_engine *e) {
     cudaFree(e->d_cum_state);
     cudaFree(e->d_rolling);
     cudaFree(e->d_scratch);
+    if (e->s_desc) cudaStreamDestroy(e->s_desc);
     if (e->own_streams) {
         if (e->s_compute) cudaStreamDestroy(e->s_compute);
         if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
@@ -1143,9 +1152,11 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
 
     if (pend_n > 0) CK(e, cudaMemcpyAsync(pend_dst, pend_src, pend_n * sizeof(float), cudaMemcpyHostToDevice, e->s_h2d));
     // ---- H2D: descriptors (+ IQ queued above) ----
-    CK(e, cudaMemcpyAsync(s.d_desc, s.h_desc, dl.total, cudaMemcpyHostToDevice, e->s_h2d));
+    CK(e, cudaMemcpyAsync(s.d_desc, s.h_desc, dl.total, cudaMemcpyHostToDevice, e->s_desc));
+    CK(e, cudaEventRecord(s.ev_desc, e->s_desc));
     CK(e, cudaEventRecord(s.ev_h2d, e->s_h2d));
     CK(e, cudaStreamWaitEvent(e->s_compute, s.ev_h2d, 0));
+    CK(e, cudaStreamWaitEvent(e->s_compute, s.ev_desc, 0));
 
     // ---- kernels ----
     K1Args a1;
