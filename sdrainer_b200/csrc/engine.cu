@@ -27,6 +27,7 @@
 #include "k1_large.cuh"
 #include "k1_mid.cuh"
 #include "k1_warp.cuh"
+#include "k1_cluster.cuh"
 
 using namespace sdr;
 
@@ -103,6 +104,10 @@ struct sdr_engine {
     float2 *d_tw_sub1 = nullptr, *d_tw_sub2 = nullptr, *d_tw_n = nullptr;
     float2 *d_tw_step = nullptr;  // [k1][c] = W_N^(c k1): step-1 twiddles of the register-resident kernels
     int round_blocks = 0;         // register-resident large path: blocks per L2-resident round (SDR_LARGE_ROUND_MB)
+    // N = 65536: 16-CTA cluster kernel (k1_cluster.cuh), opt-in with SDR_K1_CLUSTER=1 (measured slower than the
+    // two-kernel path: DESIGN.md)
+    bool k1_cluster = false;
+    int k1c_max_clusters = 0;
     // N = 512: warp-per-block kernel (k1_warp.cuh), SDR_K1_WARP=0 selects the three-pass kernel
     float2 *d_tw512 = nullptr, *d_tw256w = nullptr;
     bool k1_warp = false;
@@ -305,6 +310,50 @@ cudaError_t launch_large_fast(const sdr_engine *e, const K1Args &a, const LargeF
     fin.n = N;
     large_nf_finish_kernel<<<(n_blocks + 3) / 4, 128, 0, st>>>(fin);
     if (n_launches) *n_launches = launches + 1;
+    return cudaGetLastError();
+}
+
+// N = 65536 in one pass: clusters of 16 CTAs walk the segments (k1_cluster.cuh), then the noise-floor finish
+cudaError_t launch_k1_cluster(const sdr_engine *e, const K1Args &a, const LargeFastBufs &lb, int n_blocks, bool dbg, cudaStream_t st) {
+    ClusterArgs ca{};
+    ca.a = a;
+    if (!dbg) ca.a.dbg_psd = ca.a.dbg_spectrum = nullptr;
+    ca.tw256 = e->d_tw_sub2;
+    ca.tw_step = e->d_tw_step;
+    ca.nf_part = lb.nf_part;
+    ca.xto = lb.xto;
+    ca.nf_edge = lb.nf_edge;
+    ca.db_offset = (float)(10.0 * log10(20.0 / (65536.0 * 65536.0)));
+    int ncl = a.n_segs;
+    if (ncl > e->k1c_max_clusters) {
+        const int rounds = (ncl + e->k1c_max_clusters - 1) / e->k1c_max_clusters;
+        ncl = (a.n_segs + rounds - 1) / rounds;
+    }
+    if (ncl < 1) ncl = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(K1C_CLUSTER * ncl);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = K1C_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = K1C_CLUSTER;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    cudaError_t rc = cudaLaunchKernelEx(&cfg, k1_cluster_kernel, ca);
+    if (rc != cudaSuccess) return rc;
+    LargeFinishArgs fin{};
+    fin.nf_part = lb.nf_part;
+    fin.xto = lb.xto;
+    fin.nf_edge = lb.nf_edge;
+    fin.psd_floor = a.psd_floor;
+    fin.variance = a.variance;
+    fin.n_blocks = n_blocks;
+    fin.n_cta = K1C_CLUSTER;
+    fin.n = 65536;
+    large_nf_finish_kernel<<<(n_blocks + 3) / 4, 128, 0, st>>>(fin);
     return cudaGetLastError();
 }
 
@@ -804,6 +853,29 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
             } else {
                 e->round_blocks = cfg->max_blocks_per_batch > 16 ? cfg->max_blocks_per_batch : 16;
             }
+            if (e->N == 65536) {
+                const char *cv = getenv("SDR_K1_CLUSTER");
+                if (cv && cv[0] == '1' && cudaFuncSetAttribute(k1_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K1C_SMEM_BYTES) == cudaSuccess &&
+                    cudaFuncSetAttribute(k1_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+                    cudaLaunchConfig_t lc = {};
+                    lc.gridDim = dim3(K1C_CLUSTER);
+                    lc.blockDim = dim3(256);
+                    lc.dynamicSmemBytes = K1C_SMEM_BYTES;
+                    cudaLaunchAttribute at;
+                    at.id = cudaLaunchAttributeClusterDimension;
+                    at.val.clusterDim.x = K1C_CLUSTER;
+                    at.val.clusterDim.y = 1;
+                    at.val.clusterDim.z = 1;
+                    lc.attrs = &at;
+                    lc.numAttrs = 1;
+                    int ncl = 0;
+                    if (cudaOccupancyMaxActiveClusters(&ncl, k1_cluster_kernel, &lc) == cudaSuccess && ncl > 0) {
+                        e->k1_cluster = true;
+                        e->k1c_max_clusters = ncl;
+                    }
+                }
+                cudaGetLastError();  // a device without 16-CTA clusters simply keeps the two-kernel path
+            }
         }
     }
     if (cfg->window) {
@@ -1183,6 +1255,11 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     } else if (e->k1_mid && e->N == 8192 && block_off <= e->round_blocks && n_segs >= 2 * e->sm_count) {
         // enough segments to fill the GPU with segment-sequential CTAs: fused single pass (k1_mid.cuh)
         CK(e, launch_k1_mid(e, a1, dbg, e->s_compute));
+    } else if (e->k1_cluster && block_off <= e->round_blocks && n_segs >= 8) {
+        // one cluster of 16 CTAs per segment, the whole 512 KB block in distributed shared memory (k1_cluster.cuh)
+        const LargeFastBufs lb{s.d_tmp, s.d_spec_round, s.d_nf_part, s.d_xto, s.d_nf_edge};
+        CK(e, launch_k1_cluster(e, a1, lb, block_off, dbg, e->s_compute));
+        k1_launches = 2;
     } else if (e->round_blocks > 0) {
         // rounds of consecutive blocks; the segment table is in block order and no segment straddles a round
         std::vector<LargeRound> rounds;
