@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2_post_kernel(const K2Args a) {
                 ds = __fsub_rn(ds, s_roll.dev_values[next]);
                 s_roll.dev_values[next] = s_dev[i];
                 ds = __fadd_rn(ds, s_dev[i]);
-                next = (next + 1) % SDR_NOISE_WINDOW;
+                next = (next + 1 == SDR_NOISE_WINDOW) ? 0 : next + 1;
                 s_floor[i] = fs;
                 s_dev[i] = ds;
             }
@@ -220,20 +220,26 @@ __global__ void __launch_bounds__(K2_THREADS) k2_post_kernel(const K2Args a) {
         const int total = cn * L;
         const float *__restrict__ taps = a.taps + (size_t)(w.block_out + c0) * a.tap_stride;
         uint8_t *__restrict__ keys = a.keys + (size_t)(w.block_out + c0) * a.tap_stride;
-        for (int base = 0; base < total; base += 4 * K2_THREADS) {
-            float v[4], th[4];
-            int off[4];
+        // one warp per block row (no per-element index division), four rows in flight per warp
+        (void)total;
+        {
+            const int wq = tid >> 5, lane = tid & 31;
+            constexpr int NWQ = K2_THREADS / 32;
+            for (int i0 = wq; i0 < cn; i0 += 4 * NWQ) {
+                for (int l = lane; l < L; l += 32) {
+                    float v[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {  // four independent global loads in flight per thread
-                const int idx = base + u * K2_THREADS + tid;
-                const int i = idx < total ? idx / L : 0, l = idx < total ? idx - (idx / L) * L : 0;
-                off[u] = idx < total ? i * a.tap_stride + l : -1;
-                th[u] = s_floor[i];
-                v[u] = off[u] >= 0 ? taps[off[u]] : 0.f;
+                    for (int u = 0; u < 4; u++) {
+                        const int i = i0 + u * NWQ;
+                        v[u] = i < cn ? taps[(size_t)i * a.tap_stride + l] : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int i = i0 + u * NWQ;
+                        if (i < cn) keys[(size_t)i * a.tap_stride + l] = v[u] > s_floor[i] ? 1 : 0;
+                    }
+                }
             }
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (off[u] >= 0) keys[off[u]] = v[u] > th[u] ? 1 : 0;
         }
         __syncthreads();
     }
