@@ -284,6 +284,19 @@ cudaError_t launch_large_fast(const sdr_engine *e, const K1Args &a, const LargeF
         else fast_cols32_kernel<<<dim3(e->lg.n2 / 256, r.n_blocks), 256, 0, st>>>(fa);
         cudaError_t rc = cudaGetLastError();
         if (rc != cudaSuccess) return rc;
+        // enough segments to fill the GPU several times over: rows + cumulation in one segment-sequential kernel
+        if ((long long)r.n_segs * (e->lg.n1 / 16) >= 4LL * e->sm_count && !getenv("SDR_LARGE_NO_SEGROWS")) {
+            FastRowsSegArgs sa{};
+            sa.s = fa;
+            sa.seg0 = r.seg0;
+            sa.cum_state = a.cum_state;
+            sa.flush_cum = a.flush_cum;
+            fast_rows256_seg_kernel<<<dim3(e->lg.n1 / 16, r.n_segs), 256, smem, st>>>(sa);
+            rc = cudaGetLastError();
+            if (rc != cudaSuccess) return rc;
+            launches += 2;
+            continue;
+        }
         fast_rows256_kernel<<<dim3(e->lg.n1 / 16, r.n_blocks), 256, smem, st>>>(fa);
         rc = cudaGetLastError();
         if (rc != cudaSuccess) return rc;

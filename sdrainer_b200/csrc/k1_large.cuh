@@ -389,6 +389,97 @@ __global__ void __launch_bounds__(256) fast_rows256_kernel(const FastStepArgs a)
     }
 }
 
+// step 2 + epilogue + cumulation, segment-sequential variant of fast_rows256_kernel: grid (N1 / 16, segments of the
+// round).  A CTA walks the blocks of ONE segment in order and keeps the cumulation of its 4096 bins in registers
+// (16 per thread, sequential float32 adds in block order, rx/receiver.go:404-407): no dB-spectrum round trip and no
+// separate cumulation launch.  Chosen by the engine when segments x N1/16 CTAs fill the GPU several times over;
+// with few streams the block-parallel kernel + large_round_cum_kernel is faster.
+struct FastRowsSegArgs {
+    FastStepArgs s;
+    int seg0;  // first segment of the round
+    float *cum_state, *flush_cum;
+};
+__global__ void __launch_bounds__(256) fast_rows256_seg_kernel(const FastRowsSegArgs sa) {
+    const FastStepArgs &a = sa.s;
+    extern __shared__ __align__(16) unsigned char sub_smem[];
+    float2 *cols = reinterpret_cast<float2 *>(sub_smem);  // [16][HW_PITCH]: transpose scratch, then the (psd, dB) tile
+    __shared__ int cnt[11];
+    const int tid = threadIdx.x, hl = tid & 15, f = tid >> 4, lane = tid & 31, warp = tid >> 5;
+    const int r0 = blockIdx.x * 16;
+    const int N = a.n, N1 = a.n1;
+    const Segment sg = a.segs[sa.seg0 + blockIdx.y];
+    const WorkParams wp = a.works[sg.work];
+    const int e = wp.edge_width;
+    const int ws = nf_window_size(N, e), n_win = nf_window_count(N, e);
+    if (tid < 11) cnt[tid] = tile_count_below(e + tid * ws, r0, N1, 256);
+    HwTwiddle t;
+    hw_twiddle_load(t, a.tw256, hl);
+    const int *lbins = a.listener_bins + wp.listener_off;
+    float cum[16];
+#pragma unroll
+    for (int p = 0; p < 16; p++) {
+        const int kk = ((r0 + f) + N1 * (hl + 16 * OutIdx<16>::of(p)) + N / 2) & (N - 1);
+        cum[p] = sg.state_in >= 0 ? sa.cum_state[(size_t)sg.state_in * N + kk] : 0.f;
+    }
+    float2 *col = cols + f * HW_PITCH;
+    for (int b = 0; b < sg.n_blocks; b++) {
+        const int blk = sg.block_out + b;
+        const float2 *src = a.tmp + (size_t)(blk - a.blk0) * N + (size_t)(r0 + f) * 256 + hl;
+        float2 v[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int n1 = (q & 3) * 4 + (q >> 2);
+            v[n1] = src[16 * n1];
+        }
+        fft256_halfwarp_regs(v, col, t, hl);
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < 16; p++) {
+            const float psd = fmaf(v[p].x, v[p].x, v[p].y * v[p].y);
+            const float db = __fadd_rn(fmaf(3.01029995663981195f, fast_log2(psd), a.db_offset), 120.0f);
+            cum[p] = __fadd_rn(cum[p], db);
+            col[hl + 16 * OutIdx<16>::of(p)] = make_float2(psd, db);
+        }
+        __syncthreads();
+        if (a.psd) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int k2 = f + 16 * i;
+                const float2 o = cols[hl * HW_PITCH + k2];
+                const int kk = ((r0 + hl) + N1 * k2 + N / 2) & (N - 1);
+                a.psd[(size_t)blk * N + kk] = o.x;
+                a.spectrum[(size_t)blk * N + kk] = o.y;
+            }
+        }
+        for (int w = warp; w < 10; w += 8) {
+            double a1 = 0.0, a2 = 0.0;
+            for (int i = cnt[w] + lane; i < cnt[w + 1]; i += 32) {
+                const double x = (double)cols[(i & 15) * HW_PITCH + (((i >> 4) + 128) & 255)].x;
+                a1 += x;
+                a2 = fma(x, x, a2);
+            }
+            a1 = warp_sum(a1);
+            a2 = warp_sum(a2);
+            if (lane == 0) a.nf_part[((size_t)blk * gridDim.x + blockIdx.x) * 10 + w] = make_double2(a1, a2);
+        }
+        if (tid < n_win) {
+            const int k = (e + (tid + 1) * ws - N / 2) & (N - 1);
+            const int k1 = k & (N1 - 1);
+            if (k1 >= r0 && k1 < r0 + 16) a.xto[(size_t)blk * 10 + tid] = cols[(k1 - r0) * HW_PITCH + k / N1].x;
+        }
+        if (blockIdx.x == 0 && tid == 0) a.nf_edge[blk] = e;
+        for (int l = tid; l < wp.n_listeners; l += 256) {
+            const int k = (__ldg(&lbins[l]) - N / 2) & (N - 1);
+            const int k1 = k & (N1 - 1);
+            if (k1 >= r0 && k1 < r0 + 16) a.taps[(size_t)blk * a.tap_stride + l] = cols[(k1 - r0) * HW_PITCH + k / N1].y;
+        }
+        __syncthreads();  // the tile is read: the next block's transposes may overwrite it
+    }
+    float *dst = (sg.flush_idx >= 0) ? sa.flush_cum + (size_t)sg.flush_idx * N : sa.cum_state + (size_t)sg.state_out * N;
+#pragma unroll
+    for (int p = 0; p < 16; p++) dst[((r0 + f) + N1 * (hl + 16 * OutIdx<16>::of(p)) + N / 2) & (N - 1)] = cum[p];
+}
+
 struct LargeFinishArgs {
     const double2 *nf_part;
     const float *xto;

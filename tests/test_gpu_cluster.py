@@ -51,3 +51,34 @@ def test_cluster_65536_agrees_with_two_kernel_path_and_oracle(capi, oracle, monk
         loud = r.flush_cum[0] > np.median(r.flush_cum[0]) + 1000.0
         assert loud.any() and d[loud].max() < 0.05
         pu.check_peaks(pu.peak_keys(s1.peaks(fl)), [p.key() for p in r.peaks[0]], r.flush_cum[0], r.thresholds[99, 2])
+
+
+def test_segment_sequential_rows_kernel_equals_block_parallel_path(capi, monkeypatch):
+    """N = 65536 with >= 37 segments: fast_rows256_seg_kernel (cumulation in registers) against fast_rows256_kernel +
+    large_round_cum_kernel (SDR_LARGE_NO_SEGROWS=1): the same arithmetic in the same order -> identical bits.  101 blocks
+    per stream in two submits (60 + 41): the second closes the window (flush) and leaves one block in the next one"""
+    monkeypatch.delenv("SDR_K1_CLUSTER", raising=False)
+    n, fs, nb, ns = 65536, 24576000, 101, 40
+    rng = np.random.default_rng(66)
+    base = [(rng.standard_normal(nb * 2 * n) * 1e-3).astype(np.float32) for _ in range(3)]
+    binss = [np.sort(rng.choice(np.arange(80, n - 80), size=4, replace=False)).astype(np.int32) for _ in range(ns)]
+    names = ("psd_noise_floor", "noise_variance", "taps", "keys", "thresholds", "flush_cum", "flush_n_peaks")
+    res = []
+    for sel in (None, "1"):
+        if sel is None:
+            monkeypatch.delenv("SDR_LARGE_NO_SEGROWS", raising=False)
+        else:
+            monkeypatch.setenv("SDR_LARGE_NO_SEGROWS", sel)
+        with capi.Engine(n, max_streams=ns, max_listeners=4, max_blocks_per_batch=ns * 60, max_peaks_per_flush=64) as eng:
+            ss = [eng.open_stream(fs) for _ in range(ns)]
+            works = [dict(stream=ss[i], iq=base[i % 3], listener_bins=binss[i]) for i in range(ns)]
+            a = eng.collect(eng.submit([dict(w, iq=w["iq"][:2 * n * 60]) for w in works], capi.WANT_FLUSH_CUM))
+            keep = {k: np.array(getattr(a, k)) for k in names}
+            b = eng.collect(eng.submit([dict(w, iq=w["iq"][2 * n * 60:]) for w in works], capi.WANT_FLUSH_CUM))
+            cum = [eng.cumulation_count(s) for s in ss]
+            res.append((keep, {k: np.array(getattr(b, k)) for k in names}, cum, b.n_flushes))
+    (k1, b1, c1, f1), (k0, b0, c0, f0) = res
+    assert c1 == c0 == [1] * ns and f1 == f0 == ns
+    for d1, d0 in ((k1, k0), (b1, b0)):
+        for name in names:
+            assert np.array_equal(d1[name], d0[name], equal_nan=True), name
