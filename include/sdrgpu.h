@@ -7,8 +7,11 @@
  * code it replaces.  Plain C, no exceptions cross the boundary, every call returns an int status
  * (0 = ok, <0 = error; text via sdr_last_error), the library never aborts the process.
  *
- * Threading: calls on different engines are independent; one caller at a time per engine
- * (the Go side owns an engine from one goroutine, like rx.Receiver.run owns its state).
+ * Threading: every entry point is safe for concurrent callers on one engine (one goroutine per rx.Receiver,
+ * rx/receiver.go:145,336: the engine serialises them internally; a blocking sdr_collect does not hold the lock while
+ * it waits).  A stream and a ticket have one owner at a time, like rx.Receiver.run owns its state.  Many receivers
+ * sharing one engine fill the GPU best through ONE sdr_submit per tick (the dispatcher in host/sdrhost.hpp and
+ * go/sdrgpu does that).
  *
  * Memory: `iq` pointers passed to sdr_submit may be device pointers (SDR_MEM_DEVICE, zero copy)
  * or host pointers (SDR_MEM_HOST; pinned memory from sdr_alloc_pinned makes the copy async).
@@ -79,7 +82,9 @@ typedef struct {
     int n_blocks;             /* >= 1 */
     const float *iq;          /* n_blocks * 2N float32, interleaved I,Q (tci/tci.go:264, kiwi/kiwi.go:94) */
     int mem;                  /* SDR_MEM_HOST or SDR_MEM_DEVICE */
-    int edge_width;           /* rx.Receiver.edgeWidth (default 70, rx/receiver.go:25) */
+    int edge_width;           /* rx.Receiver.edgeWidth (default 70, rx/receiver.go:25), >= 0.  Widths that leave noise
+                                 windows of fewer than 9 bins ((N-2e)/10 < 9) take a slow exact replay of
+                                 dsp.FindNoiseFloor for that work (same results as the reference, dsp/fft.go:215-252) */
     float peak_threshold;     /* rx.Receiver.peakThreshold (default 15 dB, :24) */
     int n_listeners;          /* attached listeners */
     const int *listener_bins; /* Listener.SignalBin() of each (rx/listener.go:119-124); host memory */
@@ -154,6 +159,10 @@ int sdr_ticket_device_ptrs(sdr_engine *e, sdr_ticket t, void **psd_noise_floor, 
                            void **thresholds, void **taps, void **keys);
 /* kernels launched by this engine since creation (bench.py's gpu_launches) */
 int64_t sdr_engine_launch_count(const sdr_engine *e);
+/* The post kernel (thresholds, keys, peaks) of a batch runs on an engine-internal stream so that it overlaps the next
+ * batch's spectral kernel.  A caller that supplied cfg.cuda_stream and wants "everything submitted so far" ordered
+ * before later work on that stream (e.g. a timing event) calls this: the stream waits for the last post kernel. */
+int sdr_engine_fence(sdr_engine *e);
 
 /* ---- dsp-signature-compatible single calls (drop-in correctness, not throughput) ------------- */
 /* dsp.FFT.IQToSpectrumAndPSD with the receiver's shiftedMagnitude projection

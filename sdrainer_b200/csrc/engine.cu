@@ -22,7 +22,6 @@
 
 #include "../../include/sdrgpu.h"
 #include "k1_spectral.cuh"
-#include "k1_pair.cuh"
 #include "k2_post.cuh"
 #include "k1_large.cuh"
 #include "k1_mid.cuh"
@@ -79,12 +78,15 @@ struct Slot {
     std::vector<int> work_block_offset, work_flush_offset;
     int n_works = 0, n_blocks = 0, n_flushes = 0, launches = 0;
     cudaEvent_t ev_desc = nullptr;
-    cudaEvent_t ev_h2d = nullptr, ev_k0 = nullptr, ev_km = nullptr, ev_k1 = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_k0 = nullptr, ev_km = nullptr, ev_k2s = nullptr, ev_k1 = nullptr, ev_done = nullptr;
 };
 
 }  // namespace
 
 struct sdr_engine {
+    // the C ABI is safe for concurrent callers (one goroutine per rx.Receiver, rx/receiver.go:145,336): every entry
+    // point takes this lock; a blocking sdr_collect drops it while it waits on the ticket's event
+    std::mutex mu;
     sdr_engine_config cfg{};
     int N = 0;
     int tap_stride = 4;
@@ -96,6 +98,12 @@ struct sdr_engine {
     // slot's descriptor block is only rewritten after its ticket was released, so the copy of batch i+1 overlaps the
     // kernels of batch i instead of sitting between them on the compute stream
     cudaStream_t s_desc = nullptr;
+    // K2 (thresholds, keys, peaks) runs on its own stream behind an event: batch i's K2 overlaps batch i+1's K1 (K2 is
+    // 6 % of a step and latency/ALU-bound; K1 never reads what K2 writes).  K2s stay ordered among themselves, which
+    // keeps the per-stream rolling means sequential.  SDR_K2_OVERLAP=0 puts K2 back on the compute stream.
+    cudaStream_t s_post = nullptr;
+    bool own_post = false;
+    cudaEvent_t ev_post = nullptr;  // last K2 (sdr_engine_fence)
     bool own_streams = true;
     float2 *d_tw1 = nullptr, *d_tw2 = nullptr;
     // large-block path (N >= 8192): four-step split N = n1 * n2
@@ -124,13 +132,6 @@ struct sdr_engine {
     sdr_ticket next_ticket = 1;
     int64_t launches = 0;
     int k1_grid_cap = 0;  // resident CTAs of K1 on this device
-    // N = 2048: SDR_K1_PAIR=1 selects the warp-pair kernel (k1_pair.cuh) instead of the three-pass kernel as the
-    // spectral stage (same results, same speed on B200: DESIGN.md section 4); SDR_K1_PAIR_STAGES=1|2 is the depth of
-    // its TMA ring
-    float2 *d_twp = nullptr;
-    bool k1_pair = false;
-    int k1p_stages = 1;
-    int k1p_grid_cap = 0;
     bool k1_tw2r = true;  // kernel variant: pass-2 twiddles in registers (SDR_K1_TW2R=0 selects the smem-table variant)
     // cache of choose_nf_map results, indexed by edge width (first byte 0xff = not computed)
     std::vector<unsigned char> nf_map_cache;
@@ -160,9 +161,15 @@ bool supported_fused_n(int n) { return n == 512 || n == 1024 || n == 2048 || n =
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// one work whose edge width the fused noise-floor code does not cover (fewer than 9 bins per window, or no window at
+// all): dsp.FindNoiseFloor is replayed literally, one thread per block, on the stored PSD
+struct ExactNf {
+    int block_out, n_blocks, edge_width, pad;
+};
+
 // descriptor block layout (same on host and device)
 struct DescLayout {
-    size_t segs, works, post, lbins, block_seg, total;
+    size_t segs, works, post, lbins, block_seg, exact, total;
 };
 DescLayout desc_layout(const sdr_engine *e) {
     DescLayout l;
@@ -177,6 +184,8 @@ DescLayout desc_layout(const sdr_engine *e) {
     off = align_up(off + sizeof(int) * (size_t)e->cfg.max_streams * (size_t)(e->cfg.max_listeners > 0 ? e->cfg.max_listeners : 1), 256);
     l.block_seg = off;
     if (e->large) off = align_up(off + sizeof(int) * (size_t)e->cfg.max_blocks_per_batch, 256);
+    l.exact = off;
+    off = align_up(off + sizeof(ExactNf) * (size_t)e->cfg.max_streams, 256);
     l.total = off;
     return l;
 }
@@ -419,42 +428,6 @@ cudaError_t launch_large(const sdr_engine *e, const K1Args &a, float2 *d_tmp, co
     return cudaGetLastError();
 }
 
-template <int NSTAGE>
-const void *k1p_fn(bool dbg, bool win, bool i16) {
-    if (i16) return dbg ? (const void *)k1_pair_kernel<true, false, true, NSTAGE> : (const void *)k1_pair_kernel<false, false, true, NSTAGE>;
-    if (dbg) return win ? (const void *)k1_pair_kernel<true, true, false, NSTAGE> : (const void *)k1_pair_kernel<true, false, false, NSTAGE>;
-    return win ? (const void *)k1_pair_kernel<false, true, false, NSTAGE> : (const void *)k1_pair_kernel<false, false, false, NSTAGE>;
-}
-const void *k1p_fn(int stages, bool dbg, bool win, bool i16) { return stages == 2 ? k1p_fn<2>(dbg, win, i16) : k1p_fn<1>(dbg, win, i16); }
-
-// resident pairs per SM x SMs; also opts every variant in to its dynamic shared memory size
-int k1p_grid_cap_for(int stages, bool win, int sm_count) {
-    const int smem = K1PairGeom::smem_bytes(stages);
-    int occ = 0;
-    for (int dbg = 0; dbg < 2; dbg++) {
-        const void *fn = k1p_fn(stages, dbg != 0, win, false);
-        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (!dbg) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 64, smem);
-        if (!win) cudaFuncSetAttribute(k1p_fn(stages, dbg != 0, false, true), cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    }
-    if (occ < 1) occ = 1;
-    return occ * sm_count;
-}
-
-cudaError_t launch_k1_pair(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st, bool i16) {
-    // one pair of warps per CTA walks the segment list with stride grid: whole rounds, no straggler
-    int grid = a.n_segs;
-    if (grid > e->k1p_grid_cap) {
-        const int rounds = (grid + e->k1p_grid_cap - 1) / e->k1p_grid_cap;
-        grid = (a.n_segs + rounds - 1) / rounds;
-    }
-    if (grid < 1) grid = 1;
-    K1Args args = a;
-    void *params[] = {&args};
-    return cudaLaunchKernel(k1p_fn(e->k1p_stages, dbg, a.window != nullptr, i16), dim3(grid), dim3(64), params,
-                            K1PairGeom::smem_bytes(e->k1p_stages), st);
-}
-
 const void *k1w_fn(bool dbg, bool win, bool i16) {
     if (i16) return dbg ? (const void *)k1_warp_kernel<true, false, true> : (const void *)k1_warp_kernel<false, false, true>;
     if (dbg) return win ? (const void *)k1_warp_kernel<true, true, false> : (const void *)k1_warp_kernel<true, false, false>;
@@ -487,9 +460,9 @@ const void *k1m_fn(bool dbg, bool win) {
     if (dbg) return win ? (const void *)k1_mid_kernel<R1, true, true> : (const void *)k1_mid_kernel<R1, true, false>;
     return win ? (const void *)k1_mid_kernel<R1, false, true> : (const void *)k1_mid_kernel<R1, false, false>;
 }
-const void *k1m_fn(int n, bool dbg, bool win) { return n == 2048 ? k1m_fn<8>(dbg, win) : n == 4096 ? k1m_fn<16>(dbg, win) : k1m_fn<32>(dbg, win); }
-int k1m_smem(int n) { return n == 2048 ? K1MidGeom<8>::SMEM_BYTES : n == 4096 ? K1MidGeom<16>::SMEM_BYTES : K1MidGeom<32>::SMEM_BYTES; }
-int k1m_threads(int n) { return n == 2048 ? K1MidGeom<8>::T : 256; }
+const void *k1m_fn(int n, bool dbg, bool win) { return n == 4096 ? k1m_fn<16>(dbg, win) : k1m_fn<32>(dbg, win); }
+int k1m_smem(int n) { return n == 4096 ? K1MidGeom<16>::SMEM_BYTES : K1MidGeom<32>::SMEM_BYTES; }
+int k1m_threads(int) { return 256; }
 
 int k1m_grid_cap_for(int n, bool win, int sm_count) {
     int occ = 0;
@@ -515,12 +488,9 @@ cudaError_t launch_k1_mid(const sdr_engine *e, const K1Args &a, bool dbg, cudaSt
     return cudaLaunchKernel(k1m_fn(e->N, dbg, a.window != nullptr), dim3(grid), dim3(k1m_threads(e->N)), params, k1m_smem(e->N), st);
 }
 
-// pair_ok: every work of the launch has noise windows of at least K1PairGeom::MIN_WS bins
 // warp_ok: N = 512 and every work has noise windows of at least K1WarpGeom::MIN_WS bins
-cudaError_t launch_k1(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st, bool i16 = false, bool pair_ok = true,
-                      bool warp_ok = true) {
-    if (e->k1_mid && (e->N == 4096 || e->N == 2048) && !i16) return launch_k1_mid(e, a, dbg, st);
-    if (e->k1_pair && pair_ok) return launch_k1_pair(e, a, dbg, st, i16);
+cudaError_t launch_k1(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st, bool i16 = false, bool warp_ok = true) {
+    if (e->k1_mid && e->N == 4096 && !i16) return launch_k1_mid(e, a, dbg, st);
     if (e->k1_warp && warp_ok) return launch_k1_warp(e, a, dbg, st, i16);
     switch (e->N) {
         case 512: return launch_k1_n<512>(e, a, dbg, st, i16);
@@ -652,6 +622,7 @@ void free_slot(Slot &s) {
     if (s.ev_desc) cudaEventDestroy(s.ev_desc);
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
     if (s.ev_km) cudaEventDestroy(s.ev_km);
+    if (s.ev_k2s) cudaEventDestroy(s.ev_k2s);
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
     s = Slot();
@@ -699,6 +670,7 @@ int alloc_slot(sdr_engine *e, Slot &s) {
     CK(e, cudaEventCreateWithFlags(&s.ev_desc, cudaEventDisableTiming));
     CK(e, cudaEventCreate(&s.ev_k0));
     CK(e, cudaEventCreate(&s.ev_km));
+    CK(e, cudaEventCreate(&s.ev_k2s));
     CK(e, cudaEventCreate(&s.ev_k1));
     CK(e, cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
     return SDR_OK;
@@ -722,6 +694,50 @@ __global__ void __launch_bounds__(128) noise_floor_kernel(const float *psd, int 
         nf_select_variance(real ? wsum[lane] : 0.0, real ? wsum[16 + lane] : 0.0,
                            real ? (double)psd[e + (lane + 1) * ws] : 0.0, ws, n_win, lane, out_min, out_var);
     }
+}
+
+// dsp.FindNoiseFloor (dsp/fft.go:215-252) replayed statement by statement: the slow, exact path for edge widths whose
+// windows are too narrow for the parallel window sums (the reference then closes up to 19 windows, or none).
+// float64 sums in index order, no FMA contraction (Go/amd64 does not fuse).
+__device__ void nf_exact_block(const float *psd, int n, int edge, float *out_min, double *out_var) {
+    const int ws = (n - 2 * edge) / 10;
+    double lowest = (double)psd[0], acc = 0.0, win_mean = 0.0;
+    int filled = 0, start = 0, win_from = 0, win_to = 0;
+    bool none_yet = true;
+    for (int i = edge; i < n - edge; i++) {
+        if (filled == 0) start = i;
+        if (filled == ws) {
+            filled = 0;
+            const double mean = __ddiv_rn(acc, (double)ws);
+            if (mean < lowest || none_yet) {
+                lowest = mean;
+                none_yet = false;
+                win_mean = mean;
+                win_from = start;
+                win_to = i;
+            }
+            acc = 0.0;
+        }
+        acc = __dadd_rn(acc, (double)psd[i]);
+        filled++;
+    }
+    acc = 0.0;
+    for (int i = win_from; i <= win_to; i++) {
+        const double d = __dsub_rn((double)psd[i], win_mean);
+        acc = __dadd_rn(acc, __dmul_rn(d, d));
+    }
+    *out_var = __ddiv_rn(acc, (double)ws);
+    *out_min = (float)lowest;
+}
+
+__global__ void __launch_bounds__(128) nf_exact_kernel(const ExactNf *works, const float *psd, int n, float *psd_floor, double *variance) {
+    const ExactNf w = works[blockIdx.x];
+    for (int b = threadIdx.x; b < w.n_blocks; b += blockDim.x)
+        nf_exact_block(psd + (size_t)(w.block_out + b) * n, n, w.edge_width, &psd_floor[w.block_out + b], &variance[w.block_out + b]);
+}
+
+__global__ void nf_exact_single_kernel(const float *psd, int n, int edge, float *out_min, double *out_var) {
+    nf_exact_block(psd, n, edge, out_min, out_var);
 }
 
 __global__ void kiwi_decode_kernel(const uint32_t *raw, int n_samples, float2 *out) {
@@ -800,6 +816,19 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
         return fail(SDR_ECUDA);
     }
     CKC(cudaStreamCreateWithFlags(&e->s_desc, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&e->ev_post, cudaEventDisableTiming));
+    {
+        const char *v = getenv("SDR_K2_OVERLAP");
+        if (!(v && v[0] == '0')) {
+            // lowest priority by default: K2's CTAs fill the SM slots K1's tail leaves free instead of displacing the
+            // next K1's CTAs (SDR_K2_PRIO=high flips it)
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            const char *pv = getenv("SDR_K2_PRIO");
+            CKC(cudaStreamCreateWithPriority(&e->s_post, cudaStreamNonBlocking, (pv && pv[0] == 'h') ? hi : lo));
+            e->own_post = true;
+        }
+    }
     if (cfg->cuda_stream) {
         e->own_streams = false;
         e->s_compute = e->s_h2d = e->s_d2h = (cudaStream_t)cfg->cuda_stream;
@@ -808,6 +837,7 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
         CKC(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
         CKC(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
     }
+    if (!e->s_post) e->s_post = e->s_compute;
     if (!e->large) {
         std::vector<float2> tw1, tw2;
         build_twiddles(e->N, tw1, tw2);
@@ -815,21 +845,6 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
         CKC(cudaMalloc((void **)&e->d_tw2, tw2.size() * sizeof(float2)));
         CKC(cudaMemcpy(e->d_tw1, tw1.data(), tw1.size() * sizeof(float2), cudaMemcpyHostToDevice));
         CKC(cudaMemcpy(e->d_tw2, tw2.data(), tw2.size() * sizeof(float2), cudaMemcpyHostToDevice));
-        if (e->N == K1PairGeom::N) {
-            // k1_pair.cuh: lane l of warp h multiplies DFT32 output position p (row j = OutIdx<32>(p)) by
-            // W_2048^(l (2j + h))
-            std::vector<float2> twp((size_t)2 * 32 * 32);
-            const double two_pi = 6.283185307179586476925286766559;
-            for (int h = 0; h < 2; h++)
-                for (int p = 0; p < 32; p++)
-                    for (int l = 0; l < 32; l++) {
-                        const int ex = (l * (2 * OutIdx<32>::of(p) + h)) % 2048;
-                        const double ang = -two_pi * (double)ex / 2048.0;
-                        twp[((size_t)h * 32 + p) * 32 + l] = make_float2((float)cos(ang), (float)sin(ang));
-                    }
-            CKC(cudaMalloc((void **)&e->d_twp, twp.size() * sizeof(float2)));
-            CKC(cudaMemcpy(e->d_twp, twp.data(), twp.size() * sizeof(float2), cudaMemcpyHostToDevice));
-        }
     } else {
         auto table = [&](int len, float2 **dst) -> cudaError_t {
             std::vector<float2> t(len);
@@ -913,7 +928,7 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
         e->k1_warp = !(v && v[0] == '0');
         if (e->k1_warp) e->k1w_grid_cap = k1w_grid_cap_for(e->d_window != nullptr, e->sm_count);
     }
-    if (e->N == 2048 || e->N == 4096 || e->N == 8192) {
+    if (e->N == 4096 || e->N == 8192) {
         const int r1 = e->N / 256;
         std::vector<float2> t((size_t)r1 * 256), t256(256);
         const double two_pi = 6.283185307179586476925286766559;
@@ -932,10 +947,6 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
         CKC(cudaMemcpy(e->d_tw256m, t256.data(), t256.size() * sizeof(float2), cudaMemcpyHostToDevice));
         const char *v = getenv("SDR_K1_MID");
         e->k1_mid = !(v && v[0] == '0');
-        if (e->N == 2048) {  // N = 2048: opt-in (SDR_K1_MID2048=1); the three-pass kernel is the default
-            const char *v2 = getenv("SDR_K1_MID2048");
-            e->k1_mid = e->k1_mid && v2 && v2[0] == '1';
-        }
         if (e->k1_mid) e->k1m_grid_cap = k1m_grid_cap_for(e->N, e->d_window != nullptr, e->sm_count);
     }
     CKC(cudaMalloc((void **)&e->d_rolling, (size_t)cfg->max_streams * sizeof(RollingState)));
@@ -947,13 +958,6 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
         e->k1_tw2r = !(v && v[0] == '0');
     }
     if (!e->large) e->k1_grid_cap = k1_grid_cap_for(e->N, e->d_window != nullptr, e->k1_tw2r, e->sm_count);
-    if (e->d_twp) {
-        const char *v = getenv("SDR_K1_PAIR");
-        e->k1_pair = (v && v[0] == '1');
-        const char *st = getenv("SDR_K1_PAIR_STAGES");
-        e->k1p_stages = (st && st[0] == '2') ? 2 : 1;
-        if (e->k1_pair) e->k1p_grid_cap = k1p_grid_cap_for(e->k1p_stages, e->d_window != nullptr, e->sm_count);
-    }
     CKC(cudaGetLastError());
     e->slots.resize(cfg->n_slots);
     for (auto &s : e->slots) {
@@ -973,7 +977,6 @@ void sdr_engine_destroy(sdr_engine *e) {
     for (auto &s : e->slots) free_slot(s);
     cudaFree(e->d_tw1);
     cudaFree(e->d_tw2);
-    cudaFree(e->d_twp);
     cudaFree(e->d_tw_step);
     cudaFree(e->d_tw_mid);
     cudaFree(e->d_tw512);
@@ -987,6 +990,8 @@ void sdr_engine_destroy(sdr_engine *e) {
     cudaFree(e->d_rolling);
     cudaFree(e->d_scratch);
     if (e->s_desc) cudaStreamDestroy(e->s_desc);
+    if (e->own_post && e->s_post) cudaStreamDestroy(e->s_post);
+    if (e->ev_post) cudaEventDestroy(e->ev_post);
     if (e->own_streams) {
         if (e->s_compute) cudaStreamDestroy(e->s_compute);
         if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
@@ -1008,14 +1013,25 @@ int sdr_free_pinned(sdr_engine *e, void *p) {
     return SDR_OK;
 }
 
+static int stream_reset_locked(sdr_engine *e, int stream) {
+    CK(e, cudaSetDevice(e->cfg.device));
+    // cumulationCount := 0 (rx/receiver.go:347): with cum_count == 0 the next segment of the stream starts from
+    // state_in = -1, so the stream's two cum_state rows (2*stream, 2*stream+1) are never read and need no clearing
+    e->streams[stream].cum_count = 0;
+    e->streams[stream].state_row = 0;
+    CK(e, cudaMemsetAsync(e->d_rolling + stream, 0, sizeof(RollingState), e->s_post));
+    return SDR_OK;
+}
+
 int sdr_stream_open(sdr_engine *e, int sample_rate, int *out_stream) {
     if (!e || !out_stream || sample_rate <= 0) return SDR_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
     for (size_t i = 0; i < e->streams.size(); i++) {
         if (!e->streams[i].open) {
             e->streams[i].open = true;
             e->streams[i].sample_rate = sample_rate;
             *out_stream = (int)i;
-            return sdr_stream_reset(e, (int)i);
+            return stream_reset_locked(e, (int)i);
         }
     }
     e->err = "no free stream slot (max_streams reached)";
@@ -1023,30 +1039,41 @@ int sdr_stream_open(sdr_engine *e, int sample_rate, int *out_stream) {
 }
 
 int sdr_stream_close(sdr_engine *e, int stream) {
-    if (!e || stream < 0 || stream >= (int)e->streams.size() || !e->streams[stream].open) return SDR_EINVAL;
+    if (!e) return SDR_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (stream < 0 || stream >= (int)e->streams.size() || !e->streams[stream].open) return SDR_EINVAL;
     e->streams[stream].open = false;
     return SDR_OK;
 }
 
 int sdr_stream_reset(sdr_engine *e, int stream) {
-    if (!e || stream < 0 || stream >= (int)e->streams.size() || !e->streams[stream].open) return SDR_EINVAL;
-    CK(e, cudaSetDevice(e->cfg.device));
-    e->streams[stream].cum_count = 0;
-    CK(e, cudaMemsetAsync(e->d_rolling + stream, 0, sizeof(RollingState), e->s_compute));
-    CK(e, cudaMemsetAsync(e->d_cum_state + (size_t)stream * e->N, 0, (size_t)e->N * sizeof(float), e->s_compute));
-    return SDR_OK;
+    if (!e) return SDR_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (stream < 0 || stream >= (int)e->streams.size() || !e->streams[stream].open) return SDR_EINVAL;
+    return stream_reset_locked(e, stream);
 }
 
 int sdr_stream_cumulation_count(sdr_engine *e, int stream, int *out) {
-    if (!e || !out || stream < 0 || stream >= (int)e->streams.size() || !e->streams[stream].open) return SDR_EINVAL;
+    if (!e || !out) return SDR_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (stream < 0 || stream >= (int)e->streams.size() || !e->streams[stream].open) return SDR_EINVAL;
     *out = e->streams[stream].cum_count;
     return SDR_OK;
 }
 
 int64_t sdr_engine_launch_count(const sdr_engine *e) { return e ? e->launches : 0; }
 
+int sdr_engine_fence(sdr_engine *e) {
+    if (!e) return SDR_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(e, cudaSetDevice(e->cfg.device));
+    if (e->s_post != e->s_compute) CK(e, cudaStreamWaitEvent(e->s_compute, e->ev_post, 0));
+    return SDR_OK;
+}
+
 int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr_ticket *out) {
     if (!e || !works || !out || n_works < 1) return SDR_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
     if (n_works > e->cfg.max_streams) {
         e->err = "more works than max_streams";
         return SDR_EINVAL;
@@ -1056,6 +1083,7 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     // ---- validate (programmer errors: the Go reference panics or logs-and-drops) ----
     long long total_blocks = 0;
     bool any_host = false;
+    bool need_exact = false;  // some work's edge width needs the literal FindNoiseFloor replay on the stored PSD
     {
         std::vector<char> seen(e->streams.size(), 0);
         for (int w = 0; w < n_works; w++) {
@@ -1082,10 +1110,11 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
                     e->err = "work " + std::to_string(w) + ": listener bin out of range";
                     return SDR_EINVAL;
                 }
-            if (!nf_edge_supported(N, wk.edge_width)) {
-                e->err = "work " + std::to_string(w) + ": edge_width leaves noise windows of fewer than 9 bins ((N-2e)/10 < 9)";
+            if (wk.edge_width < 0) {  // the reference indexes psd[edgeWidth]: a negative width panics
+                e->err = "work " + std::to_string(w) + ": negative edge_width";
                 return SDR_EINVAL;
             }
+            if (!nf_edge_supported(N, wk.edge_width)) need_exact = true;
             if (wk.mem == SDR_MEM_DEVICE && ((uintptr_t)wk.iq & 15)) {
                 e->err = "work " + std::to_string(w) + ": device iq must be 16-byte aligned";
                 return SDR_EINVAL;
@@ -1117,17 +1146,20 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
         return SDR_EBUSY;
     }
     Slot &s = *sp;
-    const bool dbg = (flags & SDR_WANT_SPECTRUM) != 0;
+    const bool want_spec = (flags & SDR_WANT_SPECTRUM) != 0;
+    const bool dbg = want_spec || need_exact;  // kernel variant that stores spectrum[] and psd[]
     const bool i16 = works[0].format == SDR_FMT_KIWI_I16BE;
     const size_t sample_floats = i16 ? 1 : 2;  // a complex sample is 4 bytes on the Kiwi wire, 8 as float32 pairs
-    if (dbg && !s.h_spectrum) {
+    if (dbg) {
         const size_t bytes = (size_t)e->cfg.max_blocks_per_batch * N * sizeof(float);
         if (!s.d_spectrum) {
             CK(e, cudaMalloc((void **)&s.d_spectrum, bytes));
             CK(e, cudaMalloc((void **)&s.d_psd, bytes));
         }
-        CK(e, cudaMallocHost((void **)&s.h_spectrum, bytes));
-        CK(e, cudaMallocHost((void **)&s.h_psd, bytes));
+        if (want_spec && !s.h_spectrum) {
+            CK(e, cudaMallocHost((void **)&s.h_spectrum, bytes));
+            CK(e, cudaMallocHost((void **)&s.h_psd, bytes));
+        }
     }
     if (any_host && !s.d_iq) CK(e, cudaMalloc((void **)&s.d_iq, (size_t)e->cfg.max_blocks_per_batch * 2 * N * sizeof(float)));
 
@@ -1137,18 +1169,21 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     WorkParams *wps = reinterpret_cast<WorkParams *>(s.h_desc + dl.works);
     PostWork *pws = reinterpret_cast<PostWork *>(s.h_desc + dl.post);
     int *lbins = reinterpret_cast<int *>(s.h_desc + dl.lbins);
+    ExactNf *exs = reinterpret_cast<ExactNf *>(s.h_desc + dl.exact);
+    int n_exact = 0;
     s.work_block_offset.assign(n_works + 1, 0);
     s.work_flush_offset.assign(n_works + 1, 0);
     int n_segs = 0, n_flushes = 0, block_off = 0, lb_off = 0;
     size_t iq_off = 0;  // floats into d_iq
-    bool pair_ok = true;              // every work's noise windows are wide enough for k1_pair_kernel
+    std::vector<StreamInfo> new_state(n_works);
     bool warp_ok = (N == 512);        // ... and for k1_warp_kernel
     const float *pend_src = nullptr;  // pending coalesced H2D copy
     float *pend_dst = nullptr;
     size_t pend_n = 0;
     for (int w = 0; w < n_works; w++) {
         const sdr_work &wk = works[w];
-        StreamInfo &si = e->streams[wk.stream];
+        // bookkeeping advances on a copy and is committed only when every enqueue of this submit succeeded
+        StreamInfo si = e->streams[wk.stream];
         const float *dev_iq = wk.iq;
         if (wk.mem != SDR_MEM_DEVICE) {
             // host IQ: stage it in the slot's device buffer.  Works whose host ranges are adjacent (one pinned
@@ -1165,15 +1200,17 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
             }
             iq_off += nfl;
         }
-        wps[w].edge_width = wk.edge_width;
-        if (nf_window_size(N, wk.edge_width) < K1PairGeom::MIN_WS) pair_ok = false;
-        if (N != 512 || nf_window_size(N, wk.edge_width) < K1WarpGeom::MIN_WS) warp_ok = false;
+        // the fused kernels get a width they cover; the exact replay overwrites this work's noise scalars afterwards
+        const bool exact = !nf_edge_supported(N, wk.edge_width);
+        wps[w].edge_width = exact ? 0 : wk.edge_width;
+        if (exact) exs[n_exact++] = ExactNf{block_off, wk.n_blocks, wk.edge_width, 0};
+        if (N != 512 || nf_window_size(N, wps[w].edge_width) < K1WarpGeom::MIN_WS) warp_ok = false;
         wps[w].n_listeners = wk.n_listeners;
         wps[w].listener_off = lb_off;
         wps[w].pad = 0;
         {
-            unsigned char *cm = &e->nf_map_cache[(size_t)wk.edge_width * 16];
-            if (cm[0] == 0xff) choose_nf_map(N, wk.edge_width, cm);
+            unsigned char *cm = &e->nf_map_cache[(size_t)wps[w].edge_width * 16];
+            if (cm[0] == 0xff) choose_nf_map(N, wps[w].edge_width, cm);
             memcpy(wps[w].nf_map, cm, 16);
         }
         for (int l = 0; l < wk.n_listeners; l++) lbins[lb_off + l] = wk.listener_bins[l];
@@ -1225,6 +1262,7 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
             rem -= take;
         }
         si.cum_count = c;
+        new_state[w] = si;
         block_off += wk.n_blocks;
     }
     s.work_block_offset[n_works] = block_off;
@@ -1251,7 +1289,6 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     a1.listener_bins = reinterpret_cast<const int *>(s.d_desc + dl.lbins);
     a1.tw1 = e->d_tw1;
     a1.tw2 = e->d_tw2;
-    a1.twp = e->d_twp;
     a1.window = e->d_window;
     a1.cum_state = e->d_cum_state;
     a1.psd_floor = s.d_psd_floor;
@@ -1264,7 +1301,7 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     CK(e, cudaEventRecord(s.ev_k0, e->s_compute));
     int k1_launches = 1;
     if (!e->large) {
-        CK(e, launch_k1(e, a1, dbg, e->s_compute, i16, pair_ok, warp_ok));
+        CK(e, launch_k1(e, a1, dbg, e->s_compute, i16, warp_ok));
     } else if (e->k1_mid && e->N == 8192 && block_off <= e->round_blocks && n_segs >= 2 * e->sm_count) {
         // enough segments to fill the GPU with segment-sequential CTAs: fused single pass (k1_mid.cuh)
         CK(e, launch_k1_mid(e, a1, dbg, e->s_compute));
@@ -1293,6 +1330,12 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
         CK(e, launch_large(e, a1, s.d_tmp, reinterpret_cast<const int *>(s.d_desc + dl.block_seg), block_off, n_segs, e->s_compute));
         k1_launches = 4;
     }
+    if (n_exact > 0) {
+        nf_exact_kernel<<<n_exact, 128, 0, e->s_compute>>>(reinterpret_cast<const ExactNf *>(s.d_desc + dl.exact), s.d_psd, N,
+                                                            s.d_psd_floor, s.d_variance);
+        CK(e, cudaGetLastError());
+        k1_launches++;
+    }
     CK(e, cudaEventRecord(s.ev_km, e->s_compute));
     K2Args a2;
     a2.works = reinterpret_cast<const PostWork *>(s.d_desc + dl.post);
@@ -1309,9 +1352,12 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     a2.flush_peaks = s.d_flush_peaks;
     a2.max_peaks = e->cfg.max_peaks_per_flush;
     a2.n = N;
-    k2_post_kernel<<<n_works, K2_THREADS, 0, e->s_compute>>>(a2);
+    if (e->s_post != e->s_compute) CK(e, cudaStreamWaitEvent(e->s_post, s.ev_km, 0));
+    CK(e, cudaEventRecord(s.ev_k2s, e->s_post));
+    k2_post_kernel<<<n_works, K2_THREADS, 0, e->s_post>>>(a2);
     CK(e, cudaGetLastError());
-    CK(e, cudaEventRecord(s.ev_k1, e->s_compute));
+    CK(e, cudaEventRecord(s.ev_k1, e->s_post));
+    CK(e, cudaEventRecord(e->ev_post, e->s_post));
     s.launches = k1_launches + 1;
     e->launches += k1_launches + 1;
 
@@ -1334,14 +1380,15 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
             if (flags & SDR_WANT_FLUSH_CUM)
                 CK(e, cudaMemcpyAsync(s.h_flush_cum, s.d_flush_cum, nf * N * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
         }
-        if (dbg) {
+        if (want_spec) {
             CK(e, cudaMemcpyAsync(s.h_spectrum, s.d_spectrum, nb * N * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
             CK(e, cudaMemcpyAsync(s.h_psd, s.d_psd, nb * N * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
         }
         CK(e, cudaEventRecord(s.ev_done, e->s_d2h));
     } else {
-        CK(e, cudaEventRecord(s.ev_done, e->s_compute));
+        CK(e, cudaEventRecord(s.ev_done, e->s_post));
     }
+    for (int w = 0; w < n_works; w++) e->streams[works[w].stream] = new_state[w];
     s.busy = true;
     s.collected = false;
     s.ticket = e->next_ticket++;
@@ -1351,6 +1398,7 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
 
 int sdr_collect(sdr_engine *e, sdr_ticket t, int blocking, sdr_result *out) {
     if (!e || !out) return SDR_EINVAL;
+    std::unique_lock<std::mutex> lk(e->mu);
     Slot *sp = find_slot(e, t);
     if (!sp) {
         e->err = "unknown ticket";
@@ -1358,7 +1406,13 @@ int sdr_collect(sdr_engine *e, sdr_ticket t, int blocking, sdr_result *out) {
     }
     Slot &s = *sp;
     if (blocking) {
-        CK(e, cudaEventSynchronize(s.ev_done));
+        // wait without the engine lock: other receivers keep submitting while this one blocks on its ticket (the
+        // slot cannot go away: only this ticket's owner releases it)
+        cudaEvent_t ev = s.ev_done;
+        lk.unlock();
+        const cudaError_t st = cudaEventSynchronize(ev);
+        lk.lock();
+        CK(e, st);
     } else {
         cudaError_t st = cudaEventQuery(s.ev_done);
         if (st == cudaErrorNotReady) return SDR_ENOTREADY;
@@ -1390,13 +1444,14 @@ int sdr_collect(sdr_engine *e, sdr_ticket t, int blocking, sdr_result *out) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1) == cudaSuccess) out->gpu_ms = ms;
     if (cudaEventElapsedTime(&ms, s.ev_k0, s.ev_km) == cudaSuccess) out->k1_ms = ms;
-    if (cudaEventElapsedTime(&ms, s.ev_km, s.ev_k1) == cudaSuccess) out->k2_ms = ms;
+    if (cudaEventElapsedTime(&ms, s.ev_k2s, s.ev_k1) == cudaSuccess) out->k2_ms = ms;
     out->gpu_launches = s.launches;
     return SDR_OK;
 }
 
 int sdr_release(sdr_engine *e, sdr_ticket t) {
     if (!e) return SDR_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
     Slot *sp = find_slot(e, t);
     if (!sp) {
         e->err = "unknown ticket";
@@ -1410,6 +1465,7 @@ int sdr_release(sdr_engine *e, sdr_ticket t) {
 int sdr_ticket_device_ptrs(sdr_engine *e, sdr_ticket t, void **psd_noise_floor, void **noise_variance, void **thresholds,
                            void **taps, void **keys) {
     if (!e) return SDR_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
     Slot *sp = find_slot(e, t);
     if (!sp) {
         e->err = "unknown ticket";
@@ -1427,6 +1483,7 @@ int sdr_ticket_device_ptrs(sdr_engine *e, sdr_ticket t, void **psd_noise_floor, 
 
 int sdr_dsp_iq_to_spectrum_and_psd(sdr_engine *e, const float *iq, int n_blocks, float *spectrum, float *psd) {
     if (!e || !iq || !spectrum || !psd || n_blocks < 1) return SDR_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
     CK(e, cudaSetDevice(e->cfg.device));
     const int N = e->N;
     // every block is its own segment so the calls stay independent of any stream state
@@ -1501,7 +1558,6 @@ int sdr_dsp_iq_to_spectrum_and_psd(sdr_engine *e, const float *iq, int n_blocks,
     a.listener_bins = nullptr;
     a.tw1 = e->d_tw1;
     a.tw2 = e->d_tw2;
-    a.twp = e->d_twp;
     a.window = e->d_window;
     a.cum_state = d_cum;
     a.psd_floor = d_floor;
@@ -1539,10 +1595,11 @@ int sdr_dsp_iq_to_spectrum_and_psd(sdr_engine *e, const float *iq, int n_blocks,
 int sdr_dsp_find_noise_floor(sdr_engine *e, const float *psd, int edge_width, float *min_value, double *variance) {
     if (!e || !psd || !min_value || !variance) return SDR_EINVAL;
     const int N = e->N;
-    if (!nf_edge_supported(N, edge_width)) {
-        e->err = "edge_width leaves noise windows of fewer than 9 bins ((N-2e)/10 < 9)";
+    if (edge_width < 0) {
+        e->err = "negative edge_width";
         return SDR_EINVAL;
     }
+    std::lock_guard<std::mutex> lk(e->mu);
     CK(e, cudaSetDevice(e->cfg.device));
     int rc = ensure_scratch(e, (size_t)N * sizeof(float) + 256);
     if (rc != SDR_OK) return rc;
@@ -1551,7 +1608,8 @@ int sdr_dsp_find_noise_floor(sdr_engine *e, const float *psd, int edge_width, fl
     float *d_min = reinterpret_cast<float *>(p + 8);
     float *d_psd = reinterpret_cast<float *>(p + 256);
     CK(e, cudaMemcpyAsync(d_psd, psd, (size_t)N * sizeof(float), cudaMemcpyHostToDevice, e->s_compute));
-    noise_floor_kernel<<<1, 128, 0, e->s_compute>>>(d_psd, N, edge_width, d_min, d_var);
+    if (nf_edge_supported(N, edge_width)) noise_floor_kernel<<<1, 128, 0, e->s_compute>>>(d_psd, N, edge_width, d_min, d_var);
+    else nf_exact_single_kernel<<<1, 1, 0, e->s_compute>>>(d_psd, N, edge_width, d_min, d_var);
     CK(e, cudaGetLastError());
     e->launches += 1;
     CK(e, cudaMemcpyAsync(min_value, d_min, sizeof(float), cudaMemcpyDeviceToHost, e->s_compute));
@@ -1563,6 +1621,7 @@ int sdr_dsp_find_noise_floor(sdr_engine *e, const float *psd, int edge_width, fl
 int sdr_dsp_find_peaks(sdr_engine *e, const float *cumulation, int cumulation_size, float threshold, sdr_peak *peaks,
                        int max_peaks, int *n_peaks) {
     if (!e || !cumulation || !peaks || !n_peaks || max_peaks < 1 || cumulation_size < 1) return SDR_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
     const int N = e->N;
     CK(e, cudaSetDevice(e->cfg.device));
     int rc = ensure_scratch(e, (size_t)N * sizeof(float) + 256 + (size_t)max_peaks * sizeof(sdr_peak));
@@ -1586,6 +1645,7 @@ int sdr_dsp_find_peaks(sdr_engine *e, const float *cumulation, int cumulation_si
 
 int sdr_kiwi_decode_iq_bytes(sdr_engine *e, const unsigned char *bytes, int n_bytes, float *out) {
     if (!e || !bytes || !out || n_bytes < 4 || (n_bytes & 3)) return SDR_EINVAL;
+    std::lock_guard<std::mutex> lk(e->mu);
     CK(e, cudaSetDevice(e->cfg.device));
     const int n_samples = n_bytes / 4;
     int rc = ensure_scratch(e, (size_t)n_bytes + 256 + (size_t)n_samples * sizeof(float2));

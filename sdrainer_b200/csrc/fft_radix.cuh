@@ -124,4 +124,80 @@ __device__ __forceinline__ void dftR<8>(float2 *v) { dft8(*reinterpret_cast<floa
 template <>
 __device__ __forceinline__ void dftR<16>(float2 *v) { dft16(*reinterpret_cast<float2(*)[16]>(v)); }
 
+// ---- 32-point transform (pass A of the N = 8192 kernel, step 1 of the N = 8192 large path) ----
+// ---- W64 constants (compile-time) ---------------------------------------------------------------------------
+__host__ __device__ constexpr double w64_quarter(int k) {  // cos(2 pi k / 64), k = 0..16
+    constexpr double q[17] = {1.0,
+                              0.99518472667219693,
+                              0.98078528040323043,
+                              0.95694033573220882,
+                              0.92387953251128674,
+                              0.88192126434835505,
+                              0.83146961230254524,
+                              0.77301045336273699,
+                              0.70710678118654757,
+                              0.63439328416364549,
+                              0.55557023301960229,
+                              0.47139673682599781,
+                              0.38268343236508984,
+                              0.29028467725446233,
+                              0.19509032201612833,
+                              0.09801714032956077,
+                              0.0};
+    return q[k];
+}
+__host__ __device__ constexpr double w64_cos(int k) {
+    k &= 63;
+    return k <= 16 ? w64_quarter(k) : k <= 32 ? -w64_quarter(32 - k) : k <= 48 ? -w64_quarter(k - 32) : w64_quarter(64 - k);
+}
+__host__ __device__ constexpr double w64_sin(int k) { return w64_cos(k - 16); }  // sin(t) = cos(t - pi/2)
+
+// a * W64^E, E a compile-time exponent; the multiples of 8 cost at most two packed instructions
+template <int E>
+__device__ __forceinline__ float2 mul_w64(float2 a) {
+    constexpr int e = E & 63;
+    if constexpr (e == 0) return a;
+    else if constexpr (e == 16) return mul_mi(a);
+    else if constexpr (e == 32) return make_float2(-a.x, -a.y);
+    else if constexpr (e == 48) return make_float2(-a.y, a.x);
+    else if constexpr (e == 8) return mul_w8_1(a);
+    else if constexpr (e == 24) return mul_w8_3(a);
+    else {
+        constexpr float c = (float)w64_cos(e), s = (float)(-w64_sin(e));
+        return cmul(a, make_float2(c, s));
+    }
+}
+
+template <>
+struct OutIdx<32> {  // position p = 8*ka + q holds X[ka + 4*OutIdx<8>(q)]
+    __host__ __device__ static constexpr int of(int p) { return (p >> 3) + 4 * OutIdx<8>::of(p & 7); }
+};
+
+template <int KA, int B>
+__device__ __forceinline__ void dft32_twiddle_one(float2 (&v)[32]) {
+    v[8 * KA + B] = mul_w64<2 * B * KA>(v[8 * KA + B]);  // W32^(b ka) = W64^(2 b ka)
+}
+template <int KA>
+__device__ __forceinline__ void dft32_twiddle_row(float2 (&v)[32]) {
+    dft32_twiddle_one<KA, 1>(v);
+    dft32_twiddle_one<KA, 2>(v);
+    dft32_twiddle_one<KA, 3>(v);
+    dft32_twiddle_one<KA, 4>(v);
+    dft32_twiddle_one<KA, 5>(v);
+    dft32_twiddle_one<KA, 6>(v);
+    dft32_twiddle_one<KA, 7>(v);
+}
+
+// 32-point forward DFT in registers: n = 8a + b; DFT4 over a, twiddle W32^(b ka), DFT8 over b.
+// Natural order in; v[p] = X[OutIdx<32>::of(p)] out.  64 + 40 + 112 = 216 packed instructions.
+__device__ __forceinline__ void dft32(float2 (&v)[32]) {
+#pragma unroll
+    for (int b = 0; b < 8; b++) dft4(v[b], v[b + 8], v[b + 16], v[b + 24]);
+    dft32_twiddle_row<1>(v);
+    dft32_twiddle_row<2>(v);
+    dft32_twiddle_row<3>(v);
+#pragma unroll
+    for (int ka = 0; ka < 4; ka++) dft8(*reinterpret_cast<float2(*)[8]>(&v[8 * ka]));
+}
+
 }  // namespace sdr

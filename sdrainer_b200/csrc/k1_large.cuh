@@ -18,7 +18,6 @@
 #include <stdint.h>
 
 #include "k1_spectral.cuh"
-#include "k1_pair.cuh"
 
 namespace sdr {
 

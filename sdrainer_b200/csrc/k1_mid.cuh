@@ -1,4 +1,4 @@
-// k1_mid.cuh -- fused spectral front end for N = R1 x 256, R1 = 8 | 16 | 32 (N = 2048, 4096, 8192): one pass over the IQ,
+// k1_mid.cuh -- fused spectral front end for N = R1 x 256, R1 = 16 | 32 (N = 4096, 8192): one pass over the IQ,
 // one launch, the cumulation in registers -- the K1 contract (k1_spectral.cuh) at block sizes whose exchange no
 // longer fits the three-pass kernel's register/shared-memory budget.
 //
@@ -24,9 +24,6 @@
 #ifndef SDR_K1M_MINB16
 #define SDR_K1M_MINB16 2
 #endif
-#ifndef SDR_K1M_MINB8
-#define SDR_K1M_MINB8 4
-#endif
 
 namespace sdr {
 
@@ -37,20 +34,18 @@ struct K1MidGeom {
     static constexpr int CPT = 256 / T;                // columns per thread in pass A
     static constexpr int JR = (R1 + 15) / 16;          // rows per half-warp
     static constexpr int LOG_R1 = (R1 == 8) ? 3 : (R1 == 16) ? 4 : 5;
-    static constexpr int MINB = (R1 == 8) ? SDR_K1M_MINB8 : (R1 == 16) ? SDR_K1M_MINB16 : 2;
+    static constexpr int MINB = (R1 == 16) ? SDR_K1M_MINB16 : 2;
     static constexpr int E_BYTES = R1 * HW_PITCH * 8;  // 34 944 / 69 888
     static constexpr int TPW = (T / 10) / 3 * 3;       // noise floor: threads per window (3 lanes x TPW/3 partials combine)
     static constexpr int NFB = 8;                      // noise floor: blocks per batched selection
     static constexpr int PART_BYTES = T * 8;
     static constexpr int NF_BYTES = NFB * 10 * (8 + 8 + 4);
     static constexpr int SMEM_BYTES = E_BYTES + PART_BYTES + NF_BYTES + 64;
-    static_assert(R1 == 8 || R1 == 16 || R1 == 32, "N = 2048, 4096 or 8192");
+    static_assert(R1 == 16 || R1 == 32, "N = 4096 or 8192");
 };
 
 template <int R1>
 __device__ __forceinline__ void dft_r1(float2 (&v)[R1]);
-template <>
-__device__ __forceinline__ void dft_r1<8>(float2 (&v)[8]) { dft8(v); }
 template <>
 __device__ __forceinline__ void dft_r1<16>(float2 (&v)[16]) { dft16(v); }
 template <>

@@ -68,7 +68,6 @@ struct K1Args {
     float *flush_cum;       // [flushes][N]
     float *dbg_spectrum;    // [blocks][N] (DEBUG_STORE)
     float *dbg_psd;         // [blocks][N]
-    const float2 *twp;      // k1_pair.cuh: [2][32][32] W_2048^(l (2 j(p) + h)), nullptr when N != 2048
 };
 
 // ---- PTX helpers: mbarrier + TMA bulk copy -------------------------------------------------

@@ -50,7 +50,13 @@ struct ReceiverBox {
     std::string scratch;
     ReceiverBox(sdr_engine *e, int strain, int pool) : rx("rx", strain ? rx::ReceiverMode::Strain : rx::ReceiverMode::Decode, &clock, e, pool) {
         rx.AddReporter(&log);
+        rx.recordReports = true;  // the parity tests read one report per block and every flush's peak list
     }
+};
+struct DispatcherBox {
+    rx::Dispatcher d;
+    std::string scratch;
+    DispatcherBox(sdr_engine *e, int bs, int max_rx) : d(e, bs, max_rx) {}
 };
 }  // namespace
 
@@ -208,6 +214,34 @@ int sdrh_receiver_flush_peaks(void *p, int f, int *bins, long long *freqs, int c
     }
     return n;
 }
+
+// ---- rx.Dispatcher: many receivers, one sdr_submit per tick ----
+void *sdrh_dispatcher_new(void *engine, int block_size, int max_receivers) {
+    try {
+        return new DispatcherBox((sdr_engine *)engine, block_size, max_receivers);
+    } catch (const std::exception &) {
+        return nullptr;
+    }
+}
+void sdrh_dispatcher_free(void *p) { delete (DispatcherBox *)p; }
+int sdrh_dispatcher_add(void *p, void *receiver) {
+    try {
+        ((DispatcherBox *)p)->d.Add(&((ReceiverBox *)receiver)->rx);
+        return 0;
+    } catch (const std::exception &) {
+        return -1;
+    }
+}
+int sdrh_dispatcher_tick(void *p) {
+    try {
+        return ((DispatcherBox *)p)->d.Tick();
+    } catch (const std::exception &e) {
+        ((DispatcherBox *)p)->scratch = e.what();
+        return -1;
+    }
+}
+int sdrh_dispatcher_submits(void *p) { return ((DispatcherBox *)p)->d.submits; }
+const char *sdrh_dispatcher_error(void *p) { return ((DispatcherBox *)p)->scratch.c_str(); }
 
 // ---- cw.AudioDemodulator over the GPU Goertzel bank ----
 struct AudioBox {

@@ -435,7 +435,7 @@ class PeaksTable {  // rx/peaks.go
     };
     PeaksTable(int size, const Clock *clock) : bins_(size, nullptr), clock_(clock) {}
     void ForcePut(dsp::Peak *p) { put(p, true); }
-    void Put(dsp::Peak *p) { put(p, false); }
+    bool Put(dsp::Peak *p) { return put(p, false); }  // false: refused (overlaps an active / inactive peak)
     dsp::Peak *Get(int bin) const {
         if (bin < 0 || bin >= (int)bins_.size() || !bins_[bin]) return nullptr;
         return bins_[bin]->Peak;
@@ -455,7 +455,14 @@ class PeaksTable {  // rx/peaks.go
             i = (size_t)to + 1;
         }
     }
-    void Reset() { std::fill(bins_.begin(), bins_.end(), nullptr); }
+    void Reset() {
+        std::fill(bins_.begin(), bins_.end(), nullptr);
+        for (auto &en : entries_)
+            if (onDrop) onDrop(en->Peak);
+        entries_.clear();
+    }
+    // called with the Peak of every entry that left the table (the Go code leaves this to the garbage collector)
+    std::function<void(dsp::Peak *)> onDrop;
     void Activate(dsp::Peak *p) {
         Entry *e = getInternal(p);
         if (!e) return;  // the reference would nil-deref
@@ -489,12 +496,12 @@ class PeaksTable {  // rx/peaks.go
     uint64_t rng = 1;
 
    private:
-    void put(dsp::Peak *p, bool force) {  // :46-100
+    bool put(dsp::Peak *p, bool force) {  // :46-100
         int clearFrom = -1, clearTo = -1;
         for (int i = std::max(0, p->From); i <= std::min(p->To, (int)bins_.size() - 1); i++) {
             Entry *e = bins_[i];
             if (!e) continue;
-            if (!force && (e->state == peakActive || e->state == peakInactive)) return;
+            if (!force && (e->state == peakActive || e->state == peakInactive)) return false;
             if (clearFrom == -1) clearFrom = e->Peak->From;
             clearTo = e->Peak->To;
         }
@@ -502,9 +509,29 @@ class PeaksTable {  // rx/peaks.go
         entries_.emplace_back(new Entry{p, peakNew, clock_->Now()});
         Entry *ne = entries_.back().get();
         for (int i = std::max(0, p->From); i <= std::min(p->To, (int)bins_.size() - 1); i++) bins_[i] = ne;
+        return true;
     }
     void clear(int from, int to) {
-        for (int i = std::max(0, from); i <= std::min(to, (int)bins_.size() - 1); i++) bins_[i] = nullptr;
+        std::vector<Entry *> gone;
+        for (int i = std::max(0, from); i <= std::min(to, (int)bins_.size() - 1); i++) {
+            Entry *en = bins_[i];
+            bins_[i] = nullptr;
+            if (en && (gone.empty() || gone.back() != en)) gone.push_back(en);
+        }
+        for (Entry *en : gone) dropIfUnreferenced(en);
+    }
+    void dropIfUnreferenced(Entry *en) {
+        // a replaced peak can be wider than the range being cleared (rx/peaks.go clears exactly [from, to]): the entry
+        // stays alive while any bin still points at it
+        for (int i = std::max(0, en->Peak->From); i <= std::min(en->Peak->To, (int)bins_.size() - 1); i++)
+            if (bins_[i] == en) return;
+        for (size_t k = 0; k < entries_.size(); k++)
+            if (entries_[k].get() == en) {
+                if (onDrop) onDrop(en->Peak);
+                entries_[k].swap(entries_.back());
+                entries_.pop_back();
+                return;
+            }
     }
     Entry *getInternal(dsp::Peak *p) {
         Entry *e = bins_[p->From];
@@ -554,6 +581,12 @@ class TextProcessor : public cw::Writer {
         lastWrite_ = clock_->Now();
         text_ += s;
     }
+    // rx/text_processor.go:194-199: after defaultWriteTimeout (5 s) of silence the reference flushes its callsign
+    // window; the callsign logic itself is out of scope, the tick that triggers it is mirrored (and counted)
+    void CheckWriteTimeout() {
+        if (clock_->Now() - lastWrite_ > 5 * 1000000000ll) writeTimeouts++;
+    }
+    int writeTimeouts = 0;
     const std::string &Text() const { return text_; }
 
    private:
@@ -593,11 +626,13 @@ class Listener {  // rx/listener.go:19-147
     bool ListenState(bool state) {
         if (!Attached()) return false;
         const bool k = demodulator_.TickState(state);
-        keys_.push_back(k ? 1 : 0);
+        if (recordKeys) keys_.push_back(k ? 1 : 0);
         return k;
     }
+    void CheckWriteTimeout() { textProcessor_.CheckWriteTimeout(); }  // rx/listener.go:138-140
     const std::string &Text() const { return textProcessor_.Text(); }
     const std::vector<uint8_t> &Keys() const { return keys_; }
+    bool recordKeys = true;  // test hook: keep the debounced key stream (grows with the run time)
     int tapIndex = -1;  // column of this listener in the batch being consumed
 
    private:
@@ -675,6 +710,7 @@ class Receiver {
         blockSize_ = blockSize;
         frequencyMapping_.reset(new dsp::FrequencyMapping(sampleRate, blockSize, centerFrequency_));
         peaks_.reset(new PeaksTable(blockSize, clock_));
+        peaks_->onDrop = [this](dsp::Peak *p) { releasePeak(p); };
         peaks_->deterministic = deterministicFindNext;
         peaks_->rng = rngSeed;
         if (sdr_stream_open(engine_, sampleRate, &stream_) != SDR_OK) throw std::runtime_error(sdr_last_error(engine_));
@@ -682,6 +718,7 @@ class Receiver {
         if (sdr_alloc_pinned(engine_, (size_t)cumulationSize * 2 * blockSize * sizeof(float), &p) != SDR_OK)
             throw std::runtime_error(sdr_last_error(engine_));
         ring_ = (float *)p;
+        cumulationCount_ = 0;  // run() starts with cumulationCount := 0 (:347); sdr_stream_open reset the engine's count too
         started_ = true;
     }
     void Stop() {  // :148-164
@@ -731,44 +768,62 @@ class Receiver {
         queue_.emplace_back(data, data + len);
         return true;
     }
+    // ---- batched interface: used by Process() below and by the Dispatcher (many receivers, one sdr_submit) ----
+    // Moves the queued frames of this receiver -- at most up to the next flush: listeners change there -- into `dst`
+    // (C-owned pinned memory, contiguous) and describes them as one sdr_work.  Returns the blocks staged (0: idle).
+    int Stage(float *dst, sdr_work &w) {
+        const int room = cumulationSize - cumulationCount_;
+        const int nb = (int)std::min<size_t>(queue_.size(), (size_t)room);
+        if (nb <= 0) return 0;
+        for (int b = 0; b < nb; b++) {
+            std::memcpy(dst + (size_t)b * 2 * blockSize_, queue_.front().data(), (size_t)2 * blockSize_ * sizeof(float));
+            queue_.pop_front();
+        }
+        stagedBins_.clear();
+        for (Listener *l : listeners_.Listeners()) {
+            l->tapIndex = l->Attached() ? (int)stagedBins_.size() : -1;
+            if (l->Attached()) stagedBins_.push_back(l->SignalBin());
+        }
+        w = sdr_work{};
+        w.stream = stream_;
+        w.n_blocks = nb;
+        w.iq = dst;
+        w.mem = SDR_MEM_HOST;
+        w.edge_width = edgeWidth_;
+        w.peak_threshold = peakThreshold_;
+        w.n_listeners = (int)stagedBins_.size();
+        w.listener_bins = stagedBins_.data();
+        return nb;
+    }
+    // peaks are always scanned in strain mode: a listener may time out inside the batch and free a pool slot
+    bool WantsPeaks() const { return mode_ == ReceiverMode::Strain; }
+    // the rest of the frame iteration (:383-461) for work `wi` of a collected result
+    void Consume(const sdr_result &r, int wi) {
+        const int b0 = r.work_block_offset[wi], b1 = r.work_block_offset[wi + 1];
+        for (int b = b0; b < b1; b++) consumeBlock(r, b);
+        if (r.work_flush_offset[wi + 1] > r.work_flush_offset[wi]) consumeFlush(r, r.work_flush_offset[wi]);
+    }
+    bool Idle() const { return queue_.empty(); }
+    bool Started() const { return started_; }
+    int BlockSize() const { return blockSize_; }
     // The frame iteration of run() (:364-461) for every queued frame.  Returns the number of blocks processed.
     int Process() {
         int done = 0;
-        while (!queue_.empty()) {
-            const int room = cumulationSize - cumulationCount_;  // never cross a flush: listeners change there
-            const int nb = (int)std::min<size_t>(queue_.size(), (size_t)room);
-            for (int b = 0; b < nb; b++) {
-                std::memcpy(ring_ + (size_t)b * 2 * blockSize_, queue_.front().data(), (size_t)2 * blockSize_ * sizeof(float));
-                queue_.pop_front();
-            }
-            std::vector<int> bins;
-            for (Listener *l : listeners_.Listeners()) {
-                l->tapIndex = l->Attached() ? (int)bins.size() : -1;
-                if (l->Attached()) bins.push_back(l->SignalBin());
-            }
-            sdr_work w{};
-            w.stream = stream_;
-            w.n_blocks = nb;
-            w.iq = ring_;
-            w.mem = SDR_MEM_HOST;
-            w.edge_width = edgeWidth_;
-            w.peak_threshold = peakThreshold_;
-            w.n_listeners = (int)bins.size();
-            w.listener_bins = bins.data();
-            // peaks are always scanned in strain mode: a listener may time out inside this batch and free a pool slot
-            const bool wantPeaks = mode_ == ReceiverMode::Strain;
+        sdr_work w;
+        int nb;
+        while ((nb = Stage(ring_, w)) > 0) {
             sdr_ticket t;
-            if (sdr_submit(engine_, &w, 1, wantPeaks ? 0 : SDR_NO_PEAKS, &t) != SDR_OK) throw std::runtime_error(sdr_last_error(engine_));
+            if (sdr_submit(engine_, &w, 1, WantsPeaks() ? 0 : SDR_NO_PEAKS, &t) != SDR_OK) throw std::runtime_error(sdr_last_error(engine_));
             sdr_result r;
             if (sdr_collect(engine_, t, 1, &r) != SDR_OK) throw std::runtime_error(sdr_last_error(engine_));
-            for (int b = 0; b < nb; b++) consumeBlock(r, b);
-            if (r.n_flushes > 0) consumeFlush(r);
+            Consume(r, 0);
             sdr_release(engine_, t);
             done += nb;
         }
         return done;
     }
 
+    bool recordReports = false;  // test hooks: keep one BlockReport per block / the peak list of every flush
     const std::vector<BlockReport> &Reports() const { return reports_; }
     const std::vector<std::unique_ptr<Listener>> &AllListeners() const { return allListeners_; }
     const std::vector<int64_t> &AttachBlocks() const { return attachBlocks_; }
@@ -795,6 +850,18 @@ class Receiver {
         peakStore_.emplace_back(new dsp::Peak(p));
         return peakStore_.back().get();
     }
+    // the table dropped this peak; keep the storage only while a listener is still attached to it (a ForcePut can
+    // replace an active peak, rx/peaks.go:46-60)
+    void releasePeak(dsp::Peak *p) {
+        for (Listener *l : listeners_.Listeners())
+            if (l->Peak() == p) return;
+        for (size_t k = 0; k < peakStore_.size(); k++)
+            if (peakStore_[k].get() == p) {
+                peakStore_[k].swap(peakStore_.back());
+                peakStore_.pop_back();
+                return;
+            }
+    }
     dsp::Peak newPeakCenteredOnBin(int centerBin) {  // :491-500
         dsp::Peak peak;
         peak.From = std::max(0, centerBin - peakPadding);
@@ -809,10 +876,13 @@ class Receiver {
         const int64_t nowS = clock_->Now() / kSecond;
         if (nowS > lastCleanupS_) {  // cleanupTicker, :359-363
             lastCleanupS_ = nowS;
+            for (Listener *l : listeners_.Listeners()) l->CheckWriteTimeout();
             peaks_->Cleanup();
         }
-        const float *th = r.thresholds + (size_t)b * 4;
-        reports_.push_back(BlockReport{r.psd_noise_floor[b], th[0], th[1], th[2], th[3], r.noise_variance[b]});
+        if (recordReports) {
+            const float *th = r.thresholds + (size_t)b * 4;
+            reports_.push_back(BlockReport{r.psd_noise_floor[b], th[0], th[1], th[2], th[3], r.noise_variance[b]});
+        }
         std::vector<Listener *> detached;
         for (Listener *l : listeners_.Listeners()) {
             if (!l->Attached() || l->tapIndex < 0) continue;
@@ -827,19 +897,20 @@ class Receiver {
         cumulationCount_++;
         blockIndex_++;
     }
-    void consumeFlush(const sdr_result &r) {  // :409-460
+    void consumeFlush(const sdr_result &r, int f) {  // :409-460
         cumulationCount_ = 0;
-        flushPeaks_.emplace_back();
+        if (recordReports) flushPeaks_.emplace_back();
         if (mode_ != ReceiverMode::Strain || !listeners_.Available()) return;
-        const int n = std::min(r.flush_n_peaks[0], r.max_peaks_per_flush);
+        const int n = std::min(r.flush_n_peaks[f], r.max_peaks_per_flush);
+        const sdr_peak *gp = r.flush_peaks + (size_t)f * r.max_peaks_per_flush;
         for (int i = 0; i < n; i++) {
-            const dsp::Peak p = dsp::FromGpuPeak(r.flush_peaks[i], blockSize_, *frequencyMapping_);
-            flushPeaks_.back().push_back(p);
+            const dsp::Peak p = dsp::FromGpuPeak(gp[i], blockSize_, *frequencyMapping_);
+            if (recordReports) flushPeaks_.back().push_back(p);
             dsp::Peak centered = newPeakCenteredOnBin(p.SignalBin);  // newPeakCenteredOnSignal :474-480
             centered.SignalFrequency = p.SignalFrequency;
             centered.SignalValue = p.SignalValue;
             centered.SignalBin = p.SignalBin;
-            peaks_->Put(store(centered));
+            if (!peaks_->Put(store(centered))) peakStore_.pop_back();  // refused: nothing refers to it
         }
         dsp::Peak *selected = peaks_->FindNext();
         if (selected) {
@@ -866,6 +937,7 @@ class Receiver {
     bool started_ = false;
     int stream_ = -1;
     float *ring_ = nullptr;
+    std::vector<int> stagedBins_;
     std::deque<std::vector<float>> queue_;
     std::unique_ptr<dsp::FrequencyMapping> frequencyMapping_;
     std::unique_ptr<PeaksTable> peaks_;
@@ -877,6 +949,69 @@ class Receiver {
     std::vector<std::vector<dsp::Peak>> flushPeaks_;
     int cumulationCount_ = 0;
     int64_t blockIndex_ = 0, lastCleanupS_ = 0;
+};
+
+// Multi-receiver engine (rx/receiver.go:315-364 for R receivers at once): the reference runs one
+// goroutine per rx.Receiver, each handling one frame at a time.  The GPU path wants the frames of ALL receivers that
+// share an engine in ONE sdr_submit per tick -- one H2D copy (the works are staged back to back in one pinned arena),
+// one K1 launch over every stream's segments, one K2, one D2H -- and hands each receiver its slice of the result.
+// Receivers stay unchanged otherwise: IQData() enqueues (and drops when full), setters apply between ticks.
+class Dispatcher {
+   public:
+    Dispatcher(sdr_engine *engine, int blockSize, int maxReceivers) : engine_(engine), blockSize_(blockSize) {
+        void *p = nullptr;
+        arenaFloats_ = (size_t)maxReceivers * cumulationSize * 2 * blockSize;
+        if (sdr_alloc_pinned(engine_, arenaFloats_ * sizeof(float), &p) != SDR_OK) throw std::runtime_error(sdr_last_error(engine_));
+        arena_ = (float *)p;
+        maxReceivers_ = maxReceivers;
+    }
+    ~Dispatcher() { sdr_free_pinned(engine_, arena_); }
+    void Add(Receiver *r) {
+        if ((int)receivers_.size() >= maxReceivers_) throw std::invalid_argument("dispatcher is full");
+        receivers_.push_back(r);
+    }
+    // Drains every receiver's queue.  One pass takes each receiver up to its next flush; passes repeat until all
+    // queues are empty.  Returns the number of blocks processed; `submits` counts the sdr_submit calls made.
+    int Tick() {
+        int done = 0;
+        for (;;) {
+            works_.clear();
+            owners_.clear();
+            size_t off = 0;
+            bool peaks = false;
+            for (Receiver *r : receivers_) {
+                if (!r->Started() || r->Idle() || r->BlockSize() != blockSize_) continue;
+                sdr_work w;
+                const int nb = r->Stage(arena_ + off, w);
+                if (nb <= 0) continue;
+                off += (size_t)nb * 2 * blockSize_;
+                works_.push_back(w);
+                owners_.push_back(r);
+                peaks = peaks || r->WantsPeaks();
+                done += nb;
+            }
+            if (works_.empty()) break;
+            sdr_ticket t;
+            if (sdr_submit(engine_, works_.data(), (int)works_.size(), peaks ? 0 : SDR_NO_PEAKS, &t) != SDR_OK)
+                throw std::runtime_error(sdr_last_error(engine_));
+            submits++;
+            sdr_result r;
+            if (sdr_collect(engine_, t, 1, &r) != SDR_OK) throw std::runtime_error(sdr_last_error(engine_));
+            for (size_t i = 0; i < owners_.size(); i++) owners_[i]->Consume(r, (int)i);
+            sdr_release(engine_, t);
+        }
+        return done;
+    }
+    int submits = 0;
+
+   private:
+    sdr_engine *engine_;
+    int blockSize_, maxReceivers_ = 0;
+    float *arena_ = nullptr;
+    size_t arenaFloats_ = 0;
+    std::vector<Receiver *> receivers_;
+    std::vector<sdr_work> works_;
+    std::vector<Receiver *> owners_;
 };
 
 }  // namespace rx

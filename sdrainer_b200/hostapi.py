@@ -48,6 +48,8 @@ def lib():
         "sdrh_receiver_n_events": (i, [vp]), "sdrh_receiver_event": (cp, [vp, i]),
         "sdrh_receiver_n_flushes": (i, [vp]),
         "sdrh_receiver_flush_peaks": (i, [vp, i, C.POINTER(i), C.POINTER(ll), i]),
+        "sdrh_dispatcher_new": (vp, [vp, i, i]), "sdrh_dispatcher_free": (None, [vp]), "sdrh_dispatcher_add": (i, [vp, vp]),
+        "sdrh_dispatcher_tick": (i, [vp]), "sdrh_dispatcher_submits": (i, [vp]), "sdrh_dispatcher_error": (cp, [vp]),
         "sdrh_audio_new": (vp, [d, i]), "sdrh_audio_free": (None, [vp]), "sdrh_audio_blocksize": (i, [vp]),
         "sdrh_audio_set_scale": (None, [vp, d]), "sdrh_audio_write": (i, [vp, C.POINTER(C.c_float), i]),
         "sdrh_audio_close": (None, [vp]), "sdrh_audio_text": (cp, [vp]),
@@ -118,6 +120,9 @@ class Receiver:
             raise RuntimeError("Receiver.Start failed")
         self.block_size = block_size
 
+    def stop(self):
+        self.L.sdrh_receiver_stop(self.h)
+
     def iq_data(self, sample_rate, frame: np.ndarray) -> bool:
         frame = np.ascontiguousarray(frame, np.float32)
         return bool(self.L.sdrh_receiver_iq_data(self.h, sample_rate, frame.ctypes.data_as(C.POINTER(C.c_float)), frame.size))
@@ -164,3 +169,40 @@ class Receiver:
 
     def n_flushes(self):
         return self.L.sdrh_receiver_n_flushes(self.h)
+
+
+class Dispatcher:
+    """rx.Dispatcher (host/sdrhost.hpp): drains the queues of many Receivers into ONE sdr_submit per tick."""
+
+    def __init__(self, engine: capi.Engine, block_size: int, max_receivers: int):
+        self.L = lib()
+        self.h = self.L.sdrh_dispatcher_new(engine.h, block_size, max_receivers)
+        if not self.h:
+            raise RuntimeError("Dispatcher: pinned arena allocation failed")
+        self._rx = []
+
+    def add(self, rx: Receiver):
+        if self.L.sdrh_dispatcher_add(self.h, rx.h) != 0:
+            raise RuntimeError("dispatcher is full")
+        self._rx.append(rx)
+
+    def tick(self) -> int:
+        n = self.L.sdrh_dispatcher_tick(self.h)
+        if n < 0:
+            raise RuntimeError(self.L.sdrh_dispatcher_error(self.h).decode())
+        return n
+
+    @property
+    def submits(self) -> int:
+        return self.L.sdrh_dispatcher_submits(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sdrh_dispatcher_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

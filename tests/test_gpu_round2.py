@@ -1,0 +1,260 @@
+"""Round-2 GPU parity tests: the reference-held cw/testdata fixtures through every spectral kernel (SURVEY appendix B
+re-blocked at N = 512 ... 65536), the exact dsp.FindNoiseFloor replay for narrow windows, stream-state isolation,
+Receiver stop/start, and the multi-receiver dispatcher against the oracle's Receiver.run driver."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import parity_util as pu
+from conftest import GOLDEN
+from sdrainer_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def host():
+    from sdrainer_b200 import _build, hostapi
+    _build.build_host()
+    hostapi.lib()
+    return hostapi
+
+
+def _golden_streams():
+    with open(os.path.join(GOLDEN, "cw_keystreams.json"), encoding="utf-8") as f:
+        out = []
+        for s in json.load(f)["streams"]:
+            bits, cur = [], s["first"]
+            for r in s["runs"]:
+                bits.extend([cur] * r)
+                cur ^= 1
+            out.append((s["name"], np.asarray(bits, np.uint8), s["expected"]))
+        return out
+
+
+def _resynth(bits, n, kbin, warm, tail, seed):
+    """one block per tick, bounded-PSD background built in the frequency domain, a phase-continuous
+    on-bin tone on key-down ticks.  The tone amplitude scales with 1/sqrt(N) so that tone / background stays at the
+    64 dB of the N = 512 fixture at every block size."""
+    rng = np.random.default_rng(seed)
+    total = warm + len(bits) + tail
+    a = 0.01 * np.sqrt(512.0 / n)
+    tone = a * np.exp(2j * np.pi * (kbin - n // 2) * np.arange(n) / n)
+    iq = np.empty((total, n, 2), np.float32)
+    for b in range(total):
+        P = rng.uniform(0.5, 1.5, n) * (n * 2e-8)
+        x = np.fft.ifft(np.sqrt(P) * np.exp(2j * np.pi * rng.uniform(0, 1, n)))
+        if warm <= b < warm + len(bits) and bits[b - warm]:
+            x = x + tone
+        iq[b, :, 0], iq[b, :, 1] = x.real, x.imag
+    return iq.reshape(-1)
+
+
+# which kernel serves which block size: tests/ asserts on results only; the forcing switches make single-stream
+# submits take the many-stream kernels (k1_mid8k / k1_wide) that the engine would otherwise reserve for full launches
+KERNEL_ENV = {512: {}, 1024: {}, 2048: {}, 4096: {}, 8192: {"SDR_K1_MID8K": "force"}}
+
+
+@pytest.mark.parametrize("n", [512, 1024, 2048, 4096, 8192])
+def test_all_nine_goldens_keys_and_text_through_the_gpu(capi, host, monkeypatch, n):
+    """cw/decode_test.go:177-213: the nine recorded key streams, re-synthesised as IQ at block size n (tick = n/fs kept
+    at 10.67 ms), must come back bit-exact as key states from FFT -> noise floor -> thresholds -> value > threshold on
+    the GPU, and as the golden text from ONE decoder instance Reset() between files (as the reference test does)."""
+    for k, v in KERNEL_ENV[n].items():
+        monkeypatch.setenv(k, v)
+    fs = 48000 * n // 512
+    warm, tail = 70, 40
+    kbin = n // 2 + n // 5 + 3
+    dec = host.Decoder(fs, n)
+    streams = _golden_streams()
+    longest = max(len(b) for _, b, _ in streams) + warm + tail
+    with capi.Engine(n, max_streams=1, max_listeners=4, max_blocks_per_batch=longest, max_peaks_per_flush=64) as eng:
+        sid = eng.open_stream(fs)
+        for i, (name, bits, expected) in enumerate(streams):
+            iq = _resynth(bits, n, kbin, warm, tail, seed=100 + i)
+            eng.reset_stream(sid)
+            res = eng.collect(eng.submit([dict(stream=sid, iq=iq, listener_bins=[kbin])], capi.NO_PEAKS))
+            keys = res.keys[warm:warm + len(bits), 0]
+            assert np.array_equal(keys, bits), f"{name}: {int((keys != bits).sum())} key states differ at N={n}"
+            assert not res.keys[:warm, 0].any() and not res.keys[warm + len(bits):, 0].any()
+            dec.reset()  # Decoder.Reset keeps lastState: files run in the listed order on one instance
+            dec.feed(keys)
+            dec.stop()
+            assert dec.text == expected, name
+
+
+def test_golden_through_the_wideband_kernel(capi, host, monkeypatch):
+    """the same fixture at N = 65536 (BASELINE config 5 shape) through the single-pass wideband kernel"""
+    monkeypatch.setenv("SDR_K1_WIDE", "force")
+    n = 65536
+    fs = 48000 * n // 512
+    name, bits, expected = _golden_streams()[5]  # ly2px_1: 213 ticks
+    warm, tail, kbin = 62, 5, n // 2 + 9001
+    iq = _resynth(bits, n, kbin, warm, tail, seed=65)
+    with capi.Engine(n, max_streams=1, max_listeners=4, max_blocks_per_batch=warm + len(bits) + tail) as eng:
+        sid = eng.open_stream(fs)
+        res = eng.collect(eng.submit([dict(stream=sid, iq=iq, listener_bins=[kbin])], capi.NO_PEAKS))
+    keys = res.keys[warm:warm + len(bits), 0]
+    assert np.array_equal(keys, bits)
+    dec = host.Decoder(fs, n)
+    dec.feed(keys)
+    dec.stop()
+    assert dec.text == expected
+
+
+@pytest.mark.parametrize("n,edge", [(512, 211), (512, 220), (512, 251), (512, 256), (512, 300), (2048, 1000), (8192, 4070)])
+def test_narrow_noise_windows_take_the_exact_replay(capi, oracle, n, edge):
+    """dsp.FindNoiseFloor (dsp/fft.go:215-252) with (N-2e)/10 < 9: the reference closes a window every `windowSize`
+    bins (up to 19 of them), or none at all when windowSize <= 0; the engine replays the loop literally"""
+    spec = synth.StreamSpec(sample_rate=48000, block_size=n, n_blocks=12, seed=n + edge,
+                            tones=synth.make_tones(np.random.default_rng(edge), 3, n, 70))
+    iq = synth.generate(spec)
+    with capi.Engine(n, max_streams=1, max_listeners=4, max_blocks_per_batch=16) as eng:
+        sid = eng.open_stream(48000)
+        res = eng.collect(eng.submit([dict(stream=sid, iq=iq, edge_width=edge, listener_bins=[n // 2])], capi.WANT_SPECTRUM))
+        psd = res.psd
+        for b in range(3):  # the single call takes the same route
+            mn, var = eng.find_noise_floor(psd[b], edge)
+            L = oracle.lib()
+            omn, ovar = C.c_float(), C.c_double()
+            L.orc_find_noise_floor(np.ascontiguousarray(psd[b]).ctypes.data_as(C.POINTER(C.c_float)), n, edge, C.byref(omn), C.byref(ovar))
+            # identical PSD in, identical arithmetic: bit-exact (NaN/Inf compare as equal bit patterns)
+            assert np.float32(mn).tobytes() == np.float32(omn.value).tobytes()
+            assert np.float64(var).tobytes() == np.float64(ovar.value).tobytes()
+            assert np.float32(res.psd_noise_floor[b]).tobytes() == np.float32(omn.value).tobytes()
+            assert np.float64(res.noise_variance[b]).tobytes() == np.float64(ovar.value).tobytes()
+    with capi.Engine(n, max_streams=1) as eng:
+        sid = eng.open_stream(48000)
+        with pytest.raises(capi.SdrError):
+            eng.submit([dict(stream=sid, iq=iq, edge_width=-1)])
+
+
+def test_reset_of_one_stream_leaves_the_others_partial_window_alone(capi):
+    """opening / resetting stream B must not touch stream A's saved partial cumulation"""
+    n = 1024
+    spec = synth.StreamSpec(sample_rate=96000, block_size=n, n_blocks=100, seed=5,
+                            tones=synth.make_tones(np.random.default_rng(5), 4, n, 70))
+    iq = synth.generate(spec)
+    bins = [t.bin for t in spec.tones]
+    half = 50 * 2 * n
+    with capi.Engine(n, max_streams=4, max_listeners=8, max_blocks_per_batch=200, max_peaks_per_flush=n // 2 + 1) as eng:
+        a = eng.open_stream(96000)
+        whole = eng.collect(eng.submit([dict(stream=a, iq=iq, listener_bins=bins)], capi.WANT_FLUSH_CUM))
+        eng.reset_stream(a)
+        eng.collect(eng.submit([dict(stream=a, iq=iq[:half], listener_bins=bins)]))
+        b = eng.open_stream(96000)           # r1 bug: wiped row `b` = A's second state row
+        c = eng.open_stream(96000)
+        eng.collect(eng.submit([dict(stream=b, iq=iq[:half // 2], listener_bins=bins)]))
+        eng.reset_stream(b)
+        eng.reset_stream(c)
+        rest = eng.collect(eng.submit([dict(stream=a, iq=iq[half:], listener_bins=bins)], capi.WANT_FLUSH_CUM))
+        assert rest.n_flushes == 1
+        assert np.array_equal(rest.flush_cum[0], whole.flush_cum[0])
+        assert pu.peak_keys(rest.peaks(0)) == pu.peak_keys(whole.peaks(0))
+
+
+def test_receiver_stop_start_in_the_middle_of_a_window(capi, host):
+    """Stop/Start after 30 blocks -- run() restarts with cumulationCount = 0 on both sides of the boundary"""
+    n, fs = 512, 48000
+    spec = synth.config(1, seconds=3.0)
+    iq = synth.generate(spec)
+    with capi.Engine(n, max_streams=2, max_listeners=32, max_blocks_per_batch=100, max_peaks_per_flush=n // 2 + 1) as eng:
+        rx = host.Receiver(eng, strain=True)
+        rx.start(fs, n)
+        for b in range(30):
+            assert rx.iq_data(fs, iq[b * 2 * n:(b + 1) * 2 * n])
+        assert rx.process() == 30
+        rx.stop()
+        rx.start(fs, n)
+        done = 0
+        for b in range(30, 250):
+            assert rx.iq_data(fs, iq[b * 2 * n:(b + 1) * 2 * n])
+            if b % 10 == 9:
+                done += rx.process()
+        done += rx.process()
+        assert done == 220
+        assert rx.n_flushes() == 2  # 100 and 200 blocks after the restart
+        rx.close()
+
+
+def test_dispatcher_64_receivers_one_engine_match_64_oracle_receivers(capi, oracle, host):
+    """SURVEY 8(f1) / rx/receiver.go:315-364: 64 rx.Receiver mirrors share one engine; the dispatcher drains their
+    queues into ONE sdr_submit per tick.  Every receiver must reproduce its own oracle Receiver.run exactly (attach
+    blocks, key streams, text)."""
+    from test_gpu_receiver import _oracle_receiver
+    n, fs, n_rx = 512, 48000, 64
+    specs = [synth.config(1, seconds=5.0, stream=900 + i) for i in range(4)]
+    iqs = [synth.generate(sp) for sp in specs]
+    refs = [_oracle_receiver(oracle, sp, iq)[0] for sp, iq in zip(specs, iqs)]
+    nb = specs[0].n_blocks
+    with capi.Engine(n, max_streams=n_rx, max_listeners=32, max_blocks_per_batch=n_rx * 100, max_peaks_per_flush=n // 2 + 1) as eng:
+        disp = host.Dispatcher(eng, n, n_rx)
+        rxs = []
+        for i in range(n_rx):
+            rx = host.Receiver(eng, strain=True, pool_size=30)
+            rx.start(fs, n)
+            disp.add(rx)
+            rxs.append(rx)
+        total = 0
+        for b in range(nb):
+            for i, rx in enumerate(rxs):
+                assert rx.iq_data(fs, iqs[i % 4][b * 2 * n:(b + 1) * 2 * n])
+            if b % 8 == 7:  # ~85 ms of signal per tick
+                total += disp.tick()
+        total += disp.tick()
+        assert total == n_rx * nb
+        # one submit per tick (plus one when a tick crosses a flush boundary), not one per receiver
+        assert disp.submits <= (nb // 8 + 1) + nb // 100 + 2
+        for i, rx in enumerate(rxs):
+            got, ref = rx.listeners(), refs[i % 4]
+            assert len(got) == len(ref) >= 2
+            for g, r in zip(got, ref):
+                assert g["attach_block"] == r["attach_block"]
+                assert np.array_equal(g["keys"], r["keys"])
+                assert g["text"] == r["text"]
+        disp.close()
+        for rx in rxs:
+            rx.close()
+
+
+def test_concurrent_submitters_on_one_engine(capi):
+    """safe for concurrent calls on different streams (one goroutine per receiver in the reference)"""
+    import threading
+    n, n_thr = 1024, 8
+    spec = synth.StreamSpec(sample_rate=96000, block_size=n, n_blocks=40, seed=77,
+                            tones=synth.make_tones(np.random.default_rng(77), 4, n, 70))
+    iq = synth.generate(spec)
+    bins = [t.bin for t in spec.tones]
+    with capi.Engine(n, max_streams=n_thr, max_listeners=8, max_blocks_per_batch=64, n_slots=n_thr) as eng:
+        sids = [eng.open_stream(96000) for _ in range(n_thr)]
+        ref = eng.collect(eng.submit([dict(stream=sids[0], iq=iq, listener_bins=bins)]))
+        eng.reset_stream(sids[0])
+        outs, errs = [None] * n_thr, []
+
+        def work(i):
+            try:
+                for rep in range(5):
+                    while True:
+                        try:
+                            t = eng.submit([dict(stream=sids[i], iq=iq, listener_bins=bins)])
+                            break
+                        except capi.SdrError as ex:
+                            if ex.code != capi.EBUSY:
+                                raise
+                    r = eng.collect(t)
+                    if rep == 0:
+                        outs[i] = r
+            except Exception as ex:  # noqa: BLE001
+                errs.append(ex)
+
+        ths = [threading.Thread(target=work, args=(i,)) for i in range(n_thr)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        assert not errs, errs
+        for o in outs:
+            assert np.array_equal(o.keys, ref.keys) and np.array_equal(o.thresholds, ref.thresholds)
