@@ -9,7 +9,9 @@
 // Three CUDA streams (H2D, compute, D2H) with events give copy/compute overlap across in-flight
 // slots; kernels of successive batches stay ordered on the compute stream, which is what keeps
 // the per-stream state sequential.
+#include <cuda.h>
 #include <cuda_runtime.h>
+#include <cudaTypedefs.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -25,8 +27,9 @@
 #include "k2_post.cuh"
 #include "k1_large.cuh"
 #include "k1_mid.cuh"
+#include "k1_mid8k.cuh"
 #include "k1_warp.cuh"
-#include "k1_cluster.cuh"
+#include "k1_wide.cuh"
 
 using namespace sdr;
 
@@ -65,6 +68,10 @@ struct Slot {
     double2 *d_nf_part = nullptr;                   //   per-CTA noise-window sums
     float *d_xto = nullptr;
     int *d_nf_edge = nullptr;
+    // k1_wide: intermediate ring, per-step ready counters, the ring's tensor map, error flag
+    float2 *d_wide_tmp = nullptr;
+    int *d_wide_ready = nullptr, *d_wide_err = nullptr, *h_wide_err = nullptr;
+    CUtensorMap *d_wide_map = nullptr;
     // pinned host mirrors
     float *h_psd_floor = nullptr;
     double *h_variance = nullptr;
@@ -112,10 +119,12 @@ struct sdr_engine {
     float2 *d_tw_sub1 = nullptr, *d_tw_sub2 = nullptr, *d_tw_n = nullptr;
     float2 *d_tw_step = nullptr;  // [k1][c] = W_N^(c k1): step-1 twiddles of the register-resident kernels
     int round_blocks = 0;         // register-resident large path: blocks per L2-resident round (SDR_LARGE_ROUND_MB)
-    // N = 65536: 16-CTA cluster kernel (k1_cluster.cuh), opt-in with SDR_K1_CLUSTER=1 (measured slower than the
-    // two-kernel path: DESIGN.md)
-    bool k1_cluster = false;
-    int k1c_max_clusters = 0;
+    // N = 65536: single-pass persistent kernel (k1_wide.cuh): teams of 16 CTAs, the four-step intermediate in an
+    // L2-resident ring.  SDR_K1_WIDE=0 disables it (two-kernel path), =force takes it for every launch
+    int k1_wide = 0;          // 0 off, 1 when the launch has enough segments, 2 always
+    int k1w_max_teams = 0;    // co-resident CTAs / 16
+    int k1w_lookahead = 3, k1w_ring = 6;
+    PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
     // N = 512: warp-per-block kernel (k1_warp.cuh), SDR_K1_WARP=0 selects the three-pass kernel
     float2 *d_tw512 = nullptr, *d_tw256w = nullptr;
     bool k1_warp = false;
@@ -124,6 +133,10 @@ struct sdr_engine {
     float2 *d_tw_mid = nullptr, *d_tw256m = nullptr;
     bool k1_mid = false;
     int k1m_grid_cap = 0;
+    // N = 8192: TMA-staged 512-thread kernel (k1_mid8k.cuh), one CTA per SM.  SDR_K1_MID8K=0 disables it (the launch then
+    // falls back to k1_mid_kernel<32> / the two-kernel path), =force takes it for every launch, whatever the segment count
+    int k1_mid8k = 0;  // 0 off, 1 when the launch has enough segments, 2 always
+    int k1m8_stages = 2;
     float *d_window = nullptr;
     float *d_cum_state = nullptr;
     RollingState *d_rolling = nullptr;
@@ -169,7 +182,7 @@ struct ExactNf {
 
 // descriptor block layout (same on host and device)
 struct DescLayout {
-    size_t segs, works, post, lbins, block_seg, exact, total;
+    size_t segs, works, post, lbins, block_seg, exact, segmaps, total;
 };
 DescLayout desc_layout(const sdr_engine *e) {
     DescLayout l;
@@ -186,6 +199,8 @@ DescLayout desc_layout(const sdr_engine *e) {
     if (e->large) off = align_up(off + sizeof(int) * (size_t)e->cfg.max_blocks_per_batch, 256);
     l.exact = off;
     off = align_up(off + sizeof(ExactNf) * (size_t)e->cfg.max_streams, 256);
+    l.segmaps = off;
+    if (e->k1_wide) off = align_up(off + sizeof(CUtensorMap) * (size_t)e->max_segs, 256);
     l.total = off;
     return l;
 }
@@ -335,36 +350,50 @@ cudaError_t launch_large_fast(const sdr_engine *e, const K1Args &a, const LargeF
     return cudaGetLastError();
 }
 
-// N = 65536 in one pass: clusters of 16 CTAs walk the segments (k1_cluster.cuh), then the noise-floor finish
-cudaError_t launch_k1_cluster(const sdr_engine *e, const K1Args &a, const LargeFastBufs &lb, int n_blocks, bool dbg, cudaStream_t st) {
-    ClusterArgs ca{};
-    ca.a = a;
-    if (!dbg) ca.a.dbg_psd = ca.a.dbg_spectrum = nullptr;
-    ca.tw256 = e->d_tw_sub2;
-    ca.tw_step = e->d_tw_step;
-    ca.nf_part = lb.nf_part;
-    ca.xto = lb.xto;
-    ca.nf_edge = lb.nf_edge;
-    ca.db_offset = (float)(10.0 * log10(20.0 / (65536.0 * 65536.0)));
-    int ncl = a.n_segs;
-    if (ncl > e->k1c_max_clusters) {
-        const int rounds = (ncl + e->k1c_max_clusters - 1) / e->k1c_max_clusters;
-        ncl = (a.n_segs + rounds - 1) / rounds;
-    }
-    if (ncl < 1) ncl = 1;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(K1C_CLUSTER * ncl);
-    cfg.blockDim = dim3(256);
-    cfg.dynamicSmemBytes = K1C_SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = K1C_CLUSTER;
-    attr.val.clusterDim.y = 1;
-    attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
-    cudaError_t rc = cudaLaunchKernelEx(&cfg, k1_cluster_kernel, ca);
+// tensor map over [n_outer][256 rows][256 complex] float32 pairs with a {16 complex, 256 rows, 1} box and the 128-byte
+// swizzle k1_wide.cuh assumes
+bool encode_tile_map(const sdr_engine *e, CUtensorMap *m, const void *base, int n_outer) {
+    const cuuint64_t dims[3] = {512, 256, (cuuint64_t)n_outer};
+    const cuuint64_t strides[2] = {2048, 524288};
+    const cuuint32_t box[3] = {32, 256, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return e->encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// N = 65536 in one pass: teams of 16 CTAs walk the segments (k1_wide.cuh), then the noise-floor finish
+struct WideBufs {
+    const CUtensorMap *seg_maps, *tmp_map;
+    float2 *tmp;
+    int *ready, *err, *h_err;
+};
+cudaError_t launch_k1_wide(const sdr_engine *e, const K1Args &a, const LargeFastBufs &lb, const WideBufs &wb, int n_blocks, bool dbg,
+                           cudaStream_t st) {
+    WideArgs wa{};
+    wa.a = a;
+    if (!dbg) wa.a.dbg_psd = wa.a.dbg_spectrum = nullptr;
+    wa.seg_maps = wb.seg_maps;
+    wa.tmp_map = wb.tmp_map;
+    wa.tmp = wb.tmp;
+    wa.ready = wb.ready;
+    wa.err = wb.err;
+    wa.tw256 = e->d_tw_sub2;
+    wa.tw_step = e->d_tw_step;
+    wa.nf_part = lb.nf_part;
+    wa.xto = lb.xto;
+    wa.nf_edge = lb.nf_edge;
+    wa.db_offset = (float)(10.0 * log10(20.0 / (65536.0 * 65536.0)));
+    wa.lookahead = e->k1w_lookahead;
+    wa.ring = e->k1w_ring;
+    const int n_teams = a.n_segs < e->k1w_max_teams ? a.n_segs : e->k1w_max_teams;
+    cudaError_t rc = cudaMemsetAsync(wb.ready, 0, (size_t)n_blocks * sizeof(int), st);
+    if (rc != cudaSuccess) return rc;
+    void *params[] = {&wa};
+    // cooperative: every CTA of the launch is resident at the same time (the teams wait on one another's tiles)
+    rc = cudaLaunchCooperativeKernel((const void *)k1_wide_kernel, dim3(K1W_TEAM * n_teams), dim3(256), params, K1W_SMEM_BYTES, st);
+    if (rc != cudaSuccess) return rc;
+    rc = cudaMemcpyAsync(wb.h_err, wb.err, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (rc != cudaSuccess) return rc;
     LargeFinishArgs fin{};
     fin.nf_part = lb.nf_part;
@@ -373,7 +402,7 @@ cudaError_t launch_k1_cluster(const sdr_engine *e, const K1Args &a, const LargeF
     fin.psd_floor = a.psd_floor;
     fin.variance = a.variance;
     fin.n_blocks = n_blocks;
-    fin.n_cta = K1C_CLUSTER;
+    fin.n_cta = K1W_TEAM;
     fin.n = 65536;
     large_nf_finish_kernel<<<(n_blocks + 3) / 4, 128, 0, st>>>(fin);
     return cudaGetLastError();
@@ -473,6 +502,28 @@ int k1m_grid_cap_for(int n, bool win, int sm_count) {
     }
     if (occ < 1) occ = 1;
     return occ * sm_count;
+}
+
+template <int NSTAGE>
+const void *k1m8_fn(bool dbg, bool win) {
+    if (dbg) return win ? (const void *)k1_mid8k_kernel<NSTAGE, true, true> : (const void *)k1_mid8k_kernel<NSTAGE, true, false>;
+    return win ? (const void *)k1_mid8k_kernel<NSTAGE, false, true> : (const void *)k1_mid8k_kernel<NSTAGE, false, false>;
+}
+const void *k1m8_fn(int stages, bool dbg, bool win) { return stages == 1 ? k1m8_fn<1>(dbg, win) : k1m8_fn<2>(dbg, win); }
+int k1m8_smem(int stages) { return stages == 1 ? K1Mid8kGeom<1>::SMEM_BYTES : K1Mid8kGeom<2>::SMEM_BYTES; }
+
+cudaError_t launch_k1_mid8k(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st) {
+    // one CTA per SM walks the segment list with stride grid: whole rounds, no straggler
+    int grid = a.n_segs;
+    if (grid > e->sm_count) {
+        const int rounds = (grid + e->sm_count - 1) / e->sm_count;
+        grid = (a.n_segs + rounds - 1) / rounds;
+    }
+    if (grid < 1) grid = 1;
+    K1Args args = a;
+    const float2 *tws = e->d_tw_mid, *tw256 = e->d_tw256m;
+    void *params[] = {&args, &tws, &tw256};
+    return cudaLaunchKernel(k1m8_fn(e->k1m8_stages, dbg, a.window != nullptr), dim3(grid), dim3(512), params, k1m8_smem(e->k1m8_stages), st);
 }
 
 cudaError_t launch_k1_mid(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st) {
@@ -604,6 +655,11 @@ void free_slot(Slot &s) {
     cudaFree(s.d_nf_part);
     cudaFree(s.d_xto);
     cudaFree(s.d_nf_edge);
+    cudaFree(s.d_wide_tmp);
+    cudaFree(s.d_wide_ready);
+    cudaFree(s.d_wide_err);
+    cudaFree(s.d_wide_map);
+    cudaFreeHost(s.h_wide_err);
     cudaFree(s.d_psd);
     cudaFree(s.d_iq);
     cudaFree(s.d_tmp);
@@ -661,6 +717,22 @@ int alloc_slot(sdr_engine *e, Slot &s) {
         CK(e, cudaMalloc((void **)&s.d_nf_part, MB * (size_t)(e->lg.n1 / 16) * 10 * sizeof(double2)));
         CK(e, cudaMalloc((void **)&s.d_xto, MB * 10 * sizeof(float)));
         CK(e, cudaMalloc((void **)&s.d_nf_edge, MB * sizeof(int)));
+        if (e->k1_wide) {
+            const int n_slots = e->k1w_max_teams * e->k1w_ring;
+            CK(e, cudaMalloc((void **)&s.d_wide_tmp, (size_t)n_slots * N * sizeof(float2)));
+            CK(e, cudaMalloc((void **)&s.d_wide_ready, MB * sizeof(int)));
+            CK(e, cudaMalloc((void **)&s.d_wide_err, sizeof(int)));
+            CK(e, cudaMemset(s.d_wide_err, 0, sizeof(int)));
+            CK(e, cudaMalloc((void **)&s.d_wide_map, sizeof(CUtensorMap)));
+            CK(e, cudaMallocHost((void **)&s.h_wide_err, sizeof(int)));
+            *s.h_wide_err = 0;
+            CUtensorMap m;
+            if (!encode_tile_map(e, &m, s.d_wide_tmp, n_slots)) {
+                e->err = "cuTensorMapEncodeTiled failed for the intermediate ring";
+                return SDR_ECUDA;
+            }
+            CK(e, cudaMemcpy(s.d_wide_map, &m, sizeof(m), cudaMemcpyHostToDevice));
+        }
     } else if (e->large) {  // Stockham path: materialises spectrum / psd / the four-step intermediate of the batch
         CK(e, cudaMalloc((void **)&s.d_tmp, MB * N * sizeof(float2)));
         CK(e, cudaMalloc((void **)&s.d_spectrum, MB * N * sizeof(float)));
@@ -882,27 +954,27 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
                 e->round_blocks = cfg->max_blocks_per_batch > 16 ? cfg->max_blocks_per_batch : 16;
             }
             if (e->N == 65536) {
-                const char *cv = getenv("SDR_K1_CLUSTER");
-                if (cv && cv[0] == '1' && cudaFuncSetAttribute(k1_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K1C_SMEM_BYTES) == cudaSuccess &&
-                    cudaFuncSetAttribute(k1_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
-                    cudaLaunchConfig_t lc = {};
-                    lc.gridDim = dim3(K1C_CLUSTER);
-                    lc.blockDim = dim3(256);
-                    lc.dynamicSmemBytes = K1C_SMEM_BYTES;
-                    cudaLaunchAttribute at;
-                    at.id = cudaLaunchAttributeClusterDimension;
-                    at.val.clusterDim.x = K1C_CLUSTER;
-                    at.val.clusterDim.y = 1;
-                    at.val.clusterDim.z = 1;
-                    lc.attrs = &at;
-                    lc.numAttrs = 1;
-                    int ncl = 0;
-                    if (cudaOccupancyMaxActiveClusters(&ncl, k1_cluster_kernel, &lc) == cudaSuccess && ncl > 0) {
-                        e->k1_cluster = true;
-                        e->k1c_max_clusters = ncl;
-                    }
+                const char *wv = getenv("SDR_K1_WIDE");
+                e->k1_wide = (wv && wv[0] == '0') ? 0 : (wv && wv[0] == 'f') ? 2 : 1;
+                const char *dv = getenv("SDR_K1_WIDE_LOOKAHEAD");
+                if (dv && atoi(dv) >= 2 && atoi(dv) <= 8) e->k1w_lookahead = atoi(dv);
+                e->k1w_ring = 2 * e->k1w_lookahead;
+                int occ = 0, coop = 0;
+                cudaDriverEntryPointQueryResult qres;
+                void *fn = nullptr;
+                if (e->k1_wide &&
+                    (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device) != cudaSuccess || !coop ||
+                     cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+                     qres != cudaDriverEntryPointSuccess ||
+                     cudaFuncSetAttribute(k1_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K1W_SMEM_BYTES) != cudaSuccess ||
+                     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_wide_kernel, 256, K1W_SMEM_BYTES) != cudaSuccess || occ < 1))
+                    e->k1_wide = 0;
+                cudaGetLastError();
+                if (e->k1_wide) {
+                    e->encode_tiled = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+                    e->k1w_max_teams = occ * e->sm_count / K1W_TEAM;
+                    if (e->k1w_max_teams < 1) e->k1_wide = 0;
                 }
-                cudaGetLastError();  // a device without 16-CTA clusters simply keeps the two-kernel path
             }
         }
     }
@@ -948,6 +1020,17 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
         const char *v = getenv("SDR_K1_MID");
         e->k1_mid = !(v && v[0] == '0');
         if (e->k1_mid) e->k1m_grid_cap = k1m_grid_cap_for(e->N, e->d_window != nullptr, e->sm_count);
+        if (e->N == 8192) {
+            const char *v8 = getenv("SDR_K1_MID8K");
+            e->k1_mid8k = (v8 && v8[0] == '0') ? 0 : (v8 && v8[0] == 'f') ? 2 : 1;
+            const char *st = getenv("SDR_K1_MID8K_STAGES");
+            e->k1m8_stages = (st && st[0] == '1') ? 1 : 2;
+            for (int dbgv = 0; dbgv < 2 && e->k1_mid8k; dbgv++)
+                if (cudaFuncSetAttribute(k1m8_fn(e->k1m8_stages, dbgv != 0, e->d_window != nullptr), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         k1m8_smem(e->k1m8_stages)) != cudaSuccess)
+                    e->k1_mid8k = 0;
+            cudaGetLastError();
+        }
     }
     CKC(cudaMalloc((void **)&e->d_rolling, (size_t)cfg->max_streams * sizeof(RollingState)));
     CKC(cudaMemset(e->d_rolling, 0, (size_t)cfg->max_streams * sizeof(RollingState)));
@@ -1273,6 +1356,17 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     s.flags = flags;
     s.launches = 0;
 
+    // N = 65536 with enough segments for whole teams: the single-pass kernel; its per-segment tensor maps travel with
+    // the descriptors.  Below 4 segments the block-parallel two-kernel path fills the GPU better.
+    const bool use_wide = e->N == 65536 && (e->k1_wide == 2 || (e->k1_wide == 1 && n_segs >= 4));
+    if (use_wide) {
+        CUtensorMap *maps = reinterpret_cast<CUtensorMap *>(s.h_desc + dl.segmaps);
+        for (int i = 0; i < n_segs; i++)
+            if (!encode_tile_map(e, &maps[i], segs[i].iq, segs[i].n_blocks)) {
+                e->err = "cuTensorMapEncodeTiled failed for an IQ segment";
+                return SDR_ECUDA;
+            }
+    }
     if (pend_n > 0) CK(e, cudaMemcpyAsync(pend_dst, pend_src, pend_n * sizeof(float), cudaMemcpyHostToDevice, e->s_h2d));
     // ---- H2D: descriptors (+ IQ queued above) ----
     CK(e, cudaMemcpyAsync(s.d_desc, s.h_desc, dl.total, cudaMemcpyHostToDevice, e->s_desc));
@@ -1302,13 +1396,19 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     int k1_launches = 1;
     if (!e->large) {
         CK(e, launch_k1(e, a1, dbg, e->s_compute, i16, warp_ok));
+    } else if (e->N == 8192 && block_off <= e->round_blocks && (e->k1_mid8k == 2 || (e->k1_mid8k == 1 && n_segs >= e->sm_count / 3))) {
+        // TMA-staged single pass, one 512-thread CTA per SM (k1_mid8k.cuh).  Below ~SMs/3 segments the block-parallel
+        // two-kernel path (which does not serialise the blocks of a stream) is faster.
+        CK(e, launch_k1_mid8k(e, a1, dbg, e->s_compute));
     } else if (e->k1_mid && e->N == 8192 && block_off <= e->round_blocks && n_segs >= 2 * e->sm_count) {
         // enough segments to fill the GPU with segment-sequential CTAs: fused single pass (k1_mid.cuh)
         CK(e, launch_k1_mid(e, a1, dbg, e->s_compute));
-    } else if (e->k1_cluster && block_off <= e->round_blocks && n_segs >= 8) {
-        // one cluster of 16 CTAs per segment, the whole 512 KB block in distributed shared memory (k1_cluster.cuh)
+    } else if (use_wide) {
+        // single pass over HBM: one team of 16 CTAs per segment, the intermediate in an L2-resident ring (k1_wide.cuh)
         const LargeFastBufs lb{s.d_tmp, s.d_spec_round, s.d_nf_part, s.d_xto, s.d_nf_edge};
-        CK(e, launch_k1_cluster(e, a1, lb, block_off, dbg, e->s_compute));
+        const WideBufs wb{reinterpret_cast<const CUtensorMap *>(s.d_desc + dl.segmaps), s.d_wide_map, s.d_wide_tmp, s.d_wide_ready,
+                          s.d_wide_err, s.h_wide_err};
+        CK(e, launch_k1_wide(e, a1, lb, wb, block_off, dbg, e->s_compute));
         k1_launches = 2;
     } else if (e->round_blocks > 0) {
         // rounds of consecutive blocks; the segment table is in block order and no segment straddles a round
@@ -1417,6 +1517,10 @@ int sdr_collect(sdr_engine *e, sdr_ticket t, int blocking, sdr_result *out) {
         cudaError_t st = cudaEventQuery(s.ev_done);
         if (st == cudaErrorNotReady) return SDR_ENOTREADY;
         CK(e, st);
+    }
+    if (s.h_wide_err && *s.h_wide_err) {
+        e->err = "k1_wide: a dependency wait ran out (the batch's results are invalid)";
+        return SDR_ECUDA;
     }
     s.collected = true;
     memset(out, 0, sizeof(*out));

@@ -1,0 +1,336 @@
+// k1_wide.cuh -- N = 65536 (BASELINE config 5: 24.576 MS/s wideband peak scan) in ONE pass over HBM.
+//
+// Same reference arithmetic as the rest of K1: dsp/fft.go:23-85 (FFT, fftshift, |X|^2, dB + 120), dsp/fft.go:215-252
+// (FindNoiseFloor), rx/receiver.go:393 (listener taps), rx/receiver.go:404-407 (cumulation, float32, block order).
+//
+// A 512 KB block fits neither a CTA nor (usefully) a cluster, so the 256 x 256 four-step transform keeps its
+// intermediate -- but in a small ring that never leaves the 126 MB L2, inside ONE persistent launch:
+//   * a TEAM of 16 CTAs owns a segment (<= 100 consecutive blocks of one stream) and walks its blocks in order;
+//   * per step every CTA of the team does two things.  CONSUME step i: its row tile (16 rows x 256 of the intermediate,
+//     32 KB contiguous, one cp.async.bulk) -> half-warp 256-point transforms -> |X|^2, dB, cumulation in registers
+//     (16 bins per thread for the whole segment), this CTA's share of the ten noise-window sums, x_to, its taps.
+//     PRODUCE step i + D: its column tile of the IQ block (16 columns x 256 rows: ONE tensor-map TMA load,
+//     cp.async.bulk.tensor.3d -> SASS UTMALDG, 128-byte swizzle) -> half-warp 256-point transforms -> twiddle W_N^(c k)
+//     -> swizzled tile in shared memory -> ONE tensor-map TMA store (UTMASTG) into ring slot (i + D) mod R;
+//   * a global counter per step (`ready`) is released by each producer after its store has completed and acquired by
+//     thread 0 of each consumer before it issues the row-tile load: the only inter-CTA synchronisation.  All CTAs of
+//     the launch are co-resident (cooperative launch), every wait is on work that only depends on earlier steps, so
+//     the schedule cannot deadlock; waits are bounded all the same and report through `err`.
+// HBM sees the IQ once (8 N per block), the ten partial window sums per CTA and block, and the cumulation once per 100
+// blocks; the intermediate (8 N written + 8 N read per block) is L2 traffic: R x 512 KB per team.
+// The two-kernel path of k1_large.cuh (32 N bytes of HBM traffic per block) remains for launches with too few segments
+// to fill the GPU with teams.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "k1_large.cuh"
+
+namespace sdr {
+
+constexpr int K1W_TEAM = 16;
+constexpr int K1W_TILE_BYTES = 32768;
+constexpr int K1W_MAX_SPIN = 1 << 24;  // polls of one wait before the launch gives up (seconds; a step takes microseconds)
+
+struct WideArgs {
+    K1Args a;
+    const CUtensorMap *seg_maps;  // [n_segs] IQ of each segment as {512 floats, 256 rows, n_blocks}, box {32, 256, 1}, 128B swizzle
+    const CUtensorMap *tmp_map;   // the ring as {512 floats, 256 rows, n_teams * R}, same box
+    float2 *tmp;                  // [n_teams * R][65536] intermediate Z[k][c] (row-major)
+    int *ready;                   // [blocks of the batch] producers that have published the step (16 = complete)
+    int *err;                     // set to 1 when a bounded wait ran out
+    const float2 *tw256;          // W_256^m
+    const float2 *tw_step;        // [k][c] = W_N^(c k) (symmetric: read as [c][k])
+    double2 *nf_part;             // [blocks][16][10]
+    float *xto;                   // [blocks][10]
+    int *nf_edge;                 // [blocks]
+    float db_offset;              // 10*log10(20/N^2)
+    int lookahead;                // D >= 2: steps between producing and consuming a block (a store is published one
+                                  // step after it was committed, so D = 1 would wait on itself)
+    int ring;                     // R >= 2 D slots per team
+};
+
+constexpr int K1W_OFF_A = 0;                                   // IQ column tile, later the outgoing tile (1024-byte aligned: 128B swizzle)
+constexpr int K1W_OFF_B = K1W_OFF_A + K1W_TILE_BYTES;          // row tile of the intermediate
+constexpr int K1W_OFF_S = K1W_OFF_B + K1W_TILE_BYTES;          // [16][HW_PITCH] transpose scratch, then the (psd, dB) tile
+constexpr int K1W_OFF_TW = K1W_OFF_S + 16 * HW_PITCH * 8;     // W_256^m
+constexpr int K1W_OFF_MISC = K1W_OFF_TW + 256 * 8;
+constexpr int K1W_SMEM_BYTES = K1W_OFF_MISC + 128;
+
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_tile_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_tile_3d(const CUtensorMap *map, int c0, int c1, int c2, const void *src) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(c0), "r"(c1),
+                 "r"(c2), "r"(smem_u32(src))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int *p, int v) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// a tensor map that lives in global memory and was written by the host (cudaMemcpy) is acquired through the tensormap
+// proxy before its first use (system scope: the writer is the host)
+__device__ __forceinline__ void tensormap_acquire(const CUtensorMap *m) {
+    asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(m) : "memory");
+}
+
+// the block sequence of one team: segments team, team + n_teams, ... in order, each segment's blocks in order
+struct WideIter {
+    int seg, blk, nb, step;
+    __device__ __forceinline__ void start(const Segment *segs, int n_segs, int team) {
+        seg = team;
+        blk = 0;
+        step = 0;
+        nb = seg < n_segs ? segs[seg].n_blocks : 0;
+    }
+    __device__ __forceinline__ void next(const Segment *segs, int n_segs, int n_teams) {
+        step++;
+        if (++blk == nb) {
+            seg += n_teams;
+            blk = 0;
+            nb = seg < n_segs ? segs[seg].n_blocks : 0;
+        }
+    }
+};
+
+__global__ void __launch_bounds__(256, 2) k1_wide_kernel(const WideArgs wa) {
+    constexpr int N = 65536, N1 = 256;
+    const K1Args &a = wa.a;
+    extern __shared__ __align__(1024) unsigned char wd_smem[];
+    unsigned char *A = wd_smem + K1W_OFF_A;
+    const float2 *B = reinterpret_cast<const float2 *>(wd_smem + K1W_OFF_B);
+    float2 *S = reinterpret_cast<float2 *>(wd_smem + K1W_OFF_S);
+    uint64_t *FULL_A = reinterpret_cast<uint64_t *>(wd_smem + K1W_OFF_MISC);
+    uint64_t *FULL_B = FULL_A + 1;
+    int *cnt = reinterpret_cast<int *>(FULL_A + 2);  // [11]
+
+    const int team = blockIdx.x / K1W_TEAM, rank = blockIdx.x % K1W_TEAM, n_teams = gridDim.x / K1W_TEAM;
+    const int tid = threadIdx.x, hl = tid & 15, f = tid >> 4, lane = tid & 31, warp = tid >> 5;
+    const int c0 = 16 * rank, r0 = 16 * rank;  // my columns when producing, my rows when consuming
+    const int D = wa.lookahead, R = wa.ring;
+    // byte offset of element (row hl + 16 j, column f) in a 128B-swizzled [256][16] tile, minus j * 2048
+    const int swz_off = hl * 128 + ((((f >> 1) ^ (hl & 7))) << 4) + ((f & 1) << 3);
+
+    float2 *TW = reinterpret_cast<float2 *>(wd_smem + K1W_OFF_TW);
+    TW[tid] = __ldg(&wa.tw256[tid]);
+    // the fifteen W256^(hl k) of the half-warp transform are re-read from shared memory per transform: with the step
+    // twiddles and the cumulation resident there is no room to keep them in registers at 2 CTAs per SM
+    auto load_hw_twiddle = [&](HwTwiddle &t) {
+#pragma unroll
+        for (int k = 1; k < 16; k++) t.w[k - 1] = TW[(hl * k) & 255];
+    };
+    // step twiddles of my column c0 + f for the sixteen outputs k = hl + 16*OutIdx<16>(p): fixed for the whole launch
+    float2 twc[16];
+#pragma unroll
+    for (int p = 0; p < 16; p++) twc[p] = __ldg(&wa.tw_step[(size_t)(c0 + f) * 256 + hl + 16 * OutIdx<16>::of(p)]);
+
+    if (tid == 0) {
+        mbar_init(FULL_A, 1);
+        mbar_init(FULL_B, 1);
+        fence_mbar_init();
+        tensormap_acquire(wa.tmp_map);
+    }
+    __syncthreads();
+
+    WideIter ic, ip, ia, ib;  // consume, produce, and (thread 0) the two load iterators one step ahead of them
+    ic.start(a.segs, a.n_segs, team);
+    ip = ia = ib = ic;
+    uint32_t phase_a = 0, phase_b = 0;
+    int pend_ob = -1;  // thread 0: step whose tile store is committed but not yet published
+    const uint64_t policy = l2_evict_first_policy();
+
+    auto publish_pending = [&]() {  // thread 0
+        if (pend_ob >= 0) {
+            bulk_wait_all();  // the tile store has completed: its writes are performed
+            red_release_gpu_add(&wa.ready[pend_ob], 1);
+            pend_ob = -1;
+        }
+    };
+    auto issue_a = [&]() {  // thread 0: IQ column tile of the next step to produce
+        if (ia.nb == 0) return;
+        if (ia.blk == 0) tensormap_acquire(&wa.seg_maps[ia.seg]);  // first use of this segment's map
+        mbar_expect_tx(FULL_A, K1W_TILE_BYTES);
+        tma_load_tile_3d(A, &wa.seg_maps[ia.seg], 2 * c0, 0, ia.blk, FULL_A, policy);
+        ia.next(a.segs, a.n_segs, n_teams);
+    };
+    auto issue_b = [&]() {  // thread 0: row tile of the next step to consume, once all sixteen column tiles are published
+        if (ib.nb == 0) return;
+        const int ob = a.segs[ib.seg].block_out + ib.blk;
+        int spins = 0;
+        while (ld_acquire_gpu(&wa.ready[ob]) < K1W_TEAM) {
+            ++spins;
+            if (spins > K1W_MAX_SPIN || ((spins & 1023) == 0 && ld_acquire_gpu(wa.err) != 0)) {  // give up; once one wait failed, all do
+                atomicExch(wa.err, 1);
+                break;
+            }
+            __nanosleep(64);
+        }
+        fence_proxy_async_all();  // the acquire above orders the async-proxy read below after the producers' stores
+        mbar_expect_tx(FULL_B, K1W_TILE_BYTES);
+        tma_load_1d(wd_smem + K1W_OFF_B, wa.tmp + ((size_t)(team * R + ib.step % R) * N + (size_t)r0 * 256), K1W_TILE_BYTES, FULL_B);
+        ib.next(a.segs, a.n_segs, n_teams);
+    };
+
+    // ---------------- produce: column tile of step ip -> ring ----------------
+    auto produce = [&]() {
+        mbar_wait(FULL_A, phase_a);
+        phase_a ^= 1u;
+        float2 v[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int n1 = (q & 3) * 4 + (q >> 2);
+            v[n1] = *reinterpret_cast<const float2 *>(A + swz_off + n1 * 2048);  // x[(16 n1 + hl) * 256 + c0 + f]
+        }
+        if (a.window) {
+#pragma unroll
+            for (int n1 = 0; n1 < 16; n1++) {
+                const float w = __ldg(&a.window[(16 * n1 + hl) * 256 + c0 + f]);
+                v[n1] = __fmul2_rn(v[n1], make_float2(w, w));
+            }
+        }
+        __syncthreads();  // the tile is in registers: A can take the outgoing tile; S is free (consume's tile reads are done)
+        HwTwiddle t;
+        load_hw_twiddle(t);
+        fft256_halfwarp_regs(v, S + f * HW_PITCH, t, hl);
+#pragma unroll
+        for (int p = 0; p < 16; p++)  // Z[k][c0 + f], k = hl + 16*OutIdx<16>(p), swizzled like the TMA box
+            *reinterpret_cast<float2 *>(A + swz_off + OutIdx<16>::of(p) * 2048) = cmul(v[p], twc[p]);
+        fence_proxy_async();  // generic-proxy writes of the tile before the async-proxy (TMA) read
+        __syncthreads();
+        if (tid == 0) {
+            tma_store_tile_3d(wa.tmp_map, 2 * c0, 0, team * R + ip.step % R, A);
+            bulk_commit();
+            pend_ob = a.segs[ip.seg].block_out + ip.blk;
+        }
+        ip.next(a.segs, a.n_segs, n_teams);
+    };
+
+    // prologue: the first D steps are produced before anything is consumed
+    if (tid == 0) issue_a();
+    for (int d = 0; d < D; d++) {
+        if (ip.nb == 0) break;
+        produce();
+        if (tid == 0) {
+            publish_pending();
+            if (d + 1 < D) issue_a();
+        }
+    }
+    if (tid == 0) issue_b();
+
+    float cum[16];
+    int e = 0, ws = 1, n_win = 9, L = 0;
+    const int *lbins = nullptr;
+
+    while (ic.nb != 0) {
+        const Segment sg = a.segs[ic.seg];
+        if (ic.blk == 0) {  // a new segment: window geometry, listeners, cumulation registers
+            const WorkParams wp = a.works[sg.work];
+            e = wp.edge_width;
+            ws = nf_window_size(N, e);
+            n_win = nf_window_count(N, e);
+            L = wp.n_listeners;
+            lbins = a.listener_bins + wp.listener_off;
+            if (tid < 11) cnt[tid] = tile_count_below(e + tid * ws, r0, N1, 256);  // read after the barriers below
+#pragma unroll
+            for (int p = 0; p < 16; p++) {
+                const int kk = (r0 + f) + N1 * ((hl + 16 * OutIdx<16>::of(p) + 128) & 255);
+                cum[p] = sg.state_in >= 0 ? a.cum_state[(size_t)sg.state_in * N + kk] : 0.f;
+            }
+        }
+        const int ob = sg.block_out + ic.blk;
+
+        // ---------------- consume: row tile of step ic ----------------
+        mbar_wait(FULL_B, phase_b);
+        phase_b ^= 1u;
+        float2 v[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int n1 = (q & 3) * 4 + (q >> 2);
+            v[n1] = B[f * 256 + 16 * n1 + hl];  // Z[r0 + f][16 n1 + hl]
+        }
+        __syncthreads();  // B is in registers
+        if (tid == 0) {
+            publish_pending();  // the store committed at the end of the previous produce has long completed
+            issue_a();          // A is free again: next column tile (consumed by this iteration's produce)
+            issue_b();          // next row tile
+        }
+        float2 *col = S + f * HW_PITCH;
+        {
+            HwTwiddle t;
+            load_hw_twiddle(t);
+            fft256_halfwarp_regs(v, col, t, hl);
+        }
+        __syncwarp();
+        // X[(r0 + f) + 256 k2], k2 = hl + 16*OutIdx<16>(p)
+#pragma unroll
+        for (int p = 0; p < 16; p++) {
+            const float psd = fmaf(v[p].x, v[p].x, v[p].y * v[p].y);                                      // dsp/fft.go:71-73
+            const float db = __fadd_rn(fmaf(3.01029995663981195f, fast_log2(psd), wa.db_offset), 120.0f);  // rx/receiver.go:376-378
+            cum[p] = __fadd_rn(cum[p], db);                                                                // rx/receiver.go:404-406
+            col[hl + 16 * OutIdx<16>::of(p)] = make_float2(psd, db);
+        }
+        __syncthreads();
+        if (a.dbg_psd) {  // parity / scope only: fftshifted stores (dsp/fft.go:54-57), half-warp = 16 consecutive bins
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int k2 = f + 16 * i;
+                const float2 o = S[hl * HW_PITCH + k2];
+                const int kk = ((r0 + hl) + N1 * k2 + N / 2) & (N - 1);
+                a.dbg_psd[(size_t)ob * N + kk] = o.x;
+                a.dbg_spectrum[(size_t)ob * N + kk] = o.y;
+            }
+        }
+        // noise-window sums over this CTA's bins in ascending bin order (float64 sums of float32 values)
+        for (int w = warp; w < 10; w += 8) {
+            double a1 = 0.0, a2 = 0.0;
+            for (int i = cnt[w] + lane; i < cnt[w + 1]; i += 32) {
+                const double x = (double)S[(i & 15) * HW_PITCH + (((i >> 4) + 128) & 255)].x;
+                a1 += x;
+                a2 = fma(x, x, a2);
+            }
+            a1 = warp_sum(a1);
+            a2 = warp_sum(a2);
+            if (lane == 0) wa.nf_part[((size_t)ob * K1W_TEAM + rank) * 10 + w] = make_double2(a1, a2);
+        }
+        if (tid < n_win) {  // x_to = psd[e + (w+1)*ws] (dsp/fft.go:238-243) if this CTA owns that bin
+            const int k = (e + (tid + 1) * ws - N / 2) & (N - 1);
+            const int k1 = k & (N1 - 1);
+            if (k1 >= r0 && k1 < r0 + 16) wa.xto[(size_t)ob * 10 + tid] = S[(k1 - r0) * HW_PITCH + k / N1].x;
+        }
+        if (rank == 0 && tid == 0) wa.nf_edge[ob] = e;
+        for (int l = tid; l < L; l += 256) {  // listener taps (rx/receiver.go:393) on bins this CTA owns
+            const int k = (__ldg(&lbins[l]) - N / 2) & (N - 1);
+            const int k1 = k & (N1 - 1);
+            if (k1 >= r0 && k1 < r0 + 16) a.taps[(size_t)ob * a.tap_stride + l] = S[(k1 - r0) * HW_PITCH + k / N1].y;
+        }
+        if (ic.blk == sg.n_blocks - 1) {  // end of the segment: flush or save the cumulation
+            float *dst = (sg.flush_idx >= 0) ? a.flush_cum + (size_t)sg.flush_idx * N : a.cum_state + (size_t)sg.state_out * N;
+#pragma unroll
+            for (int p = 0; p < 16; p++) dst[(r0 + f) + N1 * ((hl + 16 * OutIdx<16>::of(p) + 128) & 255)] = cum[p];
+        }
+        __syncthreads();  // the (psd, dB) tile and cnt are read: S may be overwritten, cnt rewritten
+        ic.next(a.segs, a.n_segs, n_teams);
+
+        if (ip.nb != 0) produce();
+    }
+    if (tid == 0) publish_pending();
+}
+
+}  // namespace sdr

@@ -269,7 +269,7 @@ def test_error_codes_never_crash(capi):
         s = eng.open_stream(48000)
         iq = np.zeros(2 * n * 4, np.float32)
         for bad in (dict(stream=s + 5, iq=iq), dict(stream=s, iq=iq, listener_bins=[n]),
-                    dict(stream=s, iq=iq, listener_bins=[1, 2, 3, 4, 5]), dict(stream=s, iq=iq, edge_width=252),
+                    dict(stream=s, iq=iq, listener_bins=[1, 2, 3, 4, 5]), dict(stream=s, iq=iq, edge_width=-1),
                     dict(stream=s, iq=np.zeros(2 * n * 11, np.float32))):
             with pytest.raises(capi.SdrError) as ei:
                 eng.submit([bad])

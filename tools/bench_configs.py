@@ -19,6 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from sdrainer_b200 import capi  # noqa: E402
 
+# (name, N, fs, listeners, streams, blocks per stream[, {env overrides read at engine creation}])
 CASES = [
     # name, N, fs, listeners, streams, blocks per stream
     ("cfg1 48 kS/s N=512 L=5", 512, 48000, 5, 4 * 148 * 12, 100),
@@ -27,9 +28,17 @@ CASES = [
     ("N=4096 L=100", 4096, 384000, 100, 148 * 4, 100),
     # >= 2 GiB of blocks per batch like the other shapes; 512 streams also give the fused N = 8192
     # kernel (k1_mid.cuh) its >= 2 segments per SM, below that the engine takes the block-parallel two-kernel path
-    ("cfg3 768 kS/s N=8192 L=200 (fused k1_mid)", 8192, 768000, 200, 512, 100),
-    ("cfg3 768 kS/s N=8192 L=200, 64 streams (two-kernel large-block path)", 8192, 768000, 200, 64, 100),
-    ("cfg5 24.576 MS/s N=65536 peak scan (large-block path)", 65536, 24576000, 0, 64, 100),
+    ("cfg3 768 kS/s N=8192 L=200 (k1_mid8k: TMA ring, 512 threads)", 8192, 768000, 200, 444, 100),
+    ("cfg3 768 kS/s N=8192 L=200 (k1_mid8k, 1 stage)", 8192, 768000, 200, 444, 100, {"SDR_K1_MID8K_STAGES": "1"}),
+    ("cfg3 768 kS/s N=8192 L=200 (r1 k1_mid<32>)", 8192, 768000, 200, 512, 100, {"SDR_K1_MID8K": "0"}),
+    ("cfg3 768 kS/s N=8192 L=200, 64 streams", 8192, 768000, 200, 64, 100),
+    ("cfg3 768 kS/s N=8192 L=200, 64 streams (r1 two-kernel large-block path)", 8192, 768000, 200, 64, 100, {"SDR_K1_MID8K": "0"}),
+    ("cfg5 24.576 MS/s N=65536 peak scan, 64 streams", 65536, 24576000, 0, 64, 100),
+    ("cfg5 24.576 MS/s N=65536 peak scan, 64 streams (r1 two-kernel path)", 65536, 24576000, 0, 64, 100, {"SDR_K1_WIDE": "0"}),
+    ("cfg5 24.576 MS/s N=65536 peak scan, 8 streams", 65536, 24576000, 0, 8, 100),
+    ("cfg5 24.576 MS/s N=65536 peak scan, 8 streams (r1 two-kernel path)", 65536, 24576000, 0, 8, 100, {"SDR_K1_WIDE": "0"}),
+    ("k2 cfg2 N=2048 L=50, K2 on the compute stream (r1)", 2048, 192000, 50, 148 * 12, 100, {"SDR_K2_OVERLAP": "0"}),
+    ("k2 cfg2 N=2048 L=50, K2 overlapped, high priority", 2048, 192000, 50, 148 * 12, 100, {"SDR_K2_PRIO": "high"}),
 ]
 
 
@@ -37,7 +46,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--only", default=None, help="substring filter on the case name")
+    ap.add_argument("--only", default=None, help="comma-separated substring filters on the case name")
     ap.add_argument("--stream-scale", type=int, default=1, help="multiply the stream count of the selected cases")
     args = ap.parse_args()
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
@@ -51,9 +60,13 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.Stream(device=dev)
     rows = []
-    for name, n, fs, nl, n_streams, nb in CASES:
-        if args.only and args.only not in name:
+    for case in CASES:
+        name, n, fs, nl, n_streams, nb = case[:6]
+        env = case[6] if len(case) > 6 else {}
+        if args.only and not any(o in name for o in args.only.split(",")):
             continue
+        saved = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
         n_streams *= args.stream_scale
         g = torch.Generator(device=dev)
         g.manual_seed(n + 7919 * rank)
@@ -70,6 +83,11 @@ def main():
                 v[:, :, 1] += 0.01 * torch.sin(ph * t)
         eng = capi.Engine(n, max_streams=n_streams, max_listeners=max(nl, 1), max_blocks_per_batch=n_streams * nb,
                           max_peaks_per_flush=128, n_slots=2, device=local_rank, cuda_stream=stream.cuda_stream)
+        for k, v in saved.items():  # the engine read its switches at creation
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
         sids = [eng.open_stream(fs) for _ in range(n_streams)]
         per = nb * 2 * n * 4
         prepared = eng.prepare([dict(stream=sids[i], iq=iq.data_ptr() + i * per, n_blocks=nb, listener_bins=bins[i])
@@ -82,7 +100,7 @@ def main():
         if world > 1:
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k1 = []
+        k1, k2 = [], []
         e0.record(stream)
         pend = []
         for _ in range(args.steps):
@@ -90,11 +108,14 @@ def main():
             if len(pend) == 2:
                 r = eng.collect_raw(pend[0])
                 k1.append(r.k1_ms)
+                k2.append(r.k2_ms)
                 eng.release(pend.pop(0))
+        eng.fence()  # the last post kernels run on the engine's own stream
         e1.record(stream)
         for tk in pend:
             r = eng.collect_raw(tk)
             k1.append(r.k1_ms)
+            k2.append(r.k2_ms)
             eng.release(tk)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.steps
@@ -110,6 +131,7 @@ def main():
                      "ms_per_step": ms,
                      "spectral_stage_ms": k1_ms, "spectral_stage_gbs": alg / (k1_ms * 1e-3) / 1e9,
                      "hbm_roofline_frac": alg / (k1_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                     "path_frac": alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "k2_ms": float(np.mean(k2)), "env": env,
                      "realtime_streams": world * samples / (ms * 1e-3) / fs})
         if rank == 0:
             print(json.dumps(rows[-1]))
