@@ -56,6 +56,14 @@ extern "C" {
 #define SDR_NO_PEAKS 0x4         /* skip FindPeaks at flushes (decode mode / pool full, rx/receiver.go:410) */
 #define SDR_NO_D2H 0x8           /* leave results on the device (throughput measurement of the kernels alone) */
 #define SDR_NO_TAPS 0x10         /* do not copy the float32 tap values back (keys, thresholds and peaks still are) */
+#define SDR_NO_RAW_KEYS 0x20     /* neither write nor copy back the one-byte raw key states: the packed, debounced
+                                    key_bits (1 bit per listener and block) are the result */
+
+/* sdr_work.listener_flags[l] */
+#define SDR_LISTENER_ACTIVE 0x1  /* an attached listener sits at this position (rx/listener.go:142-147: Listen ticks only
+                                    attached listeners); inactive positions produce key bit 0 and keep their state */
+#define SDR_LISTENER_RESET 0x2   /* a new listener was bound to this position (rx/listener.go:205-219 creates a new
+                                    SpectralDemodulator): its debouncer starts from zero state with this work */
 
 typedef struct sdr_engine sdr_engine;
 typedef int64_t sdr_ticket;
@@ -89,6 +97,12 @@ typedef struct {
     int n_listeners;          /* attached listeners */
     const int *listener_bins; /* Listener.SignalBin() of each (rx/listener.go:119-124); host memory */
     int format;               /* SDR_FMT_F32 (default 0) or SDR_FMT_KIWI_I16BE; one format per submit */
+    int signal_debounce;      /* SpectralDemodulator.SetSignalDebounce (cw/spectral.go:33-35; default 1, and < 2 means
+                                 pass-through, dsp/dsp.go:165-167): the BoolDebouncer of every listener position runs on
+                                 the device, its state is carried per (stream, position) across submits */
+    const uint8_t *listener_flags; /* [n_listeners] SDR_LISTENER_* or NULL (= every position active, none reset); host memory.
+                                 Callers that use the debounced key_bits keep a listener at a stable position (its pool
+                                 slot) for as long as it is bound */
 } sdr_work;
 
 /* dsp.Peak as found by dsp.FindPeaks (dsp/fft.go:254-285), before the host's frequency mapping.
@@ -113,7 +127,11 @@ typedef struct {
     /* per block and listener: spectrum[l.SignalBin()] (rx/receiver.go:393) */
     const float *taps;             /* [n_blocks][tap_stride] */
     /* per block and listener: value > threshold (cw/spectral.go:49), before debouncing */
-    const uint8_t *keys;           /* [n_blocks][tap_stride] */
+    const uint8_t *keys;           /* [n_blocks][tap_stride], NULL with SDR_NO_RAW_KEYS */
+    /* per block and listener, packed: the DEBOUNCED key state (cw/spectral.go:50, dsp/dsp.go:164-182) that
+       cw.Decoder.Tick consumes -- bit (l % 32) of word [block][l / 32] */
+    const uint32_t *key_bits;      /* [n_blocks][key_words] */
+    int key_words;                 /* tap_stride / 32 rounded up */
     /* per flush (every SDR_CUMULATION_SIZE blocks of a stream, rx/receiver.go:409) */
     const int *flush_block;        /* [n_flushes] index of the block that closed the window */
     const int *flush_n_peaks;      /* [n_flushes] peaks found (may exceed capacity: list is truncated) */

@@ -11,7 +11,8 @@ from . import _build
 OK, EINVAL, ECUDA, ENOMEM, EBUSY, ENOTREADY, ESTATE = 0, -1, -2, -3, -4, -5, -6
 MEM_HOST, MEM_DEVICE = 0, 1
 FMT_F32, FMT_KIWI_I16BE = 0, 1
-WANT_FLUSH_CUM, WANT_SPECTRUM, NO_PEAKS, NO_D2H, NO_TAPS = 1, 2, 4, 8, 16
+WANT_FLUSH_CUM, WANT_SPECTRUM, NO_PEAKS, NO_D2H, NO_TAPS, NO_RAW_KEYS = 1, 2, 4, 8, 16, 32
+LISTENER_ACTIVE, LISTENER_RESET = 1, 2
 CUMULATION_SIZE = 100
 
 _f32p = C.POINTER(C.c_float)
@@ -29,7 +30,7 @@ class EngineConfig(C.Structure):
 class Work(C.Structure):
     _fields_ = [("stream", C.c_int), ("n_blocks", C.c_int), ("iq", C.c_void_p), ("mem", C.c_int),
                 ("edge_width", C.c_int), ("peak_threshold", C.c_float), ("n_listeners", C.c_int),
-                ("listener_bins", _i32p), ("format", C.c_int)]
+                ("listener_bins", _i32p), ("format", C.c_int), ("signal_debounce", C.c_int), ("listener_flags", _u8p)]
 
 
 class Peak(C.Structure):
@@ -49,7 +50,7 @@ class Result(C.Structure):
                 ("block_size", C.c_int), ("max_peaks_per_flush", C.c_int),
                 ("work_block_offset", _i32p), ("work_flush_offset", _i32p),
                 ("psd_noise_floor", _f32p), ("noise_variance", _f64p), ("thresholds", _f32p), ("taps", _f32p),
-                ("keys", _u8p), ("flush_block", _i32p), ("flush_n_peaks", _i32p), ("flush_peaks", C.POINTER(Peak)),
+                ("keys", _u8p), ("key_bits", C.POINTER(C.c_uint32)), ("key_words", C.c_int), ("flush_block", _i32p), ("flush_n_peaks", _i32p), ("flush_peaks", C.POINTER(Peak)),
                 ("flush_cum", _f32p), ("spectrum", _f32p), ("psd", _f32p), ("gpu_ms", C.c_float),
                 ("k1_ms", C.c_float), ("k2_ms", C.c_float), ("gpu_launches", C.c_int)]
 
@@ -152,6 +153,7 @@ class BatchResult:
         self.thresholds = _np_from(r.thresholds, (nb, 4), np.float32)
         self.taps = _np_from(r.taps, (nb, ts), np.float32)
         self.keys = _np_from(r.keys, (nb, ts), np.uint8)
+        self.key_bits = _np_from(r.key_bits, (nb, r.key_words), np.uint32)
         self.flush_block = _np_from(r.flush_block, (nf,), np.int32)
         self.flush_n_peaks = _np_from(r.flush_n_peaks, (nf,), np.int32)
         self.flush_peaks = _np_from(r.flush_peaks, (nf, mp), PEAK_DTYPE)
@@ -161,6 +163,11 @@ class BatchResult:
         self.gpu_ms = float(r.gpu_ms)
         self.k1_ms, self.k2_ms = float(r.k1_ms), float(r.k2_ms)
         self.gpu_launches = int(r.gpu_launches)
+
+    def debounced_keys(self, n_listeners: int) -> np.ndarray:
+        """[blocks, n_listeners] uint8 view of the packed, debounced key states"""
+        bits = np.unpackbits(self.key_bits.view(np.uint8), axis=1, bitorder="little")
+        return bits[:, :n_listeners]
 
     def peaks(self, flush: int):
         n = min(int(self.flush_n_peaks[flush]), self.flush_peaks.shape[1])
@@ -269,6 +276,13 @@ class Engine:
             keep.append(bins)
             arr[i].n_listeners = bins.size
             arr[i].listener_bins = bins.ctypes.data_as(_i32p)
+            arr[i].signal_debounce = w.get("signal_debounce", 1)
+            if w.get("listener_flags") is not None:
+                lf = np.ascontiguousarray(np.asarray(w["listener_flags"], dtype=np.uint8))
+                if lf.size != bins.size:
+                    raise SdrError(EINVAL, "listener_flags must have one entry per listener bin")
+                keep.append(lf)
+                arr[i].listener_flags = lf.ctypes.data_as(_u8p)
         return (arr, len(works), keep)
 
     def submit_prepared(self, prepared, flags: int = 0) -> int:

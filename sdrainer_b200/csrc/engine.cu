@@ -58,6 +58,7 @@ struct Slot {
     float *d_thresholds = nullptr;
     float *d_taps = nullptr;
     uint8_t *d_keys = nullptr;
+    uint32_t *d_key_bits = nullptr, *h_key_bits = nullptr;
     int *d_flush_block = nullptr, *d_flush_n_peaks = nullptr;
     sdr_peak *d_flush_peaks = nullptr;
     float *d_flush_cum = nullptr;
@@ -123,7 +124,7 @@ struct sdr_engine {
     // L2-resident ring.  SDR_K1_WIDE=0 disables it (two-kernel path), =force takes it for every launch
     int k1_wide = 0;          // 0 off, 1 when the launch has enough segments, 2 always
     int k1w_max_teams = 0;    // co-resident CTAs / 16
-    int k1w_lookahead = 3, k1w_ring = 6;
+    int k1w_lookahead = 4, k1w_ring = 8;
     PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
     // N = 512: warp-per-block kernel (k1_warp.cuh), SDR_K1_WARP=0 selects the three-pass kernel
     float2 *d_tw512 = nullptr, *d_tw256w = nullptr;
@@ -140,6 +141,8 @@ struct sdr_engine {
     float *d_window = nullptr;
     float *d_cum_state = nullptr;
     RollingState *d_rolling = nullptr;
+    DebounceState *d_deb = nullptr;  // [max_streams][tap_stride] BoolDebouncer state of every listener position
+    int key_words = 1;
     std::vector<StreamInfo> streams;
     std::vector<Slot> slots;
     sdr_ticket next_ticket = 1;
@@ -182,7 +185,7 @@ struct ExactNf {
 
 // descriptor block layout (same on host and device)
 struct DescLayout {
-    size_t segs, works, post, lbins, block_seg, exact, segmaps, total;
+    size_t segs, works, post, lbins, lflags, block_seg, exact, segmaps, total;
 };
 DescLayout desc_layout(const sdr_engine *e) {
     DescLayout l;
@@ -195,6 +198,8 @@ DescLayout desc_layout(const sdr_engine *e) {
     off = align_up(off + sizeof(PostWork) * (size_t)e->cfg.max_streams, 256);
     l.lbins = off;
     off = align_up(off + sizeof(int) * (size_t)e->cfg.max_streams * (size_t)(e->cfg.max_listeners > 0 ? e->cfg.max_listeners : 1), 256);
+    l.lflags = off;
+    off = align_up(off + (size_t)e->cfg.max_streams * (size_t)(e->cfg.max_listeners > 0 ? e->cfg.max_listeners : 1), 256);
     l.block_seg = off;
     if (e->large) off = align_up(off + sizeof(int) * (size_t)e->cfg.max_blocks_per_batch, 256);
     l.exact = off;
@@ -646,6 +651,8 @@ void free_slot(Slot &s) {
     cudaFree(s.d_thresholds);
     cudaFree(s.d_taps);
     cudaFree(s.d_keys);
+    cudaFree(s.d_key_bits);
+    cudaFreeHost(s.h_key_bits);
     cudaFree(s.d_flush_block);
     cudaFree(s.d_flush_n_peaks);
     cudaFree(s.d_flush_peaks);
@@ -696,6 +703,8 @@ int alloc_slot(sdr_engine *e, Slot &s) {
     CK(e, cudaMalloc((void **)&s.d_thresholds, MB * 4 * sizeof(float)));
     CK(e, cudaMalloc((void **)&s.d_taps, MB * TS * sizeof(float)));
     CK(e, cudaMalloc((void **)&s.d_keys, MB * TS));
+    CK(e, cudaMalloc((void **)&s.d_key_bits, MB * (size_t)e->key_words * sizeof(uint32_t)));
+    CK(e, cudaMallocHost((void **)&s.h_key_bits, MB * (size_t)e->key_words * sizeof(uint32_t)));
     CK(e, cudaMalloc((void **)&s.d_flush_block, MF * sizeof(int)));
     CK(e, cudaMalloc((void **)&s.d_flush_n_peaks, MF * sizeof(int)));
     CK(e, cudaMalloc((void **)&s.d_flush_peaks, MF * MP * sizeof(sdr_peak)));
@@ -862,6 +871,7 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
     e->large = is_large;
     e->lg = lgeom;
     e->tap_stride = ((cfg->max_listeners > 0 ? cfg->max_listeners : 1) + 3) / 4 * 4;
+    e->key_words = (e->tap_stride + 31) / 32;
     e->max_segs = cfg->max_blocks_per_batch / SDR_CUMULATION_SIZE + 2 * cfg->max_streams + 2;
     e->max_flushes = cfg->max_blocks_per_batch / SDR_CUMULATION_SIZE + cfg->max_streams + 1;
     if (is_large) e->max_segs += cfg->max_blocks_per_batch / 16 + 2;  // segments are also cut at round boundaries (>= 16 blocks)
@@ -957,7 +967,7 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
                 const char *wv = getenv("SDR_K1_WIDE");
                 e->k1_wide = (wv && wv[0] == '0') ? 0 : (wv && wv[0] == 'f') ? 2 : 1;
                 const char *dv = getenv("SDR_K1_WIDE_LOOKAHEAD");
-                if (dv && atoi(dv) >= 2 && atoi(dv) <= 8) e->k1w_lookahead = atoi(dv);
+                if (dv && atoi(dv) >= 3 && atoi(dv) <= 8) e->k1w_lookahead = atoi(dv);
                 e->k1w_ring = 2 * e->k1w_lookahead;
                 int occ = 0, coop = 0;
                 cudaDriverEntryPointQueryResult qres;
@@ -1034,6 +1044,8 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
     }
     CKC(cudaMalloc((void **)&e->d_rolling, (size_t)cfg->max_streams * sizeof(RollingState)));
     CKC(cudaMemset(e->d_rolling, 0, (size_t)cfg->max_streams * sizeof(RollingState)));
+    CKC(cudaMalloc((void **)&e->d_deb, (size_t)cfg->max_streams * e->tap_stride * sizeof(DebounceState)));
+    CKC(cudaMemset(e->d_deb, 0, (size_t)cfg->max_streams * e->tap_stride * sizeof(DebounceState)));
     e->streams.resize(cfg->max_streams);
     e->nf_map_cache.assign((size_t)(e->N / 2 + 1) * 16, 0xff);
     {
@@ -1071,6 +1083,7 @@ void sdr_engine_destroy(sdr_engine *e) {
     cudaFree(e->d_window);
     cudaFree(e->d_cum_state);
     cudaFree(e->d_rolling);
+    cudaFree(e->d_deb);
     cudaFree(e->d_scratch);
     if (e->s_desc) cudaStreamDestroy(e->s_desc);
     if (e->own_post && e->s_post) cudaStreamDestroy(e->s_post);
@@ -1103,6 +1116,7 @@ static int stream_reset_locked(sdr_engine *e, int stream) {
     e->streams[stream].cum_count = 0;
     e->streams[stream].state_row = 0;
     CK(e, cudaMemsetAsync(e->d_rolling + stream, 0, sizeof(RollingState), e->s_post));
+    CK(e, cudaMemsetAsync(e->d_deb + (size_t)stream * e->tap_stride, 0, (size_t)e->tap_stride * sizeof(DebounceState), e->s_post));
     return SDR_OK;
 }
 
@@ -1252,6 +1266,7 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     WorkParams *wps = reinterpret_cast<WorkParams *>(s.h_desc + dl.works);
     PostWork *pws = reinterpret_cast<PostWork *>(s.h_desc + dl.post);
     int *lbins = reinterpret_cast<int *>(s.h_desc + dl.lbins);
+    uint8_t *lflags = reinterpret_cast<uint8_t *>(s.h_desc + dl.lflags);
     ExactNf *exs = reinterpret_cast<ExactNf *>(s.h_desc + dl.exact);
     int n_exact = 0;
     s.work_block_offset.assign(n_works + 1, 0);
@@ -1297,7 +1312,8 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
             memcpy(wps[w].nf_map, cm, 16);
         }
         for (int l = 0; l < wk.n_listeners; l++) lbins[lb_off + l] = wk.listener_bins[l];
-        lb_off += wk.n_listeners;
+        if (wk.listener_flags)
+            for (int l = 0; l < wk.n_listeners; l++) lflags[lb_off + l] = wk.listener_flags[l];
         PostWork &pw = pws[w];
         pw.stream = wk.stream;
         pw.block_out = block_off;
@@ -1308,7 +1324,10 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
         pw.peak_threshold = wk.peak_threshold;
         pw.n_listeners = wk.n_listeners;
         pw.do_peaks = (flags & SDR_NO_PEAKS) ? 0 : 1;
+        pw.debounce = wk.signal_debounce;
+        pw.lflags_off = wk.listener_flags ? lb_off : -1;
         pw.pad = 0;
+        lb_off += wk.n_listeners;
         s.work_block_offset[w] = block_off;
         s.work_flush_offset[w] = n_flushes;
         int c = si.cum_count, pos = 0, rem = wk.n_blocks;
@@ -1444,7 +1463,11 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     a2.variance = s.d_variance;
     a2.thresholds = s.d_thresholds;
     a2.taps = s.d_taps;
-    a2.keys = s.d_keys;
+    a2.keys = (flags & SDR_NO_RAW_KEYS) ? nullptr : s.d_keys;
+    a2.key_bits = s.d_key_bits;
+    a2.key_words = e->key_words;
+    a2.deb = e->d_deb;
+    a2.lflags = reinterpret_cast<const uint8_t *>(s.d_desc + dl.lflags);
     a2.tap_stride = e->tap_stride;
     a2.flush_cum = s.d_flush_cum;
     a2.flush_block = s.d_flush_block;
@@ -1470,7 +1493,8 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
         CK(e, cudaMemcpyAsync(s.h_thresholds, s.d_thresholds, nb * 4 * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
         if (!(flags & SDR_NO_TAPS))
             CK(e, cudaMemcpyAsync(s.h_taps, s.d_taps, nb * TS * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
-        CK(e, cudaMemcpyAsync(s.h_keys, s.d_keys, nb * TS, cudaMemcpyDeviceToHost, e->s_d2h));
+        if (!(flags & SDR_NO_RAW_KEYS)) CK(e, cudaMemcpyAsync(s.h_keys, s.d_keys, nb * TS, cudaMemcpyDeviceToHost, e->s_d2h));
+        CK(e, cudaMemcpyAsync(s.h_key_bits, s.d_key_bits, nb * e->key_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->s_d2h));
         if (n_flushes > 0) {
             const size_t nf = (size_t)n_flushes;
             CK(e, cudaMemcpyAsync(s.h_flush_block, s.d_flush_block, nf * sizeof(int), cudaMemcpyDeviceToHost, e->s_d2h));
@@ -1528,6 +1552,7 @@ int sdr_collect(sdr_engine *e, sdr_ticket t, int blocking, sdr_result *out) {
     out->n_blocks = s.n_blocks;
     out->n_flushes = s.n_flushes;
     out->tap_stride = e->tap_stride;
+    out->key_words = e->key_words;
     out->block_size = e->N;
     out->max_peaks_per_flush = e->cfg.max_peaks_per_flush;
     out->work_block_offset = s.work_block_offset.data();
@@ -1537,7 +1562,8 @@ int sdr_collect(sdr_engine *e, sdr_ticket t, int blocking, sdr_result *out) {
         out->noise_variance = s.h_variance;
         out->thresholds = s.h_thresholds;
         out->taps = (s.flags & SDR_NO_TAPS) ? nullptr : s.h_taps;
-        out->keys = s.h_keys;
+        out->keys = (s.flags & SDR_NO_RAW_KEYS) ? nullptr : s.h_keys;
+        out->key_bits = s.h_key_bits;
         out->flush_block = s.h_flush_block;
         out->flush_n_peaks = s.h_flush_n_peaks;
         out->flush_peaks = s.h_flush_peaks;

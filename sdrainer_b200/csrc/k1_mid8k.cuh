@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(512, 1) k1_mid8k_kernel(const K1Args a, const 
     extern __shared__ __align__(128) unsigned char m8_smem[];
     float2 *E = reinterpret_cast<float2 *>(m8_smem + Gm::OFF_E);      // [32][HW_PITCH]
     float *Ef = reinterpret_cast<float *>(m8_smem + Gm::OFF_E);       // |X|^2 of bin kk at Ef[(kk & 31) * 2*HW_PITCH + (kk >> 5)]
-    float2 *TW = reinterpret_cast<float2 *>(m8_smem + Gm::OFF_TW);    // W_256^m
+    float2 *TW = reinterpret_cast<float2 *>(m8_smem + Gm::OFF_TW);    // [15][16] W_256^(hl k)
     double *NFS1 = reinterpret_cast<double *>(m8_smem + Gm::OFF_NF);  // [NFB][10]
     double *NFS2 = NFS1 + NFB * 10;
     float *NFX = reinterpret_cast<float *>(NFS2 + NFB * 10);
@@ -76,7 +76,9 @@ __global__ void __launch_bounds__(512, 1) k1_mid8k_kernel(const K1Args a, const 
         for (int s = 0; s < NSTAGE; s++) mbar_init(&FULL[s], 1);
         fence_mbar_init();
     }
-    if (tid < 256) TW[tid] = __ldg(&tw256[tid]);
+    // per-lane layout [k - 1][hl] = W_256^(hl k): the sixteen lanes of a half-warp read sixteen consecutive words (both
+    // half-warps of a warp the same ones): one conflict-free wavefront per load instead of a strided table walk
+    if (tid < 240) TW[tid] = __ldg(&tw256[((tid & 15) * ((tid >> 4) + 1)) & 255]);
     // step twiddles of this thread's sixteen outputs: register p of dft16 holds j = OutIdx<16>(p), k1 = 2j + h
     float2 tws[16];
 #pragma unroll
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(512, 1) k1_mid8k_kernel(const K1Args a, const 
             {
                 HwTwiddle t;
 #pragma unroll
-                for (int k = 1; k < 16; k++) t.w[k - 1] = TW[(hl * k) & 255];
+                for (int k = 1; k < 16; k++) t.w[k - 1] = TW[(k - 1) * 16 + hl];
                 float2 *col = E + f * HW_PITCH;
 #pragma unroll
                 for (int q = 0; q < 16; q++) {
@@ -223,11 +225,15 @@ __global__ void __launch_bounds__(512, 1) k1_mid8k_kernel(const K1Args a, const 
             // ---------------- dsp.FindNoiseFloor (dsp/fft.go:215-252): window sums ----------------
             if (warp < 10) {
                 // float32 inside the <= 26-bin share of one row, float64 across the 32 rows of the window
+                // rows k1 and k1 + 16 share their banks (row pitch 2*273 words): the upper half-warp walks its share
+                // rotated by one element, so the two halves of the warp never meet in a bank
                 const float *pp = Ef + lane * (2 * HW_PITCH) + nf_p0;
+                const int rot = lane >> 4;
                 float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
 #pragma unroll
                 for (int i = 0; i + 1 < Gm::NFMAX; i += 2) {
-                    const float x0 = (i < nf_n) ? pp[i] : 0.f, x1 = (i + 1 < nf_n) ? pp[i + 1] : 0.f;
+                    const int j0 = (i + rot == Gm::NFMAX) ? 0 : i + rot, j1 = (i + 1 + rot == Gm::NFMAX) ? 0 : i + 1 + rot;
+                    const float x0 = (j0 < nf_n) ? pp[j0] : 0.f, x1 = (j1 < nf_n) ? pp[j1] : 0.f;
                     s1a += x0;
                     s2a = fmaf(x0, x0, s2a);
                     s1b += x1;

@@ -46,8 +46,8 @@ struct WideArgs {
     float *xto;                   // [blocks][10]
     int *nf_edge;                 // [blocks]
     float db_offset;              // 10*log10(20/N^2)
-    int lookahead;                // D >= 2: steps between producing and consuming a block (a store is published one
-                                  // step after it was committed, so D = 1 would wait on itself)
+    int lookahead;                // D >= 3: step i + D - 1 is produced in iteration i and published at its end; its row tile
+                                  // is requested early in iteration i + D - 2
     int ring;                     // R >= 2 D slots per team
 };
 
@@ -76,6 +76,7 @@ __device__ __forceinline__ void tma_store_tile_3d(const CUtensorMap *map, int c0
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ int ld_acquire_gpu(const int *p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -129,12 +130,12 @@ __global__ void __launch_bounds__(256, 2) k1_wide_kernel(const WideArgs wa) {
     const int swz_off = hl * 128 + ((((f >> 1) ^ (hl & 7))) << 4) + ((f & 1) << 3);
 
     float2 *TW = reinterpret_cast<float2 *>(wd_smem + K1W_OFF_TW);
-    TW[tid] = __ldg(&wa.tw256[tid]);
+    if (tid < 240) TW[tid] = __ldg(&wa.tw256[((tid & 15) * ((tid >> 4) + 1)) & 255]);  // [k - 1][hl] = W_256^(hl k): conflict-free reads
     // the fifteen W256^(hl k) of the half-warp transform are re-read from shared memory per transform: with the step
     // twiddles and the cumulation resident there is no room to keep them in registers at 2 CTAs per SM
     auto load_hw_twiddle = [&](HwTwiddle &t) {
 #pragma unroll
-        for (int k = 1; k < 16; k++) t.w[k - 1] = TW[(hl * k) & 255];
+        for (int k = 1; k < 16; k++) t.w[k - 1] = TW[(k - 1) * 16 + hl];
     };
     // step twiddles of my column c0 + f for the sixteen outputs k = hl + 16*OutIdx<16>(p): fixed for the whole launch
     float2 twc[16];
@@ -222,23 +223,27 @@ __global__ void __launch_bounds__(256, 2) k1_wide_kernel(const WideArgs wa) {
         ip.next(a.segs, a.n_segs, n_teams);
     };
 
-    // prologue: the first D steps are produced before anything is consumed
+    // prologue: the first D - 1 steps are produced before anything is consumed; the last issue_a loads the column tile
+    // of the main loop's first produce
     if (tid == 0) issue_a();
-    for (int d = 0; d < D; d++) {
+    for (int d = 0; d + 1 < D; d++) {
         if (ip.nb == 0) break;
         produce();
         if (tid == 0) {
             publish_pending();
-            if (d + 1 < D) issue_a();
+            issue_a();
         }
     }
-    if (tid == 0) issue_b();
+    if (tid == 32) issue_b();
 
     float cum[16];
     int e = 0, ws = 1, n_win = 9, L = 0;
     const int *lbins = nullptr;
 
     while (ic.nb != 0) {
+        // produce step ic + D - 1 first: its tile store then has the whole consume phase to complete before it is
+        // published, and the shared-memory tile it reads (A) is free again by the time the next column tile is requested
+        if (ip.nb != 0) produce();
         const Segment sg = a.segs[ic.seg];
         if (ic.blk == 0) {  // a new segment: window geometry, listeners, cumulation registers
             const WorkParams wp = a.works[sg.work];
@@ -267,9 +272,10 @@ __global__ void __launch_bounds__(256, 2) k1_wide_kernel(const WideArgs wa) {
         }
         __syncthreads();  // B is in registers
         if (tid == 0) {
-            publish_pending();  // the store committed at the end of the previous produce has long completed
-            issue_a();          // A is free again: next column tile (consumed by this iteration's produce)
-            issue_b();          // next row tile
+            if (pend_ob >= 0) bulk_wait_read();  // the outgoing tile has been read out of A ...
+            issue_a();                           // ... so A takes the next column tile (next iteration's produce)
+        } else if (tid == 32) {
+            issue_b();  // next row tile (its own warp: the wait for the producers does not delay thread 0's duties)
         }
         float2 *col = S + f * HW_PITCH;
         {
@@ -326,9 +332,8 @@ __global__ void __launch_bounds__(256, 2) k1_wide_kernel(const WideArgs wa) {
             for (int p = 0; p < 16; p++) dst[(r0 + f) + N1 * ((hl + 16 * OutIdx<16>::of(p) + 128) & 255)] = cum[p];
         }
         __syncthreads();  // the (psd, dB) tile and cnt are read: S may be overwritten, cnt rewritten
+        if (tid == 0) publish_pending();  // the store committed before this consume has completed by now
         ic.next(a.segs, a.n_segs, n_teams);
-
-        if (ip.nb != 0) produce();
     }
     if (tid == 0) publish_pending();
 }

@@ -28,6 +28,10 @@ struct RollingState {  // two dsp.RollingMean[float32] of size 60 advancing in l
     int pad;
 };
 
+// dsp.BoolDebouncer (dsp/dsp.go:139-182) of one listener position, carried across submits:
+// bit 0 effectiveState, bit 1 lastRawState, bits 2.. stateCount
+typedef uint32_t DebounceState;
+
 struct PostWork {
     int stream;
     int block_out;          // first block of this work in the per-block arrays
@@ -38,6 +42,8 @@ struct PostWork {
     float peak_threshold;   // rx.Receiver.peakThreshold
     int n_listeners;
     int do_peaks;
+    int debounce;           // SpectralDemodulator.SetSignalDebounce (cw/spectral.go:33-35); < 2: pass-through
+    int lflags_off;         // offset of this work's listener flags in K2Args::lflags, -1: every listener active, no reset
     int pad;
 };
 
@@ -48,7 +54,11 @@ struct K2Args {
     const double *variance;     // [blocks]
     float *thresholds;          // [blocks][4]
     const float *taps;          // [blocks][tap_stride]
-    uint8_t *keys;              // [blocks][tap_stride]
+    uint8_t *keys;              // [blocks][tap_stride] raw value > threshold, or nullptr (SDR_NO_RAW_KEYS)
+    uint32_t *key_bits;         // [blocks][key_words] debounced key state, bit l%32 of word l/32
+    int key_words;
+    DebounceState *deb;         // [max_streams][tap_stride]
+    const uint8_t *lflags;      // per-work listener flags (SDR_LISTENER_*)
     int tap_stride;
     const float *flush_cum;     // [flushes][N]
     int *flush_block;           // [flushes]
@@ -216,29 +226,49 @@ __global__ void __launch_bounds__(K2_THREADS) k2_post_kernel(const K2Args a) {
         for (int i = tid; i < cn; i += K2_THREADS)
             s_floor[i] = __fadd_rn(__fdiv_rn(s_floor[i], (float)SDR_NOISE_WINDOW), __fdiv_rn(s_dev[i], (float)SDR_NOISE_WINDOW));
         __syncthreads();
+        // key states (cw/spectral.go:48-54): a warp owns 32 listener positions and walks the chunk's blocks in order --
+        // state := value > threshold, the listener's BoolDebouncer (dsp/dsp.go:164-182, state carried per position), one
+        // ballot per block packs the 32 debounced states into a word
         const int L = w.n_listeners;
-        const int total = cn * L;
         const float *__restrict__ taps = a.taps + (size_t)(w.block_out + c0) * a.tap_stride;
-        uint8_t *__restrict__ keys = a.keys + (size_t)(w.block_out + c0) * a.tap_stride;
-        // one warp per block row (no per-element index division), four rows in flight per warp
-        (void)total;
+        uint8_t *__restrict__ keys = a.keys ? a.keys + (size_t)(w.block_out + c0) * a.tap_stride : nullptr;
+        uint32_t *__restrict__ kbits = a.key_bits + (size_t)(w.block_out + c0) * a.key_words;
         {
             const int wq = tid >> 5, lane = tid & 31;
             constexpr int NWQ = K2_THREADS / 32;
-            for (int i0 = wq; i0 < cn; i0 += 4 * NWQ) {
-                for (int l = lane; l < L; l += 32) {
+            for (int lg = wq; lg < a.key_words; lg += NWQ) {
+                const int l = lg * 32 + lane;
+                const uint8_t lf = (l < L) ? (w.lflags_off >= 0 ? a.lflags[w.lflags_off + l] : (uint8_t)SDR_LISTENER_ACTIVE) : (uint8_t)0;
+                const bool active = (lf & SDR_LISTENER_ACTIVE) != 0;
+                DebounceState *dst = a.deb + (size_t)w.stream * a.tap_stride + l;
+                DebounceState st = 0;
+                if (l < L && !((lf & SDR_LISTENER_RESET) && c0 == 0)) st = *dst;
+                bool eff = (st & 1u) != 0, last = (st & 2u) != 0;
+                int count = (int)(st >> 2);
+                for (int i0 = 0; i0 < cn; i0 += 4) {
                     float v[4];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int i = i0 + u * NWQ;
-                        v[u] = i < cn ? taps[(size_t)i * a.tap_stride + l] : 0.f;
-                    }
+                    for (int u = 0; u < 4; u++) v[u] = (active && i0 + u < cn) ? taps[(size_t)(i0 + u) * a.tap_stride + l] : 0.f;
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
-                        const int i = i0 + u * NWQ;
-                        if (i < cn) keys[(size_t)i * a.tap_stride + l] = v[u] > s_floor[i] ? 1 : 0;
+                        const int i = i0 + u;
+                        if (i < cn) {  // uniform across the warp
+                            const bool raw = active && v[u] > s_floor[i];
+                            if (keys && l < L) keys[(size_t)i * a.tap_stride + l] = raw ? 1 : 0;
+                            bool out = raw;
+                            if (w.debounce >= 2 && active) {
+                                count = (raw != last) ? 1 : count + 1;
+                                last = raw;
+                                if (count >= w.debounce) eff = raw;
+                                out = eff;
+                            }
+                            const uint32_t word = __ballot_sync(0xffffffffu, out);
+                            if (lane == 0) kbits[(size_t)i * a.key_words + lg] = word;
+                        }
                     }
                 }
+                if (l < L && active && w.debounce >= 2) *dst = (eff ? 1u : 0u) | (last ? 2u : 0u) | ((uint32_t)count << 2);
+                else if (l < L && (lf & SDR_LISTENER_RESET) && c0 == 0) *dst = 0;
             }
         }
         __syncthreads();

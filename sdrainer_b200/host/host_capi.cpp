@@ -164,6 +164,7 @@ void sdrh_receiver_set_find_next(void *p, int deterministic, unsigned long long 
     r.deterministicFindNext = deterministic != 0;
     r.rngSeed = seed;
 }
+void sdrh_receiver_set_device_debounce(void *p, int on) { ((ReceiverBox *)p)->rx.deviceDebounce = on != 0; }
 int sdrh_receiver_iq_data(void *p, int fs, const float *data, long long len) { return ((ReceiverBox *)p)->rx.IQData(fs, data, (size_t)len) ? 1 : 0; }
 int sdrh_receiver_process(void *p) {
     try {

@@ -331,6 +331,8 @@ class SpectralDemodulator {  // cw/spectral.go
         decoder_.Tick(debounced);
         return debounced;
     }
+    // the debouncer already ran on the device (sdr_result.key_bits): only cw.Decoder.Tick is left for the host
+    void TickDebounced(bool debounced) { decoder_.Tick(debounced); }
 
    private:
     dsp::BoolDebouncer signalDebouncer_;
@@ -629,7 +631,15 @@ class Listener {  // rx/listener.go:19-147
         if (recordKeys) keys_.push_back(k ? 1 : 0);
         return k;
     }
+    bool ListenDebounced(bool debounced) {  // same, for key states debounced on the device
+        if (!Attached()) return false;
+        demodulator_.TickDebounced(debounced);
+        if (recordKeys) keys_.push_back(debounced ? 1 : 0);
+        return debounced;
+    }
     void CheckWriteTimeout() { textProcessor_.CheckWriteTimeout(); }  // rx/listener.go:138-140
+    int slot = -1;      // stable position of this listener in the device's per-stream listener table (pool slot)
+    bool fresh = true;  // bound since the last submit: the device debouncer of its slot starts from zero
     const std::string &Text() const { return textProcessor_.Text(); }
     const std::vector<uint8_t> &Keys() const { return keys_; }
     bool recordKeys = true;  // test hook: keep the debounced key stream (grows with the run time)
@@ -724,6 +734,7 @@ class Receiver {
     void Stop() {  // :148-164
         if (!started_) return;
         listeners_.Reset();
+        std::fill(slots_.begin(), slots_.end(), nullptr);
         sdr_stream_close(engine_, stream_);
         sdr_free_pinned(engine_, ring_);
         ring_ = nullptr;
@@ -780,9 +791,26 @@ class Receiver {
             queue_.pop_front();
         }
         stagedBins_.clear();
-        for (Listener *l : listeners_.Listeners()) {
-            l->tapIndex = l->Attached() ? (int)stagedBins_.size() : -1;
-            if (l->Attached()) stagedBins_.push_back(l->SignalBin());
+        stagedFlags_.clear();
+        if (deviceDebounce) {
+            // one table entry per pool slot: a listener keeps its position for as long as it is bound, so the device can
+            // carry its BoolDebouncer state from submit to submit
+            stagedBins_.assign(slots_.size(), 0);
+            stagedFlags_.assign(slots_.size(), 0);
+            for (size_t sl = 0; sl < slots_.size(); sl++) {
+                Listener *l = slots_[sl];
+                if (!l) continue;
+                l->tapIndex = l->Attached() ? (int)sl : -1;
+                if (!l->Attached()) continue;
+                stagedBins_[sl] = l->SignalBin();
+                stagedFlags_[sl] = (uint8_t)(SDR_LISTENER_ACTIVE | (l->fresh ? SDR_LISTENER_RESET : 0));
+                l->fresh = false;
+            }
+        } else {
+            for (Listener *l : listeners_.Listeners()) {
+                l->tapIndex = l->Attached() ? (int)stagedBins_.size() : -1;
+                if (l->Attached()) stagedBins_.push_back(l->SignalBin());
+            }
         }
         w = sdr_work{};
         w.stream = stream_;
@@ -793,6 +821,8 @@ class Receiver {
         w.peak_threshold = peakThreshold_;
         w.n_listeners = (int)stagedBins_.size();
         w.listener_bins = stagedBins_.data();
+        w.signal_debounce = deviceDebounce ? signalDebounce_ : 1;
+        w.listener_flags = deviceDebounce ? stagedFlags_.data() : nullptr;
         return nb;
     }
     // peaks are always scanned in strain mode: a listener may time out inside the batch and free a pool slot
@@ -824,6 +854,9 @@ class Receiver {
     }
 
     bool recordReports = false;  // test hooks: keep one BlockReport per block / the peak list of every flush
+    // run dsp.BoolDebouncer on the device: the host reads one packed, debounced bit per listener and block
+    // and only ticks the decoder.  Set before Start().
+    bool deviceDebounce = false;
     const std::vector<BlockReport> &Reports() const { return reports_; }
     const std::vector<std::unique_ptr<Listener>> &AllListeners() const { return allListeners_; }
     const std::vector<int64_t> &AttachBlocks() const { return attachBlocks_; }
@@ -844,6 +877,13 @@ class Receiver {
         l->SetSilenceTimeout(silenceTimeout_);
         l->SetSignalDebounce(signalDebounce_);
         attachBlocks_.push_back(blockIndex_);
+        if (slots_.empty()) slots_.assign((size_t)listeners_.Size(), nullptr);
+        for (size_t sl = 0; sl < slots_.size(); sl++)
+            if (!slots_[sl]) {
+                slots_[sl] = l;
+                l->slot = (int)sl;
+                break;
+            }
         return l;
     }
     dsp::Peak *store(const dsp::Peak &p) {
@@ -886,14 +926,18 @@ class Receiver {
         std::vector<Listener *> detached;
         for (Listener *l : listeners_.Listeners()) {
             if (!l->Attached() || l->tapIndex < 0) continue;
-            l->ListenState(r.keys[(size_t)b * r.tap_stride + l->tapIndex] != 0);
+            if (deviceDebounce) l->ListenDebounced(((r.key_bits[(size_t)b * r.key_words + (l->tapIndex >> 5)] >> (l->tapIndex & 31)) & 1u) != 0);
+            else l->ListenState(r.keys[(size_t)b * r.tap_stride + l->tapIndex] != 0);
             if (mode_ == ReceiverMode::Strain && l->TimeoutExceeded()) {
                 peaks_->Deactivate(l->Peak());
                 l->Detach();
                 detached.push_back(l);
             }
         }
-        for (Listener *l : detached) listeners_.Release(l);
+        for (Listener *l : detached) {
+            if (l->slot >= 0 && l->slot < (int)slots_.size()) slots_[l->slot] = nullptr;
+            listeners_.Release(l);
+        }
         cumulationCount_++;
         blockIndex_++;
     }
@@ -938,6 +982,8 @@ class Receiver {
     int stream_ = -1;
     float *ring_ = nullptr;
     std::vector<int> stagedBins_;
+    std::vector<uint8_t> stagedFlags_;
+    std::vector<Listener *> slots_;  // pool slot -> bound listener
     std::deque<std::vector<float>> queue_;
     std::unique_ptr<dsp::FrequencyMapping> frequencyMapping_;
     std::unique_ptr<PeaksTable> peaks_;

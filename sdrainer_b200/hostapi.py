@@ -37,6 +37,7 @@ def lib():
         "sdrh_receiver_new": (vp, [vp, i, i]), "sdrh_receiver_free": (None, [vp]), "sdrh_receiver_start": (i, [vp, i, i]),
         "sdrh_receiver_stop": (None, [vp]), "sdrh_receiver_set": (None, [vp, f, i, d, d, i, ll]),
         "sdrh_receiver_set_find_next": (None, [vp, i, C.c_ulonglong]),
+        "sdrh_receiver_set_device_debounce": (None, [vp, i]),
         "sdrh_receiver_iq_data": (i, [vp, i, C.POINTER(C.c_float), ll]), "sdrh_receiver_process": (i, [vp]),
         "sdrh_receiver_error": (cp, [vp]), "sdrh_receiver_attach_at_bin": (i, [vp, i]),
         "sdrh_receiver_skipped": (i, [vp]), "sdrh_receiver_rejected": (i, [vp]),
@@ -111,6 +112,10 @@ class Receiver:
 
     def configure(self, peak_threshold=15.0, edge_width=70, silence_s=20.0, attach_s=120.0, debounce=1, center=0):
         self.L.sdrh_receiver_set(self.h, peak_threshold, edge_width, silence_s, attach_s, debounce, center)
+
+    def set_device_debounce(self, on=True):
+        """dsp.BoolDebouncer on the device, packed key bits back (call before start)"""
+        self.L.sdrh_receiver_set_device_debounce(self.h, 1 if on else 0)
 
     def set_find_next(self, deterministic=True, seed=1):
         self.L.sdrh_receiver_set_find_next(self.h, 1 if deterministic else 0, seed)

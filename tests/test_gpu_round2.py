@@ -258,3 +258,117 @@ def test_concurrent_submitters_on_one_engine(capi):
         assert not errs, errs
         for o in outs:
             assert np.array_equal(o.keys, ref.keys) and np.array_equal(o.thresholds, ref.thresholds)
+
+
+def _py_debounce(raw, thr, state=None):
+    """dsp.BoolDebouncer.Debounce (dsp/dsp.go:164-182) in plain Python"""
+    eff, last, count = state or (False, False, 0)
+    out = []
+    for r in raw:
+        r = bool(r)
+        if thr < 2:
+            out.append(r)
+            continue
+        count = 1 if r != last else count + 1
+        last = r
+        if count >= thr and r != eff:
+            eff = r
+        out.append(eff)
+    return np.asarray(out, np.uint8), (eff, last, count)
+
+
+@pytest.mark.parametrize("n,thr", [(512, 1), (512, 3), (2048, 2), (8192, 4)])
+def test_packed_key_bits_and_device_debouncer(capi, n, thr):
+    """one bit per listener and block, debounced on the device with the state carried per position across
+    ragged submits (dsp/dsp.go:139-182, cw/spectral.go:48-54); inactive positions stay 0 and keep their state; a reset
+    position starts from zero"""
+    fs = 48000 * n // 512
+    spec = synth.StreamSpec(sample_rate=fs, block_size=n, n_blocks=260, seed=n + thr,
+                            tones=synth.make_tones(np.random.default_rng(n + thr), 37, n, 70, wpm_range=(25.0, 40.0)))
+    iq = synth.generate(spec)
+    bins = [t.bin for t in spec.tones]
+    L = len(bins)
+    with capi.Engine(n, max_streams=2, max_listeners=40, max_blocks_per_batch=260, max_peaks_per_flush=64) as eng:
+        sid = eng.open_stream(fs)
+        whole = eng.collect(eng.submit([dict(stream=sid, iq=iq, listener_bins=bins, signal_debounce=thr)]))
+        raw = whole.keys[:, :L]
+        got = whole.debounced_keys(L)
+        for l in range(L):
+            want, _ = _py_debounce(raw[:, l], thr)
+            assert np.array_equal(got[:, l], want), (l, thr)
+        assert not whole.debounced_keys(whole.key_bits.shape[1] * 32)[:, L:].any()  # unused positions
+        # ragged submits: identical bits, no raw keys copied back
+        eng.reset_stream(sid)
+        parts, pos = [], 0
+        for c in (1, 59, 3, 100, 97):
+            r = eng.collect(eng.submit([dict(stream=sid, iq=iq[pos * 2 * n:(pos + c) * 2 * n], listener_bins=bins, signal_debounce=thr)],
+                                       capi.NO_RAW_KEYS | capi.NO_TAPS))
+            assert r.keys is None
+            parts.append(r.debounced_keys(L))
+            pos += c
+        assert np.array_equal(np.concatenate(parts), got)
+        # flags: position 1 inactive in the middle part (bit 0, state kept), position 2 reset at the start of the last part
+        eng.reset_stream(sid)
+        cuts = (0, 80, 170, 260)
+        outs = []
+        for k in range(3):
+            fl = np.full(L, capi.LISTENER_ACTIVE, np.uint8)
+            if k == 1:
+                fl[1] = 0
+            if k == 2:
+                fl[2] |= capi.LISTENER_RESET
+            r = eng.collect(eng.submit([dict(stream=sid, iq=iq[cuts[k] * 2 * n:cuts[k + 1] * 2 * n], listener_bins=bins,
+                                             signal_debounce=thr, listener_flags=fl)]))
+            outs.append(r.debounced_keys(L))
+        flagged = np.concatenate(outs)
+        others = [l for l in range(L) if l not in (1, 2)]
+        assert np.array_equal(flagged[:, others], got[:, others])
+        a, st = _py_debounce(raw[:80, 1], thr)
+        c, _ = _py_debounce(raw[170:, 1], thr, st)  # the debouncer did not see blocks 80..169
+        assert np.array_equal(flagged[:, 1], np.concatenate([a, np.zeros(90, np.uint8), c]))
+        a, _ = _py_debounce(raw[:170, 2], thr)
+        c, _ = _py_debounce(raw[170:, 2], thr)      # fresh debouncer from block 170
+        assert np.array_equal(flagged[:, 2], np.concatenate([a, c]))
+
+
+@pytest.mark.parametrize("debounce", [1, 2, 3])
+def test_receiver_with_device_debounce_matches_oracle(capi, oracle, host, debounce):
+    """rx.Receiver in strain mode with SetSignalDebounce(d): the debouncer runs on the device, the host mirror only ticks
+    the decoder -- same attach blocks, debounced key streams and text as the oracle's Receiver.run"""
+    from test_gpu_receiver import _oracle_receiver  # noqa: F401
+    L = oracle.lib()
+    spec = synth.config(1, seconds=9.0)
+    iq = synth.generate(spec)
+    n = spec.block_size
+    cfg = oracle.ReceiverConfig()
+    L.orc_receiver_config_default(C.byref(cfg), spec.sample_rate, n)
+    cfg.strain_mode, cfg.listener_pool_size, cfg.signal_debounce = 1, 30, debounce
+    orx = L.orc_receiver_new(C.byref(cfg))
+    fp = C.POINTER(C.c_float)
+    for b in range(spec.n_blocks):
+        blk = np.ascontiguousarray(iq[b * 2 * n:(b + 1) * 2 * n])
+        assert L.orc_receiver_process_block(orx, blk.ctypes.data_as(fp)) == 0
+    ref = []
+    for i in range(L.orc_receiver_listener_count(orx)):
+        nk = C.c_int64()
+        kp = L.orc_receiver_listener_keys(orx, i, C.byref(nk))
+        ref.append(dict(text=L.orc_receiver_listener_text(orx, i).decode("utf-8"), keys=np.array([kp[j] for j in range(nk.value)], np.uint8),
+                        attach_block=L.orc_receiver_listener_attach_block(orx, i)))
+    L.orc_receiver_free(orx)
+    with capi.Engine(n, max_streams=1, max_listeners=32, max_blocks_per_batch=100, max_peaks_per_flush=n // 2 + 1) as eng:
+        rx = host.Receiver(eng, strain=True, pool_size=30)
+        rx.set_device_debounce(True)
+        rx.configure(debounce=debounce)
+        rx.start(spec.sample_rate, n)
+        for b in range(spec.n_blocks):
+            assert rx.iq_data(spec.sample_rate, iq[b * 2 * n:(b + 1) * 2 * n])
+            if b % 5 == 4:
+                rx.process()
+        rx.process()
+        got = rx.listeners()
+        rx.close()
+    assert len(got) == len(ref) >= 3
+    for g, r in zip(got, ref):
+        assert g["attach_block"] == r["attach_block"]
+        assert np.array_equal(g["keys"], r["keys"])
+        assert g["text"] == r["text"]
