@@ -45,7 +45,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 HOST_LIB = os.path.join(HERE, "libsdrhost.so")
-HOST_SOURCES = [os.path.join(HERE, "host", "host_capi.cpp"), os.path.join(HERE, "host", "sdrhost.hpp")]
+HOST_SOURCES = [os.path.join(HERE, "host", "host_capi.cpp"), os.path.join(HERE, "host", "sdrhost.hpp"),
+                os.path.join(HERE, "host", "realtime.hpp")]
 
 
 def build_host(force: bool = False) -> str:
@@ -55,7 +56,7 @@ def build_host(force: bool = False) -> str:
     stale = (not os.path.exists(HOST_LIB)) or any(os.path.getmtime(d) > os.path.getmtime(HOST_LIB) for d in HOST_SOURCES + [LIB])
     if force or stale:
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-o", HOST_LIB,
-                               HOST_SOURCES[0], "-L" + HERE, "-lsdrgpu", "-Wl,-rpath,$ORIGIN"])
+                               HOST_SOURCES[0], "-L" + HERE, "-lsdrgpu", "-lpthread", "-Wl,-rpath,$ORIGIN"])
     return HOST_LIB
 
 

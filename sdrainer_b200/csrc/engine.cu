@@ -124,7 +124,8 @@ struct sdr_engine {
     // L2-resident ring.  SDR_K1_WIDE=0 disables it (two-kernel path), =force takes it for every launch
     int k1_wide = 0;          // 0 off, 1 when the launch has enough segments, 2 always
     int k1w_max_teams = 0;    // co-resident CTAs / 16
-    int k1w_lookahead = 4, k1w_ring = 8;
+    int k1w_lookahead = 3, k1w_ring = 6;
+    bool k1w_discard = true;  // SDR_K1_WIDE_DISCARD=0: leave consumed ring tiles to L2's write-back
     PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
     // N = 512: warp-per-block kernel (k1_warp.cuh), SDR_K1_WARP=0 selects the three-pass kernel
     float2 *d_tw512 = nullptr, *d_tw256w = nullptr;
@@ -391,12 +392,13 @@ cudaError_t launch_k1_wide(const sdr_engine *e, const K1Args &a, const LargeFast
     wa.db_offset = (float)(10.0 * log10(20.0 / (65536.0 * 65536.0)));
     wa.lookahead = e->k1w_lookahead;
     wa.ring = e->k1w_ring;
+    wa.discard = e->k1w_discard ? 1 : 0;
     const int n_teams = a.n_segs < e->k1w_max_teams ? a.n_segs : e->k1w_max_teams;
     cudaError_t rc = cudaMemsetAsync(wb.ready, 0, (size_t)n_blocks * sizeof(int), st);
     if (rc != cudaSuccess) return rc;
     void *params[] = {&wa};
     // cooperative: every CTA of the launch is resident at the same time (the teams wait on one another's tiles)
-    rc = cudaLaunchCooperativeKernel((const void *)k1_wide_kernel, dim3(K1W_TEAM * n_teams), dim3(256), params, K1W_SMEM_BYTES, st);
+    rc = cudaLaunchCooperativeKernel((const void *)k1_wide_kernel, dim3(K1W_TEAM * n_teams), dim3(K1W_THREADS), params, K1W_SMEM_BYTES, st);
     if (rc != cudaSuccess) return rc;
     rc = cudaMemcpyAsync(wb.h_err, wb.err, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (rc != cudaSuccess) return rc;
@@ -969,6 +971,10 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
                 const char *dv = getenv("SDR_K1_WIDE_LOOKAHEAD");
                 if (dv && atoi(dv) >= 3 && atoi(dv) <= 8) e->k1w_lookahead = atoi(dv);
                 e->k1w_ring = 2 * e->k1w_lookahead;
+                const char *rv = getenv("SDR_K1_WIDE_RING");
+                if (rv && atoi(rv) >= 2 * e->k1w_lookahead - 1 && atoi(rv) <= 16) e->k1w_ring = atoi(rv);
+                const char *kv = getenv("SDR_K1_WIDE_DISCARD");
+                e->k1w_discard = !(kv && kv[0] == '0');
                 int occ = 0, coop = 0;
                 cudaDriverEntryPointQueryResult qres;
                 void *fn = nullptr;
@@ -977,7 +983,7 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
                      cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
                      qres != cudaDriverEntryPointSuccess ||
                      cudaFuncSetAttribute(k1_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K1W_SMEM_BYTES) != cudaSuccess ||
-                     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_wide_kernel, 256, K1W_SMEM_BYTES) != cudaSuccess || occ < 1))
+                     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_wide_kernel, K1W_THREADS, K1W_SMEM_BYTES) != cudaSuccess || occ < 1))
                     e->k1_wide = 0;
                 cudaGetLastError();
                 if (e->k1_wide) {

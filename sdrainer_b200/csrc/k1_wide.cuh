@@ -48,15 +48,18 @@ struct WideArgs {
     float db_offset;              // 10*log10(20/N^2)
     int lookahead;                // D >= 3: step i + D - 1 is produced in iteration i and published at its end; its row tile
                                   // is requested early in iteration i + D - 2
-    int ring;                     // R >= 2 D slots per team
+    int ring;                     // R >= 2 D - 1 slots per team
+    int discard;                  // drop consumed row tiles from L2 (discard.global.L2) instead of letting them be written back
 };
 
 constexpr int K1W_OFF_A = 0;                                   // IQ column tile, later the outgoing tile (1024-byte aligned: 128B swizzle)
 constexpr int K1W_OFF_B = K1W_OFF_A + K1W_TILE_BYTES;          // row tile of the intermediate
 constexpr int K1W_OFF_S = K1W_OFF_B + K1W_TILE_BYTES;          // [16][HW_PITCH] transpose scratch, then the (psd, dB) tile
 constexpr int K1W_OFF_TW = K1W_OFF_S + 16 * HW_PITCH * 8;     // W_256^m
-constexpr int K1W_OFF_MISC = K1W_OFF_TW + 256 * 8;
+constexpr int K1W_OFF_TQ = K1W_OFF_TW + 256 * 8;             // [16][17] W_N^(16 c q)
+constexpr int K1W_OFF_MISC = K1W_OFF_TQ + 16 * 17 * 8;
 constexpr int K1W_SMEM_BYTES = K1W_OFF_MISC + 128;
+constexpr int K1W_THREADS = 288;                               // eight compute warps + the DMA warp
 
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
     uint64_t p;
@@ -111,85 +114,127 @@ struct WideIter {
     }
 };
 
-__global__ void __launch_bounds__(256, 2) k1_wide_kernel(const WideArgs wa) {
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the eight compute warps
+__device__ __forceinline__ void discard_l2_line(const void *p) { asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory"); }
+
+// Warps 0-7 compute; warp 8 (one lane) is the DMA warp: it owns every wait on another CTA, every TMA issue and every
+// publication, so that the compute warps only ever wait on shared-memory mbarriers.
+//   FULL_A   tx barrier: the IQ column tile has landed in A            (DMA -> compute)
+//   FULL_B   tx barrier: the row tile of the intermediate has landed in B (DMA -> compute)
+//   OUT_RDY  256 arrivals: the outgoing tile is complete in A           (compute -> DMA: store it)
+//   B_FREE   256 arrivals: B has been read into registers               (compute -> DMA: refill it)
+__global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs wa) {
     constexpr int N = 65536, N1 = 256;
     const K1Args &a = wa.a;
     extern __shared__ __align__(1024) unsigned char wd_smem[];
     unsigned char *A = wd_smem + K1W_OFF_A;
     const float2 *B = reinterpret_cast<const float2 *>(wd_smem + K1W_OFF_B);
     float2 *S = reinterpret_cast<float2 *>(wd_smem + K1W_OFF_S);
+    float2 *TW = reinterpret_cast<float2 *>(wd_smem + K1W_OFF_TW);  // [15][16] W_256^(hl k)
+    float2 *TQ = reinterpret_cast<float2 *>(wd_smem + K1W_OFF_TQ);  // [16 columns][17] W_N^(16 c q)
     uint64_t *FULL_A = reinterpret_cast<uint64_t *>(wd_smem + K1W_OFF_MISC);
-    uint64_t *FULL_B = FULL_A + 1;
-    int *cnt = reinterpret_cast<int *>(FULL_A + 2);  // [11]
+    uint64_t *FULL_B = FULL_A + 1, *OUT_RDY = FULL_A + 2, *B_FREE = FULL_A + 3;
+    int *cnt = reinterpret_cast<int *>(FULL_A + 4);  // [11]
 
     const int team = blockIdx.x / K1W_TEAM, rank = blockIdx.x % K1W_TEAM, n_teams = gridDim.x / K1W_TEAM;
-    const int tid = threadIdx.x, hl = tid & 15, f = tid >> 4, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int c0 = 16 * rank, r0 = 16 * rank;  // my columns when producing, my rows when consuming
     const int D = wa.lookahead, R = wa.ring;
+
+    if (tid < 240) TW[tid] = __ldg(&wa.tw256[((tid & 15) * ((tid >> 4) + 1)) & 255]);
+    // W_N^(c k) for k = hl + 16 q is W_N^(c hl) (one register pair per thread) times W_N^(16 c q) (this table):
+    // sixteen resident step twiddles per thread would not fit next to the cumulation at 2 CTAs per SM
+    if (tid < 256) TQ[(tid >> 4) * 17 + (tid & 15)] = __ldg(&wa.tw_step[(size_t)(c0 + (tid >> 4)) * 256 + 16 * (tid & 15)]);
+    if (tid == 0) {
+        mbar_init(FULL_A, 1);
+        mbar_init(FULL_B, 1);
+        mbar_init(OUT_RDY, 256);
+        mbar_init(B_FREE, 256);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (tid >= 256) {
+        // ================================ DMA warp ================================
+        if (tid != 256) return;
+        tensormap_acquire(wa.tmp_map);
+        const uint64_t policy = l2_evict_first_policy();
+        WideIter jc, jp, ja, jb;
+        jc.start(a.segs, a.n_segs, team);
+        jp = ja = jb = jc;
+        uint32_t ph_out = 0, ph_free = 0;
+        auto issue_a = [&]() {  // IQ column tile of the next step to produce (A is free)
+            if (ja.nb == 0) return;
+            if (ja.blk == 0) tensormap_acquire(&wa.seg_maps[ja.seg]);  // first use of this segment's map
+            mbar_expect_tx(FULL_A, K1W_TILE_BYTES);
+            tma_load_tile_3d(A, &wa.seg_maps[ja.seg], 2 * c0, 0, ja.blk, FULL_A, policy);
+            ja.next(a.segs, a.n_segs, n_teams);
+        };
+        auto issue_b = [&]() {  // row tile of the next step to consume, once all sixteen column tiles are published
+            if (jb.nb == 0) return;
+            const int ob = a.segs[jb.seg].block_out + jb.blk;
+            int spins = 0;
+            while (ld_acquire_gpu(&wa.ready[ob]) < K1W_TEAM) {
+                ++spins;
+                if (spins > K1W_MAX_SPIN || ((spins & 1023) == 0 && ld_acquire_gpu(wa.err) != 0)) {  // give up; once one wait failed, all do
+                    atomicExch(wa.err, 1);
+                    break;
+                }
+                __nanosleep(32);
+            }
+            fence_proxy_async_all();  // the acquire above orders the async-proxy read below after the producers' stores
+            mbar_expect_tx(FULL_B, K1W_TILE_BYTES);
+            tma_load_1d(wd_smem + K1W_OFF_B, wa.tmp + ((size_t)(team * R + jb.step % R) * N + (size_t)r0 * 256), K1W_TILE_BYTES, FULL_B);
+            jb.next(a.segs, a.n_segs, n_teams);
+        };
+        auto store_and_publish = [&]() {  // the compute warps finished producing step jp
+            mbar_wait(OUT_RDY, ph_out);
+            ph_out ^= 1u;
+            fence_proxy_async_all();  // consumers' discards of the slot's old lines (generic proxy) before this async-proxy write
+            tma_store_tile_3d(wa.tmp_map, 2 * c0, 0, team * R + jp.step % R, A);
+            bulk_commit();
+            bulk_wait_read();  // the tile has been read out of A ...
+            issue_a();         // ... which takes the next column tile at once
+            bulk_wait_all();   // the store has completed: publish the step
+            red_release_gpu_add(&wa.ready[a.segs[jp.seg].block_out + jp.blk], 1);
+            jp.next(a.segs, a.n_segs, n_teams);
+        };
+        issue_a();
+        for (int d = 0; d + 1 < D; d++) {  // prologue: D - 1 steps are produced before anything is consumed
+            if (jp.nb == 0) break;
+            store_and_publish();
+        }
+        issue_b();
+        while (jc.nb != 0) {
+            if (jp.nb != 0) store_and_publish();
+            mbar_wait(B_FREE, ph_free);
+            ph_free ^= 1u;
+            issue_b();
+            jc.next(a.segs, a.n_segs, n_teams);
+        }
+        return;
+    }
+
+    // ================================ compute warps ================================
+    const int hl = tid & 15, f = tid >> 4, lane = tid & 31, warp = tid >> 5;
     // byte offset of element (row hl + 16 j, column f) in a 128B-swizzled [256][16] tile, minus j * 2048
     const int swz_off = hl * 128 + ((((f >> 1) ^ (hl & 7))) << 4) + ((f & 1) << 3);
-
-    float2 *TW = reinterpret_cast<float2 *>(wd_smem + K1W_OFF_TW);
-    if (tid < 240) TW[tid] = __ldg(&wa.tw256[((tid & 15) * ((tid >> 4) + 1)) & 255]);  // [k - 1][hl] = W_256^(hl k): conflict-free reads
-    // the fifteen W256^(hl k) of the half-warp transform are re-read from shared memory per transform: with the step
-    // twiddles and the cumulation resident there is no room to keep them in registers at 2 CTAs per SM
+    const float2 tw_base = __ldg(&wa.tw_step[(size_t)(c0 + f) * 256 + hl]);  // W_N^(c hl)
+    // the fifteen W256^(hl k) of the half-warp transform are re-read from shared memory per transform
     auto load_hw_twiddle = [&](HwTwiddle &t) {
 #pragma unroll
         for (int k = 1; k < 16; k++) t.w[k - 1] = TW[(k - 1) * 16 + hl];
     };
-    // step twiddles of my column c0 + f for the sixteen outputs k = hl + 16*OutIdx<16>(p): fixed for the whole launch
-    float2 twc[16];
-#pragma unroll
-    for (int p = 0; p < 16; p++) twc[p] = __ldg(&wa.tw_step[(size_t)(c0 + f) * 256 + hl + 16 * OutIdx<16>::of(p)]);
 
-    if (tid == 0) {
-        mbar_init(FULL_A, 1);
-        mbar_init(FULL_B, 1);
-        fence_mbar_init();
-        tensormap_acquire(wa.tmp_map);
-    }
-    __syncthreads();
-
-    WideIter ic, ip, ia, ib;  // consume, produce, and (thread 0) the two load iterators one step ahead of them
+    WideIter ic, ip;
     ic.start(a.segs, a.n_segs, team);
-    ip = ia = ib = ic;
+    ip = ic;
     uint32_t phase_a = 0, phase_b = 0;
-    int pend_ob = -1;  // thread 0: step whose tile store is committed but not yet published
-    const uint64_t policy = l2_evict_first_policy();
 
-    auto publish_pending = [&]() {  // thread 0
-        if (pend_ob >= 0) {
-            bulk_wait_all();  // the tile store has completed: its writes are performed
-            red_release_gpu_add(&wa.ready[pend_ob], 1);
-            pend_ob = -1;
-        }
-    };
-    auto issue_a = [&]() {  // thread 0: IQ column tile of the next step to produce
-        if (ia.nb == 0) return;
-        if (ia.blk == 0) tensormap_acquire(&wa.seg_maps[ia.seg]);  // first use of this segment's map
-        mbar_expect_tx(FULL_A, K1W_TILE_BYTES);
-        tma_load_tile_3d(A, &wa.seg_maps[ia.seg], 2 * c0, 0, ia.blk, FULL_A, policy);
-        ia.next(a.segs, a.n_segs, n_teams);
-    };
-    auto issue_b = [&]() {  // thread 0: row tile of the next step to consume, once all sixteen column tiles are published
-        if (ib.nb == 0) return;
-        const int ob = a.segs[ib.seg].block_out + ib.blk;
-        int spins = 0;
-        while (ld_acquire_gpu(&wa.ready[ob]) < K1W_TEAM) {
-            ++spins;
-            if (spins > K1W_MAX_SPIN || ((spins & 1023) == 0 && ld_acquire_gpu(wa.err) != 0)) {  // give up; once one wait failed, all do
-                atomicExch(wa.err, 1);
-                break;
-            }
-            __nanosleep(64);
-        }
-        fence_proxy_async_all();  // the acquire above orders the async-proxy read below after the producers' stores
-        mbar_expect_tx(FULL_B, K1W_TILE_BYTES);
-        tma_load_1d(wd_smem + K1W_OFF_B, wa.tmp + ((size_t)(team * R + ib.step % R) * N + (size_t)r0 * 256), K1W_TILE_BYTES, FULL_B);
-        ib.next(a.segs, a.n_segs, n_teams);
-    };
-
-    // ---------------- produce: column tile of step ip -> ring ----------------
+    // ---------------- produce: column tile of step ip -> outgoing tile in A ----------------
     auto produce = [&]() {
         mbar_wait(FULL_A, phase_a);
         phase_a ^= 1u;
@@ -206,43 +251,33 @@ __global__ void __launch_bounds__(256, 2) k1_wide_kernel(const WideArgs wa) {
                 v[n1] = __fmul2_rn(v[n1], make_float2(w, w));
             }
         }
-        __syncthreads();  // the tile is in registers: A can take the outgoing tile; S is free (consume's tile reads are done)
-        HwTwiddle t;
-        load_hw_twiddle(t);
-        fft256_halfwarp_regs(v, S + f * HW_PITCH, t, hl);
-#pragma unroll
-        for (int p = 0; p < 16; p++)  // Z[k][c0 + f], k = hl + 16*OutIdx<16>(p), swizzled like the TMA box
-            *reinterpret_cast<float2 *>(A + swz_off + OutIdx<16>::of(p) * 2048) = cmul(v[p], twc[p]);
-        fence_proxy_async();  // generic-proxy writes of the tile before the async-proxy (TMA) read
-        __syncthreads();
-        if (tid == 0) {
-            tma_store_tile_3d(wa.tmp_map, 2 * c0, 0, team * R + ip.step % R, A);
-            bulk_commit();
-            pend_ob = a.segs[ip.seg].block_out + ip.blk;
+        compute_sync();  // the tile is in registers: A can take the outgoing tile; S is free (consume's tile reads are done)
+        {
+            HwTwiddle t;
+            load_hw_twiddle(t);
+            fft256_halfwarp_regs(v, S + f * HW_PITCH, t, hl);
         }
+#pragma unroll
+        for (int p = 0; p < 16; p++) {  // Z[k][c0 + f], k = hl + 16 q, swizzled like the TMA box
+            const int q = OutIdx<16>::of(p);
+            *reinterpret_cast<float2 *>(A + swz_off + q * 2048) = cmul(cmul(v[p], tw_base), TQ[f * 17 + q]);
+        }
+        fence_proxy_async();  // generic-proxy writes of the tile before the async-proxy (TMA) read
+        mbar_arrive(OUT_RDY);
         ip.next(a.segs, a.n_segs, n_teams);
     };
 
-    // prologue: the first D - 1 steps are produced before anything is consumed; the last issue_a loads the column tile
-    // of the main loop's first produce
-    if (tid == 0) issue_a();
-    for (int d = 0; d + 1 < D; d++) {
+    for (int d = 0; d + 1 < D; d++) {  // prologue (mirrors the DMA warp's)
         if (ip.nb == 0) break;
         produce();
-        if (tid == 0) {
-            publish_pending();
-            issue_a();
-        }
     }
-    if (tid == 32) issue_b();
 
     float cum[16];
     int e = 0, ws = 1, n_win = 9, L = 0;
     const int *lbins = nullptr;
 
     while (ic.nb != 0) {
-        // produce step ic + D - 1 first: its tile store then has the whole consume phase to complete before it is
-        // published, and the shared-memory tile it reads (A) is free again by the time the next column tile is requested
+        // produce step ic + D - 1 first: its store then has the whole consume phase to complete and be published
         if (ip.nb != 0) produce();
         const Segment sg = a.segs[ic.seg];
         if (ic.blk == 0) {  // a new segment: window geometry, listeners, cumulation registers
@@ -270,13 +305,11 @@ __global__ void __launch_bounds__(256, 2) k1_wide_kernel(const WideArgs wa) {
             const int n1 = (q & 3) * 4 + (q >> 2);
             v[n1] = B[f * 256 + 16 * n1 + hl];  // Z[r0 + f][16 n1 + hl]
         }
-        __syncthreads();  // B is in registers
-        if (tid == 0) {
-            if (pend_ob >= 0) bulk_wait_read();  // the outgoing tile has been read out of A ...
-            issue_a();                           // ... so A takes the next column tile (next iteration's produce)
-        } else if (tid == 32) {
-            issue_b();  // next row tile (its own warp: the wait for the producers does not delay thread 0's duties)
-        }
+        // The tile's lines in the ring are dead until a later step overwrites them: drop them from L2 instead of
+        // letting their eviction write 8 N bytes per block back to HBM (one 128-byte line per thread)
+        if (wa.discard)
+            discard_l2_line(reinterpret_cast<const unsigned char *>(wa.tmp + ((size_t)(team * R + ic.step % R) * N + (size_t)r0 * 256)) + tid * 128);
+        mbar_arrive(B_FREE);  // B is in registers: the DMA warp refills it
         float2 *col = S + f * HW_PITCH;
         {
             HwTwiddle t;
@@ -292,7 +325,7 @@ __global__ void __launch_bounds__(256, 2) k1_wide_kernel(const WideArgs wa) {
             cum[p] = __fadd_rn(cum[p], db);                                                                // rx/receiver.go:404-406
             col[hl + 16 * OutIdx<16>::of(p)] = make_float2(psd, db);
         }
-        __syncthreads();
+        compute_sync();
         if (a.dbg_psd) {  // parity / scope only: fftshifted stores (dsp/fft.go:54-57), half-warp = 16 consecutive bins
 #pragma unroll
             for (int i = 0; i < 16; i++) {
@@ -331,11 +364,9 @@ __global__ void __launch_bounds__(256, 2) k1_wide_kernel(const WideArgs wa) {
 #pragma unroll
             for (int p = 0; p < 16; p++) dst[(r0 + f) + N1 * ((hl + 16 * OutIdx<16>::of(p) + 128) & 255)] = cum[p];
         }
-        __syncthreads();  // the (psd, dB) tile and cnt are read: S may be overwritten, cnt rewritten
-        if (tid == 0) publish_pending();  // the store committed before this consume has completed by now
+        compute_sync();  // the (psd, dB) tile and cnt are read: S may be overwritten, cnt rewritten
         ic.next(a.segs, a.n_segs, n_teams);
     }
-    if (tid == 0) publish_pending();
 }
 
 }  // namespace sdr

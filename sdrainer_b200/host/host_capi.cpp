@@ -4,6 +4,7 @@
 #include <vector>
 
 #include "sdrhost.hpp"
+#include "realtime.hpp"
 
 using namespace sdrhost;
 
@@ -243,6 +244,36 @@ int sdrh_dispatcher_tick(void *p) {
 }
 int sdrh_dispatcher_submits(void *p) { return ((DispatcherBox *)p)->d.submits; }
 const char *sdrh_dispatcher_error(void *p) { return ((DispatcherBox *)p)->scratch.c_str(); }
+
+// ---- real-time channel-count harness (realtime.hpp) ----
+void *sdrh_rt_new(void *engine, int fs, int n, int listeners, int s_cap, int blocks_per_batch, int threads, int debounce, const float *src,
+                  int n_templates, int src_blocks, const int *bins) {
+    try {
+        return new rt::Harness((sdr_engine *)engine, fs, n, listeners, s_cap, blocks_per_batch, threads, debounce, src, n_templates,
+                               src_blocks, bins);
+    } catch (const std::exception &) {
+        return nullptr;
+    }
+}
+void sdrh_rt_free(void *p) { delete (rt::Harness *)p; }
+// out[0..8] = batch_s, copy_s, submit_s, collect_wait_s, decode_s, gpu_ms, ticks, chars, key_downs
+int sdrh_rt_run(void *p, int n_streams, int n_batches, double *out) {
+    try {
+        const rt::Stats st = ((rt::Harness *)p)->Run(n_streams, n_batches);
+        out[0] = st.batch_s;
+        out[1] = st.copy_s;
+        out[2] = st.submit_s;
+        out[3] = st.collect_wait_s;
+        out[4] = st.decode_s;
+        out[5] = st.gpu_ms;
+        out[6] = (double)st.ticks;
+        out[7] = (double)st.chars;
+        out[8] = (double)st.key_downs;
+        return 0;
+    } catch (const std::exception &) {
+        return -1;
+    }
+}
 
 // ---- cw.AudioDemodulator over the GPU Goertzel bank ----
 struct AudioBox {

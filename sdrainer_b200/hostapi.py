@@ -51,6 +51,8 @@ def lib():
         "sdrh_receiver_flush_peaks": (i, [vp, i, C.POINTER(i), C.POINTER(ll), i]),
         "sdrh_dispatcher_new": (vp, [vp, i, i]), "sdrh_dispatcher_free": (None, [vp]), "sdrh_dispatcher_add": (i, [vp, vp]),
         "sdrh_dispatcher_tick": (i, [vp]), "sdrh_dispatcher_submits": (i, [vp]), "sdrh_dispatcher_error": (cp, [vp]),
+        "sdrh_rt_new": (vp, [vp, i, i, i, i, i, i, i, C.POINTER(C.c_float), i, i, C.POINTER(C.c_int)]),
+        "sdrh_rt_free": (None, [vp]), "sdrh_rt_run": (i, [vp, i, i, C.POINTER(d)]),
         "sdrh_audio_new": (vp, [d, i]), "sdrh_audio_free": (None, [vp]), "sdrh_audio_blocksize": (i, [vp]),
         "sdrh_audio_set_scale": (None, [vp, d]), "sdrh_audio_write": (i, [vp, C.POINTER(C.c_float), i]),
         "sdrh_audio_close": (None, [vp]), "sdrh_audio_text": (cp, [vp]),
@@ -204,6 +206,40 @@ class Dispatcher:
     def close(self):
         if getattr(self, "h", None):
             self.L.sdrh_dispatcher_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class RealtimeHarness:
+    """host/realtime.hpp: S streams x L listeners through ring copy -> sdr_submit -> sdr_collect -> Decoder.Tick"""
+
+    FIELDS = ("batch_s", "copy_s", "submit_s", "collect_wait_s", "decode_s", "gpu_ms", "ticks", "chars", "key_downs")
+
+    def __init__(self, engine: capi.Engine, sample_rate, block_size, listeners, s_cap, blocks_per_batch, threads, src: np.ndarray,
+                 bins: np.ndarray, debounce=1):
+        self.L = lib()
+        self.src = np.ascontiguousarray(src, np.float32)       # [templates, src_blocks, 2N]
+        self.bins = np.ascontiguousarray(bins, np.int32)       # [templates, listeners]
+        nt, sb = self.src.shape[0], self.src.shape[1]
+        self.h = self.L.sdrh_rt_new(engine.h, sample_rate, block_size, listeners, s_cap, blocks_per_batch, threads, debounce,
+                                    self.src.ctypes.data_as(C.POINTER(C.c_float)), nt, sb, self.bins.ctypes.data_as(C.POINTER(C.c_int)))
+        if not self.h:
+            raise RuntimeError("realtime harness: allocation failed")
+
+    def run(self, n_streams, n_batches):
+        out = (C.c_double * 9)()
+        if self.L.sdrh_rt_run(self.h, n_streams, n_batches, out) != 0:
+            raise RuntimeError("realtime harness: run failed")
+        return dict(zip(self.FIELDS, [float(x) for x in out]))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sdrh_rt_free(self.h)
             self.h = None
 
     def __del__(self):
