@@ -9,8 +9,17 @@ x 100 blocks (one cumulation window, 1.07 s of signal) per step, S chosen so tha
 
   value  : Msamples/s with the IQ already resident in HBM (CUDA events on the launch stream).
   e2e    : same metric through the C ABI with HOST buffers: pinned H2D + kernels + result D2H in the
-           timed region, double-buffered over the engine's three streams.
-  roofline: K1's algorithmic bytes / K1's event-timed duration vs MEASURED_PEAKS.json hbm_gbs.
+           timed region, double-buffered over the engine's streams; beside it a bare pinned-H2D ceiling
+           probe on all ranks at once, the same loop with the float32 taps copied back, and the KiwiSDR
+           int16 wire format (4 bytes per sample).
+  roofline: the PATH's (K1 + K2) algorithmic bytes / device time per step vs MEASURED_PEAKS.json hbm_gbs
+           (`frac`); `k1_frac` is the spectral kernel alone.
+  configs : every other BASELINE.json config shape -- cfg 1, 3, 5 at a saturating stream count and cfg 3, 4, 5 at
+           their literal stream counts, deep in time, sharded by stream at --gpus N -- with ms_per_step, path
+           fraction and the kernel that served it.
+  realtime: MEASURED real-time channel count: S streams x 50 listeners fed in 107 ms batches through pinned ring
+           copy -> sdr_submit -> sdr_collect -> cw.Decoder.Tick per key bit on the host cores; the largest S whose
+           batch time stays below the batch's signal time.
   cpu_baseline: the CPU oracle (C restatement of the Go reference; the Go toolchain is absent)
            timed on this box's host cores on a bounded sample of the same workload.
 
@@ -337,6 +346,7 @@ def run_gpu(args):
             k1_ms.append(r.k1_ms)
             k2_ms.append(r.k2_ms)
             eng.release(tickets.pop(0))
+    eng.fence()  # K2 of the last batches runs on the engine's own stream: order it before the closing event
     e1.record(stream)
     for t in tickets:
         r = eng.collect_raw(t)
@@ -373,20 +383,35 @@ def run_gpu(args):
         parity = spot_check(eng, capi, iq, bins_all, sids)
 
     # ---- e2e: host buffers through the C ABI, H2D + kernels + D2H inside the timed region ----
+    kernel_name = eng.last_kernel()
     eng.close()
+    numa = bind_to_gpu_numa_node(torch, local_rank)  # pinned rings are first-touched NUMA-local to the GPU
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(args, capi, torch, iq, bins_all, local_rank, world, dist, device)
-
+        e2e["numa"] = numa
+    realtime = None
+    if not args.no_realtime:
+        realtime = run_realtime(args, capi, torch, iq, bins_all, local_rank, world, dist, device)
+    del iq
+    torch.cuda.empty_cache()
     peaks, peak_src = measured_peaks()
+    configs = None
+    if not args.no_configs:
+        configs = run_configs(args, capi, torch, dist, world, rank, local_rank, device, peaks["hbm_gbs"])
+
     abytes = alg_bytes_per_block() * n_blocks
-    achieved = abytes / (k1_avg_ms * 1e-3) / 1e9
+    step_ms = elapsed_ms / args.steps
+    achieved = abytes / (step_ms * 1e-3) / 1e9          # the path: K1 + K2 per step
+    k1_achieved = abytes / (k1_avg_ms * 1e-3) / 1e9      # the spectral kernel alone
     tr = ncu_traffic()
-    roofline = {"bound": "hbm", "kernel": "k1_spectral_kernel<2048>", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "peak_source": peak_src,
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "frac_of": "whole path (K1 + K2) per step",
+                "k1_frac": k1_achieved / peaks["hbm_gbs"], "peak_source": peak_src,
                 "traffic": (tr or {}).get("dram_bytes_per_launch"), "algorithmic_bytes_per_launch": abytes,
                 "k1_ms_per_launch": k1_avg_ms, "k1_share_of_step": k1_avg_ms * args.steps / elapsed_ms,
-                "k2_ms_per_launch": float(np.mean(k2_ms))}
+                "k2_ms_per_launch": float(np.mean(k2_ms)),
+                "k2_note": "K2 runs on the engine's second stream and overlaps the next batch's K1"}
     if tr:
         roofline["traffic_note"] = tr.get("note")
     # why the HBM fraction stops near 0.6: the arithmetic of a 2048-point fp32 transform + dB +
@@ -402,8 +427,7 @@ def run_gpu(args):
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(n_streams),
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "realtime_streams_per_gpu": value / world / (FS / 1e6),
-            "realtime_cw_channels_per_gpu": value / world / (FS / 1e6) * LISTENERS,
+            "realtime": realtime, "configs": configs,
             "parity_spot_check": parity,
         }
         print(json.dumps(line))
@@ -438,6 +462,56 @@ def spot_check(eng, capi, iq, bins_all, sids):
             "peak_lists_identical": bool(peaks_equal), "noise_floor_max_rel_err": worst}
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Best effort: run this rank on the CPUs next to its GPU so that pinned memory is first-touched on the GPU's NUMA
+    node.  Returns what was done (recorded in the JSON line)."""
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bus}"
+        with open(base + "/numa_node") as f:
+            node = int(f.read().strip())
+        with open(base + "/local_cpulist") as f:
+            cpulist = f.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use:
+            os.sched_setaffinity(0, use)
+        return {"pci": bus, "node": node, "cpus": cpulist, "bound": bool(use), "n_cpus": len(use) if use else len(allowed)}
+    except Exception as ex:  # noqa: BLE001
+        return {"bound": False, "why": str(ex)[:120]}
+
+
+def h2d_ceiling(torch, dist, world, device, nbytes, reps=4):
+    """Bare pinned-host -> device copy of the e2e batch size on all ranks at the same time (one cudaMemcpyAsync per
+    copy): what the box gives any H2D consumer at this GPU count."""
+    src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    src.zero_()
+    dst = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([dt], device=device, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    del src, dst
+    return nbytes * reps / dt / 1e9  # GB/s per rank, slowest rank
+
+
 def run_e2e(args, capi, torch, iq, bins_all, local_rank, world, dist, device):
     n_streams = iq.shape[0]
     n_blocks = n_streams * BLOCKS_PER_STREAM
@@ -451,8 +525,14 @@ def run_e2e(args, capi, torch, iq, bins_all, local_rank, world, dist, device):
     per = BLOCKS_PER_STREAM * 2 * N
     works = [dict(stream=sids[i], iq=host[i * per:(i + 1) * per], n_blocks=BLOCKS_PER_STREAM, edge_width=EDGE,
                   peak_threshold=15.0, listener_bins=bins_all[i]) for i in range(n_streams)]
-    flags = capi.NO_TAPS
-    prepared = eng.prepare(works)
+    # Kiwi wire format of the same batch: big-endian int16 I,Q, 4 bytes per sample (kiwi/client.go:298-308)
+    pinned16 = eng.alloc_pinned(nbytes // 2)
+    q = np.clip(np.rint(host * 32767.0), -32767, 32767).astype(">i2")
+    pinned16[:] = q.view(np.uint8)
+    del q
+    per16 = BLOCKS_PER_STREAM * 4 * N
+    works16 = [dict(stream=sids[i], iq=pinned16[i * per16:(i + 1) * per16], n_blocks=BLOCKS_PER_STREAM, edge_width=EDGE,
+                    peak_threshold=15.0, listener_bins=bins_all[i], format=capi.FMT_KIWI_I16BE) for i in range(n_streams)]
 
     def sync():
         if world > 1:
@@ -460,39 +540,194 @@ def run_e2e(args, capi, torch, iq, bins_all, local_rank, world, dist, device):
         torch.cuda.synchronize()
 
     steps = max(2, min(args.steps, args.e2e_steps))
-    for _ in range(2):
-        t = eng.submit_prepared(prepared, flags)
-        eng.collect_raw(t)
-        eng.release(t)
-    sync()
-    t0 = time.perf_counter()
-    pending = []
-    checksum = 0
-    for _ in range(steps):
-        pending.append(eng.submit_prepared(prepared, flags))
-        if len(pending) == 2:
-            r = eng.collect_raw(pending[0])
-            checksum += int(r.keys[0])  # touch the device->host result
-            eng.release(pending.pop(0))
-    for t in pending:
-        r = eng.collect_raw(t)
-        checksum += int(r.keys[0])
-        eng.release(t)
-    sync()
-    dt = time.perf_counter() - t0
-    if world > 1:
-        tt = torch.tensor([dt], device=device, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
+
+    def timed(prepared, flags):
+        for _ in range(2):
+            t = eng.submit_prepared(prepared, flags)
+            eng.collect_raw(t)
+            eng.release(t)
+        sync()
+        t0 = time.perf_counter()
+        pending = []
+        checksum = 0
+        for _ in range(steps):
+            pending.append(eng.submit_prepared(prepared, flags))
+            if len(pending) == 2:
+                r = eng.collect_raw(pending[0])
+                checksum += int(r.key_bits[0])  # touch the device->host result
+                eng.release(pending.pop(0))
+        for t in pending:
+            r = eng.collect_raw(t)
+            checksum += int(r.key_bits[0])
+            eng.release(t)
+        sync()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dt], device=device, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        return dt
+
     ts = (LISTENERS + 3) // 4 * 4
+    kw = (ts + 31) // 32
     n_flush = n_streams
-    d2h = n_blocks * (4 + 8 + 16 + ts) + n_flush * (4 + 4 + 128 * 28)
+    base_d2h = n_blocks * (4 + 8 + 16 + 4 * kw) + n_flush * (4 + 4 + 128 * 28)
+    # headline: the key-state design -- the Go loop's l.Listen(value, threshold) (rx/listener.go:142) is replaced by the
+    # device's debounced key bits, so neither the float32 taps nor the raw key bytes travel
+    dt = timed(eng.prepare(works), capi.NO_TAPS | capi.NO_RAW_KEYS)
+    # the same loop with the taps and raw keys copied back (what a host-side Listen() would need)
+    dt_taps = timed(eng.prepare(works), 0)
+    # KiwiSDR wire bytes in: half the H2D volume, bit-exact with the float path (tests/test_gpu_kiwi.py)
+    dt_i16 = timed(eng.prepare(works16), capi.NO_TAPS | capi.NO_RAW_KEYS)
     eng.free_pinned(pinned)
+    eng.free_pinned(pinned16)
     eng.close()
-    return {"value": world * n_blocks * N * steps / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(nbytes),
-            "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": 1e3 * dt / steps,
-            "note": "pinned host IQ -> sdr_submit (H2D, K1, K2) -> sdr_collect (keys, thresholds, noise scalars, peaks D2H); "
-                    "2 slots in flight; PCIe-bound"}
+    ceiling = h2d_ceiling(torch, dist, world, device, nbytes)
+    rate = lambda d: world * n_blocks * N * steps / d / 1e6  # noqa: E731
+    h2d_gbs = nbytes * steps / dt / 1e9
+    return {"value": rate(dt), "unit": "Msamples/s", "h2d_bytes_per_step": int(nbytes),
+            "d2h_bytes_per_step": int(base_d2h), "steps": steps, "ms_per_step": 1e3 * dt / steps,
+            "h2d_gbs_per_gpu": h2d_gbs, "h2d_ceiling_gbs": ceiling, "frac_of_ceiling": h2d_gbs / ceiling,
+            "ceiling_note": "bare cudaMemcpyAsync of the same pinned batch on all ranks at once, GB/s per GPU of the slowest rank",
+            "with_taps": {"value": rate(dt_taps), "d2h_bytes_per_step": int(base_d2h + n_blocks * (4 * ts + ts))},
+            "e2e_i16": {"value": rate(dt_i16), "h2d_bytes_per_step": int(nbytes // 2), "format": "SDR_FMT_KIWI_I16BE (4 B/sample)"},
+            "note": "pinned host IQ -> sdr_submit (H2D, K1, K2) -> sdr_collect (packed debounced key bits, thresholds, noise "
+                    "scalars, peaks D2H); 2 slots in flight; PCIe-bound"}
+
+
+def run_realtime(args, capi, torch, iq, bins_all, local_rank, world, dist, device):
+    """Largest number of 192 kS/s streams x 50 listeners this rank sustains at >= 1x real time, measured end to end with
+    the host decoder in the loop (host/realtime.hpp).  All ranks run at the same time and share the host."""
+    from sdrainer_b200 import hostapi
+    B = 10                                   # blocks per stream per batch: 106.7 ms of signal (<= 100 ms-class batches)
+    signal_s = B * N / FS
+    cap = args.rt_cap if args.rt_cap else (32768 if world == 1 else 16384)
+    # host threads of this rank: the CPUs it is bound to (NUMA-local to the GPU), an equal share of the box at N > 1
+    threads = max(2, min(len(os.sched_getaffinity(0)), (os.cpu_count() or 2) // world))
+    nt = min(16, iq.shape[0])
+    src = iq[:nt].reshape(nt, BLOCKS_PER_STREAM, 2 * N).cpu().numpy()
+    bins = np.stack([np.asarray(bins_all[i], np.int32) for i in range(nt)])
+    eng = capi.Engine(N, max_streams=cap, max_listeners=LISTENERS, max_blocks_per_batch=cap * B, max_peaks_per_flush=64,
+                      n_slots=2, device=local_rank)
+    h = hostapi.RealtimeHarness(eng, FS, N, LISTENERS, cap, B, threads, src, bins, debounce=1)
+    trials = []
+
+    def trial(S):
+        r = h.run(S, 8)
+        ok = r["batch_s"] <= signal_s
+        if world > 1:  # the whole job keeps up only if every rank does
+            tt = torch.tensor([0.0 if ok else 1.0], device=device, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ok = float(tt.item()) == 0.0
+        trials.append({"streams": S, "batch_ms": 1e3 * r["batch_s"], "keeps_up": ok})
+        return ok, r
+
+    if world > 1:
+        dist.barrier()
+    ok, best = trial(cap)
+    lo, hi = (cap, cap) if ok else (0, cap)
+    best_r = best if ok else None
+    while hi - lo > max(256, cap // 64):
+        mid = (lo + hi) // 2 // 64 * 64
+        ok, r = trial(mid)
+        if ok:
+            lo, best_r = mid, r
+        else:
+            hi = mid
+    h.close()
+    eng.close()
+    if best_r is None:
+        return {"streams_per_gpu": 0, "trials": trials, "note": "no tested stream count kept up"}
+    total = lo * world
+    return {"streams_per_gpu": lo, "listeners_per_stream": LISTENERS, "cw_channels_per_gpu": lo * LISTENERS,
+            "cw_channels_total": total * LISTENERS, "streams_total": total, "capped_by_probe": lo >= cap,
+            "signal_ms_per_batch": 1e3 * signal_s, "batch_ms": 1e3 * best_r["batch_s"],
+            "stage_ms": {"ring_copy": 1e3 * best_r["copy_s"], "submit": 1e3 * best_r["submit_s"],
+                         "collect_wait": 1e3 * best_r["collect_wait_s"], "decode": 1e3 * best_r["decode_s"],
+                         "gpu_kernels": best_r["gpu_ms"]},
+            "decoder_ticks_per_s": best_r["ticks"] / max(best_r["batch_s"], 1e-9) / 6, "host_threads": threads,
+            "chars_decoded": int(best_r["chars"]), "trials": trials,
+            "method": "S streams x 50 listeners, 10-block (106.7 ms) batches: pageable frames -> pinned ring copy -> one "
+                      "sdr_submit (device debounce, packed key bits) -> sdr_collect -> cw.Decoder.Tick per key bit; two "
+                      "batches in flight; keeps up = steady-state batch time <= signal time of a batch (lag < 1 batch)"}
+
+
+CONFIG_CASES = [
+    # name, N, fs, listeners, streams TOTAL (literal counts are sharded over the ranks) or per GPU, blocks per stream, sharded?
+    ("cfg1 48 kS/s N=512 L=5, saturating", 512, 48000, 5, 4 * 148 * 12, 100, False),
+    ("cfg3 768 kS/s N=8192 L=200, saturating", 8192, 768000, 200, 444, 100, False),
+    ("cfg3 literal: 1 stream x 4000 blocks (5.3 s)", 8192, 768000, 200, 1, 4000, False),
+    ("cfg4 literal: 64 streams total x 2000 blocks (21 s)", 2048, 192000, 50, 64, 2000, True),
+    ("cfg5 24.576 MS/s N=65536 peak scan, saturating", 65536, 24576000, 0, 72, 100, False),
+    ("cfg5 literal: 8 streams total x 800 blocks (2.1 s)", 65536, 24576000, 0, 8, 800, True),
+]
+
+
+def run_configs(args, capi, torch, dist, world, rank, local_rank, device, hbm_gbs):
+    """Device-resident step time of every other BASELINE config shape (same timing rules as the headline: CUDA events
+    on the launch stream, >= 3 warm-up steps, inputs larger than L2 or stated otherwise, max over ranks)."""
+    out = []
+    stream = torch.cuda.Stream(device=device)
+    steps = max(3, min(args.steps, args.config_steps))
+    for name, n, fs, nl, n_streams, nb, sharded in CONFIG_CASES:
+        if sharded:
+            n_streams = max(1, n_streams // world)
+        g = torch.Generator(device=device)
+        g.manual_seed(n + 7919 * rank)
+        iq = torch.randn((n_streams, nb * n * 2), generator=g, device=device, dtype=torch.float32) * 1e-4
+        rng = np.random.default_rng(n)
+        bins = [np.sort(rng.choice(np.arange(80, n - 80), size=nl, replace=False)).astype(np.int32) for _ in range(n_streams)]
+        t = torch.arange(n, device=device, dtype=torch.float32)
+        for si in range(min(n_streams, 16)):  # carriers on a few listener bins so that keys / peaks have work
+            for b in bins[si][:8]:
+                ph = 2 * np.pi * float(b - n // 2) / n
+                v = iq[si].view(nb, n, 2)
+                v[:, :, 0] += 0.01 * torch.cos(ph * t)
+                v[:, :, 1] += 0.01 * torch.sin(ph * t)
+        eng = capi.Engine(n, max_streams=n_streams, max_listeners=max(nl, 1), max_blocks_per_batch=n_streams * nb,
+                          max_peaks_per_flush=128, n_slots=2, device=local_rank, cuda_stream=stream.cuda_stream)
+        sids = [eng.open_stream(fs) for _ in range(n_streams)]
+        per = nb * 2 * n * 4
+        prepared = eng.prepare([dict(stream=sids[i], iq=iq.data_ptr() + i * per, n_blocks=nb, listener_bins=bins[i])
+                                for i in range(n_streams)])
+        for _ in range(3):
+            tk = eng.submit_prepared(prepared, capi.NO_D2H)
+            eng.collect_raw(tk)
+            eng.release(tk)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k1 = []
+        pend = []
+        e0.record(stream)
+        for _ in range(steps):
+            pend.append(eng.submit_prepared(prepared, capi.NO_D2H))
+            if len(pend) == 2:
+                k1.append(eng.collect_raw(pend[0]).k1_ms)
+                eng.release(pend.pop(0))
+        eng.fence()
+        e1.record(stream)
+        for tk in pend:
+            k1.append(eng.collect_raw(tk).k1_ms)
+            eng.release(tk)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            tt = torch.tensor([ms], device=device, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        alg = alg_bytes_per_block(n, nl) * n_streams * nb
+        k1_ms = float(np.mean(k1))
+        out.append({"config": name, "block_size": n, "sample_rate": fs, "listeners": nl, "streams_per_gpu": n_streams,
+                    "blocks_per_stream": nb, "batch_bytes_per_gpu": int(n_streams * nb * n * 8), "kernel": eng.last_kernel(),
+                    "ms_per_step": ms, "msamples_per_s": world * n_streams * nb * n / (ms * 1e-3) / 1e6,
+                    "path_frac": alg / (ms * 1e-3) / 1e9 / hbm_gbs, "k1_frac": alg / (k1_ms * 1e-3) / 1e9 / hbm_gbs,
+                    "realtime_x": (nb * n / fs) / (ms * 1e-3), "steps": steps})
+        eng.close()
+        del iq
+        torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -507,6 +742,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config table (cfg 1, 3, 4, 5 shapes)")
+    ap.add_argument("--no-realtime", action="store_true", help="skip the measured real-time channel count")
+    ap.add_argument("--config-steps", type=int, default=8)
+    ap.add_argument("--rt-cap", type=int, default=0, help="largest stream count the real-time probe tries (per GPU)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: at least 3 warm-up steps

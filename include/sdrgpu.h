@@ -181,6 +181,9 @@ int64_t sdr_engine_launch_count(const sdr_engine *e);
  * batch's spectral kernel.  A caller that supplied cfg.cuda_stream and wants "everything submitted so far" ordered
  * before later work on that stream (e.g. a timing event) calls this: the stream waits for the last post kernel. */
 int sdr_engine_fence(sdr_engine *e);
+/* name of the spectral kernel the most recent sdr_submit launched (which one serves a block size / batch shape is the
+ * engine's choice: DESIGN.md section 4); for benchmarks and logs */
+const char *sdr_engine_last_kernel(const sdr_engine *e);
 
 /* ---- dsp-signature-compatible single calls (drop-in correctness, not throughput) ------------- */
 /* dsp.FFT.IQToSpectrumAndPSD with the receiver's shiftedMagnitude projection

@@ -65,7 +65,7 @@ SYMBOLS = [
     "sdr_version", "sdr_device_count", "sdr_engine_create", "sdr_engine_destroy", "sdr_last_error",
     "sdr_alloc_pinned", "sdr_free_pinned", "sdr_stream_open", "sdr_stream_close", "sdr_stream_reset",
     "sdr_stream_cumulation_count", "sdr_submit", "sdr_collect", "sdr_release", "sdr_ticket_device_ptrs",
-    "sdr_engine_launch_count", "sdr_engine_fence", "sdr_dsp_iq_to_spectrum_and_psd", "sdr_dsp_find_noise_floor",
+    "sdr_engine_launch_count", "sdr_engine_fence", "sdr_engine_last_kernel", "sdr_dsp_iq_to_spectrum_and_psd", "sdr_dsp_find_noise_floor",
     "sdr_dsp_find_peaks", "sdr_kiwi_decode_iq_bytes", "sdr_goertzel_create", "sdr_goertzel_destroy", "sdr_goertzel_last_error",
     "sdr_goertzel_blocksize", "sdr_goertzel_process_audio", "sdr_goertzel_process_iq",
 ]
@@ -114,6 +114,8 @@ def lib():
     L.sdr_engine_launch_count.argtypes = [C.c_void_p]
     L.sdr_engine_launch_count.restype = C.c_int64
     L.sdr_engine_fence.argtypes = [C.c_void_p]
+    L.sdr_engine_last_kernel.argtypes = [C.c_void_p]
+    L.sdr_engine_last_kernel.restype = C.c_char_p
     L.sdr_dsp_iq_to_spectrum_and_psd.argtypes = [C.c_void_p, _f32p, C.c_int, _f32p, _f32p]
     L.sdr_dsp_find_noise_floor.argtypes = [C.c_void_p, _f32p, C.c_int, _f32p, _f64p]
     L.sdr_dsp_find_peaks.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_float, C.POINTER(Peak), C.c_int, _i32p]
@@ -321,6 +323,9 @@ class Engine:
 
     def launch_count(self) -> int:
         return int(self.L.sdr_engine_launch_count(self.h))
+
+    def last_kernel(self) -> str:
+        return self.L.sdr_engine_last_kernel(self.h).decode()
 
     def fence(self):
         """orders everything submitted so far before later work on the caller's cuda_stream (sdr_engine_fence)"""

@@ -148,6 +148,7 @@ struct sdr_engine {
     std::vector<Slot> slots;
     sdr_ticket next_ticket = 1;
     int64_t launches = 0;
+    const char *last_kernel = "";  // spectral kernel of the most recent submit (sdr_engine_last_kernel)
     int k1_grid_cap = 0;  // resident CTAs of K1 on this device
     bool k1_tw2r = true;  // kernel variant: pass-2 twiddles in registers (SDR_K1_TW2R=0 selects the smem-table variant)
     // cache of choose_nf_map results, indexed by edge width (first byte 0xff = not computed)
@@ -1166,6 +1167,8 @@ int sdr_stream_cumulation_count(sdr_engine *e, int stream, int *out) {
 
 int64_t sdr_engine_launch_count(const sdr_engine *e) { return e ? e->launches : 0; }
 
+const char *sdr_engine_last_kernel(const sdr_engine *e) { return e ? e->last_kernel : ""; }
+
 int sdr_engine_fence(sdr_engine *e) {
     if (!e) return SDR_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
@@ -1421,19 +1424,25 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     int k1_launches = 1;
     if (!e->large) {
         CK(e, launch_k1(e, a1, dbg, e->s_compute, i16, warp_ok));
+        e->last_kernel = (e->k1_mid && e->N == 4096 && !i16) ? "k1_mid_kernel<16>" : (e->k1_warp && warp_ok) ? "k1_warp_kernel"
+                         : e->N == 512 ? "k1_spectral_kernel<512>" : e->N == 1024 ? "k1_spectral_kernel<1024>"
+                         : e->N == 2048 ? "k1_spectral_kernel<2048>" : "k1_spectral_kernel<4096>";
     } else if (e->N == 8192 && block_off <= e->round_blocks && (e->k1_mid8k == 2 || (e->k1_mid8k == 1 && n_segs >= e->sm_count / 3))) {
         // TMA-staged single pass, one 512-thread CTA per SM (k1_mid8k.cuh).  Below ~SMs/3 segments the block-parallel
         // two-kernel path (which does not serialise the blocks of a stream) is faster.
         CK(e, launch_k1_mid8k(e, a1, dbg, e->s_compute));
+        e->last_kernel = "k1_mid8k_kernel";
     } else if (e->k1_mid && e->N == 8192 && block_off <= e->round_blocks && n_segs >= 2 * e->sm_count) {
         // enough segments to fill the GPU with segment-sequential CTAs: fused single pass (k1_mid.cuh)
         CK(e, launch_k1_mid(e, a1, dbg, e->s_compute));
+        e->last_kernel = "k1_mid_kernel<32>";
     } else if (use_wide) {
         // single pass over HBM: one team of 16 CTAs per segment, the intermediate in an L2-resident ring (k1_wide.cuh)
         const LargeFastBufs lb{s.d_tmp, s.d_spec_round, s.d_nf_part, s.d_xto, s.d_nf_edge};
         const WideBufs wb{reinterpret_cast<const CUtensorMap *>(s.d_desc + dl.segmaps), s.d_wide_map, s.d_wide_tmp, s.d_wide_ready,
                           s.d_wide_err, s.h_wide_err};
         CK(e, launch_k1_wide(e, a1, lb, wb, block_off, dbg, e->s_compute));
+        e->last_kernel = "k1_wide_kernel";
         k1_launches = 2;
     } else if (e->round_blocks > 0) {
         // rounds of consecutive blocks; the segment table is in block order and no segment straddles a round
@@ -1451,8 +1460,10 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
         const LargeFastBufs lb{s.d_tmp, s.d_spec_round, s.d_nf_part, s.d_xto, s.d_nf_edge};
         CK(e, launch_large_fast(e, a1, lb, reinterpret_cast<const int *>(s.d_desc + dl.block_seg), rounds, block_off, dbg, e->s_compute,
                                 &k1_launches));
+        e->last_kernel = e->lg.n1 == 256 ? "fast_cols256_kernel + fast_rows256_kernel" : "fast_cols32_kernel + fast_rows256_kernel";
     } else {
         CK(e, launch_large(e, a1, s.d_tmp, reinterpret_cast<const int *>(s.d_desc + dl.block_seg), block_off, n_segs, e->s_compute));
+        e->last_kernel = "sub_fft_kernel (Stockham four-step)";
         k1_launches = 4;
     }
     if (n_exact > 0) {

@@ -59,6 +59,7 @@ constexpr int K1W_OFF_TW = K1W_OFF_S + 16 * HW_PITCH * 8;     // W_256^m
 constexpr int K1W_OFF_TQ = K1W_OFF_TW + 256 * 8;             // [16][17] W_N^(16 c q)
 constexpr int K1W_OFF_MISC = K1W_OFF_TQ + 16 * 17 * 8;
 constexpr int K1W_SMEM_BYTES = K1W_OFF_MISC + 128;
+constexpr int K1W_NFMAX = 26;                                  // positions of one noise window in one row: ceil(6553 / 256)
 constexpr int K1W_THREADS = 288;                               // eight compute warps + the DMA warp
 
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
@@ -137,7 +138,6 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
     float2 *TQ = reinterpret_cast<float2 *>(wd_smem + K1W_OFF_TQ);  // [16 columns][17] W_N^(16 c q)
     uint64_t *FULL_A = reinterpret_cast<uint64_t *>(wd_smem + K1W_OFF_MISC);
     uint64_t *FULL_B = FULL_A + 1, *OUT_RDY = FULL_A + 2, *B_FREE = FULL_A + 3;
-    int *cnt = reinterpret_cast<int *>(FULL_A + 4);  // [11]
 
     const int team = blockIdx.x / K1W_TEAM, rank = blockIdx.x % K1W_TEAM, n_teams = gridDim.x / K1W_TEAM;
     const int tid = threadIdx.x;
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
     }
 
     float cum[16];
-    int e = 0, ws = 1, n_win = 9, L = 0;
+    int e = 0, ws = 1, n_win = 9, L = 0, nf_p0 = 0, nf_n = 0;
     const int *lbins = nullptr;
 
     while (ic.nb != 0) {
@@ -287,7 +287,16 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
             n_win = nf_window_count(N, e);
             L = wp.n_listeners;
             lbins = a.listener_bins + wp.listener_off;
-            if (tid < 11) cnt[tid] = tile_count_below(e + tid * ws, r0, N1, 256);  // read after the barriers below
+            // noise floor: thread (window w = 2 warp + lane/16, row j = lane % 16) of warps 0-4; the window's bins in row
+            // k1 = r0 + j are the positions [nf_p0, nf_p0 + nf_n) (bin kk = k1 + 256 p)
+            nf_p0 = nf_n = 0;
+            if (warp < 5) {
+                const int w = 2 * warp + (lane >> 4), k1 = r0 + (lane & 15);
+                const int lo = e + w * ws, hi = lo + ws;
+                nf_p0 = lo < k1 ? 0 : (lo - k1 + 255) >> 8;
+                const int p1 = hi <= k1 ? 0 : min(256, (hi - k1 + 255) >> 8);
+                nf_n = max(p1 - nf_p0, 0);
+            }
 #pragma unroll
             for (int p = 0; p < 16; p++) {
                 const int kk = (r0 + f) + N1 * ((hl + 16 * OutIdx<16>::of(p) + 128) & 255);
@@ -317,54 +326,70 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
             fft256_halfwarp_regs(v, col, t, hl);
         }
         __syncwarp();
-        // X[(r0 + f) + 256 k2], k2 = hl + 16*OutIdx<16>(p)
+        // X[(r0 + f) + 256 k2], k2 = hl + 16*OutIdx<16>(p).  The row's (dead) transpose storage takes two float planes in
+        // fftshifted order (dsp/fft.go:54-57): |X|^2 at prow[k2s], dB at prow[256 + k2s], k2s = (k2 + 128) & 255, i.e.
+        // bin kk = (r0 + f) + 256 k2s
+        float *prow = reinterpret_cast<float *>(col);
 #pragma unroll
         for (int p = 0; p < 16; p++) {
             const float psd = fmaf(v[p].x, v[p].x, v[p].y * v[p].y);                                      // dsp/fft.go:71-73
             const float db = __fadd_rn(fmaf(3.01029995663981195f, fast_log2(psd), wa.db_offset), 120.0f);  // rx/receiver.go:376-378
             cum[p] = __fadd_rn(cum[p], db);                                                                // rx/receiver.go:404-406
-            col[hl + 16 * OutIdx<16>::of(p)] = make_float2(psd, db);
+            const int k2s = hl + ((16 * OutIdx<16>::of(p) + 128) & 255);
+            prow[k2s] = psd;
+            prow[256 + k2s] = db;
         }
         compute_sync();
-        if (a.dbg_psd) {  // parity / scope only: fftshifted stores (dsp/fft.go:54-57), half-warp = 16 consecutive bins
+        const float *Sf = reinterpret_cast<const float *>(S);  // row j of the tile: Sf[j * 2*HW_PITCH + (0 | 256) + k2s]
+        if (a.dbg_psd) {  // parity / scope only: half-warp = 16 consecutive bins
 #pragma unroll
             for (int i = 0; i < 16; i++) {
-                const int k2 = f + 16 * i;
-                const float2 o = S[hl * HW_PITCH + k2];
-                const int kk = ((r0 + hl) + N1 * k2 + N / 2) & (N - 1);
-                a.dbg_psd[(size_t)ob * N + kk] = o.x;
-                a.dbg_spectrum[(size_t)ob * N + kk] = o.y;
+                const int k2s = f + 16 * i;
+                const int kk = (r0 + hl) + N1 * k2s;
+                a.dbg_psd[(size_t)ob * N + kk] = Sf[hl * (2 * HW_PITCH) + k2s];
+                a.dbg_spectrum[(size_t)ob * N + kk] = Sf[hl * (2 * HW_PITCH) + 256 + k2s];
             }
         }
-        // noise-window sums over this CTA's bins in ascending bin order (float64 sums of float32 values)
-        for (int w = warp; w < 10; w += 8) {
-            double a1 = 0.0, a2 = 0.0;
-            for (int i = cnt[w] + lane; i < cnt[w + 1]; i += 32) {
-                const double x = (double)S[(i & 15) * HW_PITCH + (((i >> 4) + 128) & 255)].x;
-                a1 += x;
-                a2 = fma(x, x, a2);
+        // dsp.FindNoiseFloor (dsp/fft.go:215-252), window sums over this CTA's bins: thread (window w, row j) sums the <= 27
+        // positions of window w that live in row j (contiguous floats, float32 inside the share), a float64 half-warp
+        // reduction over the sixteen rows gives this CTA's (sum x, sum x^2) of the window
+        if (warp < 5) {
+            const int w = 2 * warp + (lane >> 4);
+            const float *pp = Sf + (lane & 15) * (2 * HW_PITCH) + nf_p0;
+            float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+#pragma unroll
+            for (int i = 0; i + 1 < K1W_NFMAX; i += 2) {
+                const float x0 = (i < nf_n) ? pp[i] : 0.f, x1 = (i + 1 < nf_n) ? pp[i + 1] : 0.f;
+                s1a += x0;
+                s2a = fmaf(x0, x0, s2a);
+                s1b += x1;
+                s2b = fmaf(x1, x1, s2b);
             }
-            a1 = warp_sum(a1);
-            a2 = warp_sum(a2);
-            if (lane == 0) wa.nf_part[((size_t)ob * K1W_TEAM + rank) * 10 + w] = make_double2(a1, a2);
+            double d1 = (double)(s1a + s1b), d2 = (double)(s2a + s2b);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+                d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+            }
+            if ((lane & 15) == 0) wa.nf_part[((size_t)ob * K1W_TEAM + rank) * 10 + w] = make_double2(d1, d2);
         }
         if (tid < n_win) {  // x_to = psd[e + (w+1)*ws] (dsp/fft.go:238-243) if this CTA owns that bin
-            const int k = (e + (tid + 1) * ws - N / 2) & (N - 1);
-            const int k1 = k & (N1 - 1);
-            if (k1 >= r0 && k1 < r0 + 16) wa.xto[(size_t)ob * 10 + tid] = S[(k1 - r0) * HW_PITCH + k / N1].x;
+            const int kk = e + (tid + 1) * ws;
+            const int k1 = kk & (N1 - 1);
+            if (k1 >= r0 && k1 < r0 + 16) wa.xto[(size_t)ob * 10 + tid] = Sf[(k1 - r0) * (2 * HW_PITCH) + (kk >> 8)];
         }
         if (rank == 0 && tid == 0) wa.nf_edge[ob] = e;
         for (int l = tid; l < L; l += 256) {  // listener taps (rx/receiver.go:393) on bins this CTA owns
-            const int k = (__ldg(&lbins[l]) - N / 2) & (N - 1);
-            const int k1 = k & (N1 - 1);
-            if (k1 >= r0 && k1 < r0 + 16) a.taps[(size_t)ob * a.tap_stride + l] = S[(k1 - r0) * HW_PITCH + k / N1].y;
+            const int kk = __ldg(&lbins[l]);
+            const int k1 = kk & (N1 - 1);
+            if (k1 >= r0 && k1 < r0 + 16) a.taps[(size_t)ob * a.tap_stride + l] = Sf[(k1 - r0) * (2 * HW_PITCH) + 256 + (kk >> 8)];
         }
         if (ic.blk == sg.n_blocks - 1) {  // end of the segment: flush or save the cumulation
             float *dst = (sg.flush_idx >= 0) ? a.flush_cum + (size_t)sg.flush_idx * N : a.cum_state + (size_t)sg.state_out * N;
 #pragma unroll
             for (int p = 0; p < 16; p++) dst[(r0 + f) + N1 * ((hl + 16 * OutIdx<16>::of(p) + 128) & 255)] = cum[p];
         }
-        compute_sync();  // the (psd, dB) tile and cnt are read: S may be overwritten, cnt rewritten
+        compute_sync();  // the |X|^2 / dB planes are read: S may be overwritten
         ic.next(a.segs, a.n_segs, n_teams);
     }
 }
