@@ -1,6 +1,6 @@
 // k2_post.cuh -- K2: per-stream threshold scan, key states and peak lists.
 //
-// Replaces, per stream and batch (one CTA per work):
+// Replaces, per stream and batch:
 //   rx/receiver.go:383-385   dB conversion of the noise-floor scalars + two float32 rolling means
 //                            over 60 blocks (dsp.RollingMean.Put, dsp/dsp.go:257-268), peak and
 //                            listener thresholds
@@ -74,7 +74,7 @@ __device__ __forceinline__ float psd_value_in_db_shifted(float psd_value, double
     return __fadd_rn(db, (float)SDR_DBM_SHIFT);
 }
 
-constexpr int K2_THREADS = 128;  // one CTA per work; ~2000 works fit in one wave of 148 x 12 CTAs (latency-bound kernel)
+constexpr int K2_THREADS = 128;
 constexpr int K2_CHUNK = 1024;  // blocks staged in shared memory per sequential pass
 
 // dsp.FindPeaks on one vector `cum` of n bins; all K2_THREADS threads of the CTA participate.
@@ -160,11 +160,16 @@ __device__ void find_peaks_block(const float *__restrict__ cum, int n, float cum
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(K2_THREADS) k2_post_kernel(const K2Args a) {
+// K2 is three launches so that every stage has its own parallelism (a launch with few streams but many blocks -- 64
+// receivers, 21 s each -- must not collapse onto a handful of CTAs):
+//   k2_thresholds_kernel  one CTA per work: the two rolling means (inherently sequential per stream) and the thresholds
+//   k2_keys_kernel        one CTA per (work, 64 blocks): value > threshold for every listener, packed by warp ballot
+//   k2_peaks_kernel       one CTA per flush: dsp.FindPeaks
+
+__global__ void __launch_bounds__(K2_THREADS) k2_thresholds_kernel(const K2Args a) {
     __shared__ float s_floor[K2_CHUNK];
     __shared__ float s_dev[K2_CHUNK];
     __shared__ RollingState s_roll;
-    __shared__ int s_scan[K2_THREADS];
     const PostWork w = a.works[blockIdx.x];
     const int tid = threadIdx.x;
     const double n2 = (double)a.n * (double)a.n;
@@ -173,6 +178,11 @@ __global__ void __launch_bounds__(K2_THREADS) k2_post_kernel(const K2Args a) {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(a.rolling + w.stream);
         uint32_t *dst = reinterpret_cast<uint32_t *>(&s_roll);
         for (int i = tid; i < (int)(sizeof(RollingState) / 4); i += K2_THREADS) dst[i] = src[i];
+    }
+    // flushes of this work (rx/receiver.go:409-425): which block closed each window
+    for (int f = tid; f < w.n_flushes; f += K2_THREADS) {
+        a.flush_block[w.flush_out + f] = w.block_out + w.first_flush_block + f * SDR_CUMULATION_SIZE;
+        if (!w.do_peaks) a.flush_n_peaks[w.flush_out + f] = 0;
     }
     __syncthreads();
 
@@ -218,81 +228,108 @@ __global__ void __launch_bounds__(K2_THREADS) k2_post_kernel(const K2Args a) {
             th.x = noise_floor;
             th.y = noise_dev;
             th.z = __fadd_rn(w.peak_threshold, noise_floor);
-            th.w = __fadd_rn(noise_floor, noise_dev);
+            th.w = __fadd_rn(noise_floor, noise_dev);  // the listeners' threshold (rx/receiver.go:394)
             reinterpret_cast<float4 *>(a.thresholds)[b] = th;
         }
         __syncthreads();
-        // key states (cw/spectral.go:49) for this chunk: the listen threshold of block i is kept in s_floor[i]
-        for (int i = tid; i < cn; i += K2_THREADS)
-            s_floor[i] = __fadd_rn(__fdiv_rn(s_floor[i], (float)SDR_NOISE_WINDOW), __fdiv_rn(s_dev[i], (float)SDR_NOISE_WINDOW));
-        __syncthreads();
-        // key states (cw/spectral.go:48-54): a warp owns 32 listener positions and walks the chunk's blocks in order --
-        // state := value > threshold, the listener's BoolDebouncer (dsp/dsp.go:164-182, state carried per position), one
-        // ballot per block packs the 32 debounced states into a word
-        const int L = w.n_listeners;
-        const float *__restrict__ taps = a.taps + (size_t)(w.block_out + c0) * a.tap_stride;
-        uint8_t *__restrict__ keys = a.keys ? a.keys + (size_t)(w.block_out + c0) * a.tap_stride : nullptr;
-        uint32_t *__restrict__ kbits = a.key_bits + (size_t)(w.block_out + c0) * a.key_words;
-        {
-            const int wq = tid >> 5, lane = tid & 31;
-            constexpr int NWQ = K2_THREADS / 32;
-            for (int lg = wq; lg < a.key_words; lg += NWQ) {
-                const int l = lg * 32 + lane;
-                const uint8_t lf = (l < L) ? (w.lflags_off >= 0 ? a.lflags[w.lflags_off + l] : (uint8_t)SDR_LISTENER_ACTIVE) : (uint8_t)0;
-                const bool active = (lf & SDR_LISTENER_ACTIVE) != 0;
-                DebounceState *dst = a.deb + (size_t)w.stream * a.tap_stride + l;
-                DebounceState st = 0;
-                if (l < L && !((lf & SDR_LISTENER_RESET) && c0 == 0)) st = *dst;
-                bool eff = (st & 1u) != 0, last = (st & 2u) != 0;
-                int count = (int)(st >> 2);
-                for (int i0 = 0; i0 < cn; i0 += 4) {
-                    float v[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) v[u] = (active && i0 + u < cn) ? taps[(size_t)(i0 + u) * a.tap_stride + l] : 0.f;
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int i = i0 + u;
-                        if (i < cn) {  // uniform across the warp
-                            const bool raw = active && v[u] > s_floor[i];
-                            if (keys && l < L) keys[(size_t)i * a.tap_stride + l] = raw ? 1 : 0;
-                            bool out = raw;
-                            if (w.debounce >= 2 && active) {
-                                count = (raw != last) ? 1 : count + 1;
-                                last = raw;
-                                if (count >= w.debounce) eff = raw;
-                                out = eff;
-                            }
-                            const uint32_t word = __ballot_sync(0xffffffffu, out);
-                            if (lane == 0) kbits[(size_t)i * a.key_words + lg] = word;
-                        }
-                    }
-                }
-                if (l < L && active && w.debounce >= 2) *dst = (eff ? 1u : 0u) | (last ? 2u : 0u) | ((uint32_t)count << 2);
-                else if (l < L && (lf & SDR_LISTENER_RESET) && c0 == 0) *dst = 0;
-            }
-        }
-        __syncthreads();
     }
-    __syncthreads();
     {
         uint32_t *dst = reinterpret_cast<uint32_t *>(a.rolling + w.stream);
         const uint32_t *src = reinterpret_cast<const uint32_t *>(&s_roll);
         for (int i = tid; i < (int)(sizeof(RollingState) / 4); i += K2_THREADS) dst[i] = src[i];
     }
+}
 
-    // flushes of this work (rx/receiver.go:409-425)
-    for (int f = 0; f < w.n_flushes; f++) {
-        const int fb = w.first_flush_block + f * SDR_CUMULATION_SIZE;  // block that closed the window
-        const int slot = w.flush_out + f;
-        if (tid == 0) a.flush_block[slot] = w.block_out + fb;
-        if (w.do_peaks) {
-            const float thr = a.thresholds[(size_t)(w.block_out + fb) * 4 + 2];
-            find_peaks_block(a.flush_cum + (size_t)slot * a.n, a.n, (float)SDR_CUMULATION_SIZE, thr,
-                             a.flush_peaks + (size_t)slot * a.max_peaks, a.max_peaks, &a.flush_n_peaks[slot], s_scan);
-        } else if (tid == 0) {
-            a.flush_n_peaks[slot] = 0;
+constexpr int K2_KEY_ROWS = 64;  // blocks per CTA of the key kernel
+
+// Key states (cw/spectral.go:48-54): state := value > threshold, the listener's BoolDebouncer (dsp/dsp.go:164-182), one
+// warp ballot packs 32 listener positions of a block into a word.  grid = (ceil(max blocks of a work / 64), works).
+// Pass-through debouncers (threshold < 2, the reference's default) are stateless: every (block, 32 listeners) word is
+// independent.  A real debouncer is sequential per listener: CTA 0 of the work walks all its blocks in order, a warp
+// per 32 positions, the state carried per (stream, position) across submits.
+__global__ void __launch_bounds__(K2_THREADS) k2_keys_kernel(const K2Args a) {
+    const PostWork w = a.works[blockIdx.y];
+    const int tid = threadIdx.x, wq = tid >> 5, lane = tid & 31;
+    constexpr int NWQ = K2_THREADS / 32;
+    const int L = w.n_listeners;
+    const float *__restrict__ taps = a.taps + (size_t)w.block_out * a.tap_stride;
+    const float *__restrict__ thr = a.thresholds + (size_t)w.block_out * 4 + 3;  // listen threshold of block i at thr[4 i]
+    uint8_t *__restrict__ keys = a.keys ? a.keys + (size_t)w.block_out * a.tap_stride : nullptr;
+    uint32_t *__restrict__ kbits = a.key_bits + (size_t)w.block_out * a.key_words;
+    if (w.debounce < 2) {
+        const int row0 = blockIdx.x * K2_KEY_ROWS;
+        const int row1 = min(row0 + K2_KEY_ROWS, w.n_blocks);
+        for (int lg = 0; lg < a.key_words; lg++) {
+            const int l = lg * 32 + lane;
+            const bool active = l < L && (w.lflags_off < 0 || (a.lflags[w.lflags_off + l] & SDR_LISTENER_ACTIVE));
+            for (int i0 = row0 + wq; i0 < row1; i0 += 4 * NWQ) {  // four rows of this warp in flight
+                float v[4], t[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i = i0 + u * NWQ;
+                    v[u] = (active && i < row1) ? taps[(size_t)i * a.tap_stride + l] : 0.f;
+                    t[u] = (i < row1) ? thr[(size_t)i * 4] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i = i0 + u * NWQ;
+                    if (i < row1) {  // uniform across the warp
+                        const bool raw = active && v[u] > t[u];
+                        if (keys && l < L) keys[(size_t)i * a.tap_stride + l] = raw ? 1 : 0;
+                        const uint32_t word = __ballot_sync(0xffffffffu, raw);
+                        if (lane == 0) kbits[(size_t)i * a.key_words + lg] = word;
+                    }
+                }
+            }
         }
+        return;
     }
+    if (blockIdx.x != 0) return;
+    for (int lg = wq; lg < a.key_words; lg += NWQ) {
+        const int l = lg * 32 + lane;
+        const uint8_t lf = (l < L) ? (w.lflags_off >= 0 ? a.lflags[w.lflags_off + l] : (uint8_t)SDR_LISTENER_ACTIVE) : (uint8_t)0;
+        const bool active = (lf & SDR_LISTENER_ACTIVE) != 0;
+        DebounceState *dst = a.deb + (size_t)w.stream * a.tap_stride + l;
+        DebounceState st = 0;
+        if (l < L && !(lf & SDR_LISTENER_RESET)) st = *dst;
+        bool eff = (st & 1u) != 0, last = (st & 2u) != 0;
+        int count = (int)(st >> 2);
+        for (int i0 = 0; i0 < w.n_blocks; i0 += 8) {
+            float v[8], t[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                v[u] = (active && i0 + u < w.n_blocks) ? taps[(size_t)(i0 + u) * a.tap_stride + l] : 0.f;
+                t[u] = (i0 + u < w.n_blocks) ? thr[(size_t)(i0 + u) * 4] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = i0 + u;
+                if (i < w.n_blocks) {  // uniform across the warp
+                    const bool raw = active && v[u] > t[u];
+                    if (keys && l < L) keys[(size_t)i * a.tap_stride + l] = raw ? 1 : 0;
+                    bool out = false;
+                    if (active) {
+                        count = (raw != last) ? 1 : count + 1;
+                        last = raw;
+                        if (count >= w.debounce) eff = raw;
+                        out = eff;
+                    }
+                    const uint32_t word = __ballot_sync(0xffffffffu, out);
+                    if (lane == 0) kbits[(size_t)i * a.key_words + lg] = word;
+                }
+            }
+        }
+        if (l < L && (active || (lf & SDR_LISTENER_RESET))) *dst = (eff ? 1u : 0u) | (last ? 2u : 0u) | ((uint32_t)count << 2);
+    }
+}
+
+// dsp.FindPeaks (dsp/fft.go:254-285) on every flushed cumulation vector: one CTA per flush
+__global__ void __launch_bounds__(K2_THREADS) k2_peaks_kernel(const K2Args a) {
+    __shared__ int s_scan[K2_THREADS];
+    const int slot = blockIdx.x;
+    const float thr = a.thresholds[(size_t)a.flush_block[slot] * 4 + 2];
+    find_peaks_block(a.flush_cum + (size_t)slot * a.n, a.n, (float)SDR_CUMULATION_SIZE, thr, a.flush_peaks + (size_t)slot * a.max_peaks,
+                     a.max_peaks, &a.flush_n_peaks[slot], s_scan);
 }
 
 // ---- stand-alone kernels behind the dsp-signature-compatible calls --------------------------

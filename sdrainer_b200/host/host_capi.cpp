@@ -257,9 +257,9 @@ void *sdrh_rt_new(void *engine, int fs, int n, int listeners, int s_cap, int blo
 }
 void sdrh_rt_free(void *p) { delete (rt::Harness *)p; }
 // out[0..8] = batch_s, copy_s, submit_s, collect_wait_s, decode_s, gpu_ms, ticks, chars, key_downs
-int sdrh_rt_run(void *p, int n_streams, int n_batches, double *out) {
+int sdrh_rt_run(void *p, int n_streams, int n_batches, int ring_copy, double *out) {
     try {
-        const rt::Stats st = ((rt::Harness *)p)->Run(n_streams, n_batches);
+        const rt::Stats st = ((rt::Harness *)p)->Run(n_streams, n_batches, ring_copy != 0);
         out[0] = st.batch_s;
         out[1] = st.copy_s;
         out[2] = st.submit_s;

@@ -126,7 +126,9 @@ class Harness {
     }
 
     // n_batches batches of S streams; the first two fill the pipeline and are not timed
-    Stats Run(int S, int n_batches) {
+    // ring_copy = false: the frames are produced directly in the pinned ring (a client that receives into C-owned pinned
+    // memory, the zero-copy variant INTEGRATION.md describes): the ring is filled by the two untimed batches only
+    Stats Run(int S, int n_batches, bool ring_copy = true) {
         using clk = std::chrono::steady_clock;
         auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
         if (S > cap_) S = cap_;
@@ -142,7 +144,7 @@ class Harness {
             if (k == 2) t_start = clk::now();
             if (k == n_batches) t_end = clk::now();
             auto t0 = clk::now();
-            if (k < n_batches) {
+            if (k < n_batches && (ring_copy || k < 2)) {
                 // 1. ring copy (parallel over streams): frames of template s % nt, blocks (k B + b) % src_blocks
                 float *ring = ring_[slot];
                 pool_.parallel_for((size_t)S, [&](size_t lo, size_t hi) {

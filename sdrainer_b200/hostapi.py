@@ -52,7 +52,7 @@ def lib():
         "sdrh_dispatcher_new": (vp, [vp, i, i]), "sdrh_dispatcher_free": (None, [vp]), "sdrh_dispatcher_add": (i, [vp, vp]),
         "sdrh_dispatcher_tick": (i, [vp]), "sdrh_dispatcher_submits": (i, [vp]), "sdrh_dispatcher_error": (cp, [vp]),
         "sdrh_rt_new": (vp, [vp, i, i, i, i, i, i, i, C.POINTER(C.c_float), i, i, C.POINTER(C.c_int)]),
-        "sdrh_rt_free": (None, [vp]), "sdrh_rt_run": (i, [vp, i, i, C.POINTER(d)]),
+        "sdrh_rt_free": (None, [vp]), "sdrh_rt_run": (i, [vp, i, i, i, C.POINTER(d)]),
         "sdrh_audio_new": (vp, [d, i]), "sdrh_audio_free": (None, [vp]), "sdrh_audio_blocksize": (i, [vp]),
         "sdrh_audio_set_scale": (None, [vp, d]), "sdrh_audio_write": (i, [vp, C.POINTER(C.c_float), i]),
         "sdrh_audio_close": (None, [vp]), "sdrh_audio_text": (cp, [vp]),
@@ -231,9 +231,9 @@ class RealtimeHarness:
         if not self.h:
             raise RuntimeError("realtime harness: allocation failed")
 
-    def run(self, n_streams, n_batches):
+    def run(self, n_streams, n_batches, ring_copy=True):
         out = (C.c_double * 9)()
-        if self.L.sdrh_rt_run(self.h, n_streams, n_batches, out) != 0:
+        if self.L.sdrh_rt_run(self.h, n_streams, n_batches, 1 if ring_copy else 0, out) != 0:
             raise RuntimeError("realtime harness: run failed")
         return dict(zip(self.FIELDS, [float(x) for x in out]))
 
