@@ -55,7 +55,7 @@ def build_host(force: bool = False) -> str:
     build(force=False)
     stale = (not os.path.exists(HOST_LIB)) or any(os.path.getmtime(d) > os.path.getmtime(HOST_LIB) for d in HOST_SOURCES + [LIB])
     if force or stale:
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-o", HOST_LIB,
+        subprocess.check_call(["g++", "-O2", "-mavx2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-o", HOST_LIB,
                                HOST_SOURCES[0], "-L" + HERE, "-lsdrgpu", "-lpthread", "-Wl,-rpath,$ORIGIN"])
     return HOST_LIB
 

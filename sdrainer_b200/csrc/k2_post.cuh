@@ -77,6 +77,19 @@ __device__ __forceinline__ float psd_value_in_db_shifted(float psd_value, double
 constexpr int K2_THREADS = 128;
 constexpr int K2_CHUNK = 1024;  // blocks staged in shared memory per sequential pass
 
+// The smallest float32 x with fl(x / c) > thr (c > 0).  fl(x / c) is non-decreasing in x, so `value > threshold` of
+// dsp.FindPeaks (dsp/fft.go:259-260, value := v / T(cumulationSize)) is exactly `cum >= cut` and, for a non-NaN bin,
+// `value <= threshold` is exactly `cum < cut`: the scan over the bins needs no division.  NaN when no x qualifies
+// (threshold NaN or +Inf): every comparison with it is false, as the reference's are.
+__device__ float find_peaks_cut(float thr, float c) {
+    if (isnan(thr) || thr == __int_as_float(0x7f800000)) return __int_as_float(0x7fc00000);
+    float x = __fmul_rn(thr, c);
+    if (isnan(x)) x = 0.f;  // -Inf * c stays -Inf, so only 0 * Inf style cases land here
+    for (int it = 0; it < 4096 && __fdiv_rn(x, c) > thr; it++) x = nextafterf(x, -INFINITY);  // now fl(x / c) <= thr (or x = -Inf)
+    for (int it = 0; it < 4096 && !(__fdiv_rn(x, c) > thr); it++) x = nextafterf(x, INFINITY);
+    return x;
+}
+
 // dsp.FindPeaks on one vector `cum` of n bins; all K2_THREADS threads of the CTA participate.
 __device__ void find_peaks_block(const float *__restrict__ cum, int n, float cumulation_size, float thr,
                                  sdr_peak *__restrict__ out, int max_peaks, int *__restrict__ n_out, int *s_scan) {
@@ -84,27 +97,31 @@ __device__ void find_peaks_block(const float *__restrict__ cum, int n, float cum
     const int per = (n + K2_THREADS - 1) / K2_THREADS;
     const int lo = tid * per, hi = min(n, lo + per);
     auto val = [&](int i) { return __fdiv_rn(cum[i], cumulation_size); };  // v / T(cumulationSize)
+    if (tid == 0) s_scan[0] = __float_as_int(find_peaks_cut(thr, cumulation_size));
+    __syncthreads();
+    const float cut = __int_as_float(s_scan[0]);
+    __syncthreads();
     // The Go loop is a two-state machine: a run opens at value > threshold while closed, and closes at the first
     // value <= threshold (a NaN neither opens nor closes a run).  Each thread replays it over its chunk; the
     // state at the chunk start is found by looking back (past NaNs) at the last decisive bin.
     bool open0 = false;
     for (int j = lo - 1; j >= 0 && lo < hi; j--) {
-        const float p = val(j);
-        if (p > thr) {
+        const float p = cum[j];
+        if (p >= cut) {
             open0 = true;
             break;
         }
-        if (p <= thr) break;
+        if (p < cut) break;
     }
     int count = 0;
     {
         bool open = open0;
         for (int i = lo; i < hi; i++) {
-            const float v = val(i);
-            if (!open && v > thr) {
+            const float v = cum[i];
+            if (!open && v >= cut) {
                 count++;
                 open = true;
-            } else if (open && v <= thr) {
+            } else if (open && v < cut) {
                 open = false;
             }
         }
@@ -123,19 +140,19 @@ __device__ void find_peaks_block(const float *__restrict__ cum, int n, float cum
     if (count > 0) {
         bool open = open0;
         for (int i = lo; i < hi; i++) {
-            const float v0 = val(i);
+            const float c0 = cum[i];
             if (open) {
-                if (v0 <= thr) open = false;
+                if (c0 < cut) open = false;
                 continue;
             }
-            if (!(v0 > thr)) continue;
+            if (!(c0 >= cut)) continue;
             open = true;
             int bin = i;
-            float best = v0;
+            float best = val(i);
             int j = i + 1;
             while (j < n) {  // the run may extend past this thread's chunk
+                if (cum[j] < cut) break;
                 const float v = val(j);
-                if (v <= thr) break;
                 if (best < v) {  // strict: the first maximum wins
                     best = v;
                     bin = j;
