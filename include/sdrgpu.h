@@ -177,9 +177,9 @@ int sdr_ticket_device_ptrs(sdr_engine *e, sdr_ticket t, void **psd_noise_floor, 
                            void **thresholds, void **taps, void **keys);
 /* kernels launched by this engine since creation (bench.py's gpu_launches) */
 int64_t sdr_engine_launch_count(const sdr_engine *e);
-/* The post kernel (thresholds, keys, peaks) of a batch runs on an engine-internal stream so that it overlaps the next
- * batch's spectral kernel.  A caller that supplied cfg.cuda_stream and wants "everything submitted so far" ordered
- * before later work on that stream (e.g. a timing event) calls this: the stream waits for the last post kernel. */
+/* The post kernels (thresholds, keys, peaks) of a batch may run on an engine-internal stream (SDR_K2_OVERLAP=1).  A
+ * caller that supplied cfg.cuda_stream and wants "everything submitted so far" ordered before later work on that
+ * stream (e.g. a timing event) calls this: the stream waits for the last post kernel.  No-op otherwise. */
 int sdr_engine_fence(sdr_engine *e);
 /* name of the spectral kernel the most recent sdr_submit launched (which one serves a block size / batch shape is the
  * engine's choice: DESIGN.md section 4); for benchmarks and logs */

@@ -19,8 +19,11 @@
 
 #include <mutex>
 #include <new>
+#include <optional>
 #include <string>
 #include <vector>
+
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges cost nothing unless a profiler injects itself
 
 #include "../../include/sdrgpu.h"
 #include "k1_spectral.cuh"
@@ -34,6 +37,11 @@
 using namespace sdr;
 
 namespace {
+
+struct NvtxRange {  // sdr_submit / K1 / K2 / D2H show up as named ranges in Nsight Systems and ncu --nvtx
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 std::string g_create_error;
 
@@ -106,9 +114,9 @@ struct sdr_engine {
     // slot's descriptor block is only rewritten after its ticket was released, so the copy of batch i+1 overlaps the
     // kernels of batch i instead of sitting between them on the compute stream
     cudaStream_t s_desc = nullptr;
-    // K2 (thresholds, keys, peaks) runs on its own stream behind an event: batch i's K2 overlaps batch i+1's K1 (K2 is
-    // 6 % of a step and latency/ALU-bound; K1 never reads what K2 writes).  K2s stay ordered among themselves, which
-    // keeps the per-stream rolling means sequential.  SDR_K2_OVERLAP=0 puts K2 back on the compute stream.
+    // K2 (thresholds, keys, peaks) can run on its own stream behind an event so that batch i's K2 overlaps batch i+1's K1
+    // (K1 never reads what K2 writes; K2s stay ordered among themselves, which keeps the per-stream rolling means
+    // sequential).  Opt-in with SDR_K2_OVERLAP=1: see the measurement at the stream's creation.
     cudaStream_t s_post = nullptr;
     bool own_post = false;
     cudaEvent_t ev_post = nullptr;  // last K2 (sdr_engine_fence)
@@ -903,8 +911,11 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
     CKC(cudaStreamCreateWithFlags(&e->s_desc, cudaStreamNonBlocking));
     CKC(cudaEventCreateWithFlags(&e->ev_post, cudaEventDisableTiming));
     {
+        // Measured on B200 (tools/bench_configs.py, 100 steps): K1 fills every SM's registers, so a K2 on a second stream
+        // only runs when a K1 drains -- 0.827 ms per step against 0.825 ms with K2 behind K1 on the compute stream.  The
+        // second stream stays available (SDR_K2_OVERLAP=1) for engines whose K1 leaves room.
         const char *v = getenv("SDR_K2_OVERLAP");
-        if (!(v && v[0] == '0')) {
+        if (v && v[0] == '1') {
             // K1 fills every SM (registers and shared memory), so K2's CTAs run when a K1 drains: with the higher
             // priority they go first and the batch's results reach the D2H stream as early as possible, while the next
             // K1's CTAs fill in behind them (SDR_K2_PRIO=low: the other order; measured within 0.5 % of each other)
@@ -1181,6 +1192,7 @@ int sdr_engine_fence(sdr_engine *e) {
 int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr_ticket *out) {
     if (!e || !works || !out || n_works < 1) return SDR_EINVAL;
     std::lock_guard<std::mutex> lk(e->mu);
+    NvtxRange nvtx_submit("sdr_submit");
     if (n_works > e->cfg.max_streams) {
         e->err = "more works than max_streams";
         return SDR_EINVAL;
@@ -1425,6 +1437,8 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     a1.dbg_psd = s.d_psd;
     CK(e, cudaEventRecord(s.ev_k0, e->s_compute));
     int k1_launches = 1;
+    std::optional<NvtxRange> nvtx_k1;
+    nvtx_k1.emplace("K1 spectral (FFT, |X|^2, dB, noise floor, taps, cumulation)");
     if (!e->large) {
         CK(e, launch_k1(e, a1, dbg, e->s_compute, i16, warp_ok));
         e->last_kernel = (e->k1_mid && e->N == 4096 && !i16) ? "k1_mid_kernel<16>" : (e->k1_warp && warp_ok) ? "k1_warp_kernel"
@@ -1476,6 +1490,8 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
         k1_launches++;
     }
     CK(e, cudaEventRecord(s.ev_km, e->s_compute));
+    nvtx_k1.reset();
+    NvtxRange nvtx_k2("K2 post (thresholds, keys, peaks) + D2H");
     K2Args a2;
     a2.works = reinterpret_cast<const PostWork *>(s.d_desc + dl.post);
     a2.rolling = e->d_rolling;

@@ -116,14 +116,31 @@ __device__ void find_peaks_block(const float *__restrict__ cum, int n, float cum
     int count = 0;
     {
         bool open = open0;
-        for (int i = lo; i < hi; i++) {
-            const float v = cum[i];
+        auto step = [&](float v) {
             if (!open && v >= cut) {
                 count++;
                 open = true;
             } else if (open && v < cut) {
                 open = false;
             }
+        };
+        if ((per & 3) == 0 && hi - lo == per) {  // whole chunk, 16-byte aligned: four bins per load, loads issued ahead
+            const float4 *c4 = reinterpret_cast<const float4 *>(cum + lo);
+            for (int i0 = 0; i0 < per / 4; i0 += 4) {
+                float4 q[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) q[u] = (i0 + u < per / 4) ? c4[i0 + u] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (i0 + u < per / 4) {
+                        step(q[u].x);
+                        step(q[u].y);
+                        step(q[u].z);
+                        step(q[u].w);
+                    }
+            }
+        } else {
+            for (int i = lo; i < hi; i++) step(cum[i]);
         }
     }
     // block-wide exclusive scan of `count`
@@ -274,28 +291,28 @@ __global__ void __launch_bounds__(K2_THREADS) k2_keys_kernel(const K2Args a) {
     uint8_t *__restrict__ keys = a.keys ? a.keys + (size_t)w.block_out * a.tap_stride : nullptr;
     uint32_t *__restrict__ kbits = a.key_bits + (size_t)w.block_out * a.key_words;
     if (w.debounce < 2) {
-        const int row0 = blockIdx.x * K2_KEY_ROWS;
-        const int row1 = min(row0 + K2_KEY_ROWS, w.n_blocks);
+        // the kernel is pure latency (one tap row per listener group and block): every warp keeps all sixteen rows it owns
+        // in flight at once
+        constexpr int RPW = K2_KEY_ROWS / NWQ;  // rows per warp
+        const int row0 = blockIdx.x * K2_KEY_ROWS + wq * RPW;
+        const int nrow = min(RPW, w.n_blocks - row0);
+        if (nrow <= 0) return;
+        float t[RPW];
+#pragma unroll
+        for (int u = 0; u < RPW; u++) t[u] = (u < nrow) ? thr[(size_t)(row0 + u) * 4] : 0.f;
         for (int lg = 0; lg < a.key_words; lg++) {
             const int l = lg * 32 + lane;
             const bool active = l < L && (w.lflags_off < 0 || (a.lflags[w.lflags_off + l] & SDR_LISTENER_ACTIVE));
-            for (int i0 = row0 + wq; i0 < row1; i0 += 4 * NWQ) {  // four rows of this warp in flight
-                float v[4], t[4];
+            float v[RPW];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int i = i0 + u * NWQ;
-                    v[u] = (active && i < row1) ? taps[(size_t)i * a.tap_stride + l] : 0.f;
-                    t[u] = (i < row1) ? thr[(size_t)i * 4] : 0.f;
-                }
+            for (int u = 0; u < RPW; u++) v[u] = (active && u < nrow) ? taps[(size_t)(row0 + u) * a.tap_stride + l] : 0.f;
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int i = i0 + u * NWQ;
-                    if (i < row1) {  // uniform across the warp
-                        const bool raw = active && v[u] > t[u];
-                        if (keys && l < L) keys[(size_t)i * a.tap_stride + l] = raw ? 1 : 0;
-                        const uint32_t word = __ballot_sync(0xffffffffu, raw);
-                        if (lane == 0) kbits[(size_t)i * a.key_words + lg] = word;
-                    }
+            for (int u = 0; u < RPW; u++) {
+                if (u < nrow) {  // uniform across the warp
+                    const bool raw = active && v[u] > t[u];
+                    if (keys && l < L) keys[(size_t)(row0 + u) * a.tap_stride + l] = raw ? 1 : 0;
+                    const uint32_t word = __ballot_sync(0xffffffffu, raw);
+                    if (lane == 0) kbits[(size_t)(row0 + u) * a.key_words + lg] = word;
                 }
             }
         }

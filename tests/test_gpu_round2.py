@@ -372,3 +372,18 @@ def test_receiver_with_device_debounce_matches_oracle(capi, oracle, host, deboun
         assert g["attach_block"] == r["attach_block"]
         assert np.array_equal(g["keys"], r["keys"])
         assert g["text"] == r["text"]
+
+
+@pytest.mark.parametrize("n", [16384, 32768])
+def test_stockham_block_sizes_against_the_oracle(capi, oracle, n):
+    """N = 16384 / 32768 (the shared-memory Stockham four-step kernels): noise floor, thresholds, taps, key states,
+    cumulation and peak list against the oracle -- the same checks the fused block sizes get"""
+    import test_gpu_parity as tp
+    fs = 48000 * n // 512
+    rng = np.random.default_rng(n)
+    tones = synth.make_tones(rng, 24, n, 70, wpm_range=(18.0, 28.0))
+    spec = synth.StreamSpec(sample_rate=fs, block_size=n, n_blocks=130, seed=n + 1, tones=tones)
+    iq = synth.generate(spec)
+    bins = [t.bin for t in tones]
+    outs = tp._run_batch(capi, spec, iq, bins, chunks=[70, 60])
+    tp._compare_with_oracle(oracle, spec, iq, bins, outs)

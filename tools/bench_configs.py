@@ -41,8 +41,8 @@ CASES = [
     ("cfg5 24.576 MS/s N=65536 peak scan, 64 streams (r1 two-kernel path)", 65536, 24576000, 0, 64, 100, {"SDR_K1_WIDE": "0"}),
     ("cfg5 24.576 MS/s N=65536 peak scan, 8 streams", 65536, 24576000, 0, 8, 100),
     ("cfg5 24.576 MS/s N=65536 peak scan, 8 streams (r1 two-kernel path)", 65536, 24576000, 0, 8, 100, {"SDR_K1_WIDE": "0"}),
-    ("k2 cfg2 N=2048 L=50, K2 on the compute stream (r1)", 2048, 192000, 50, 148 * 12, 100, {"SDR_K2_OVERLAP": "0"}),
-    ("k2 cfg2 N=2048 L=50, K2 overlapped, low priority", 2048, 192000, 50, 148 * 12, 100, {"SDR_K2_PRIO": "low"}),
+    ("k2 cfg2 N=2048 L=50, K2 on a second stream, high priority", 2048, 192000, 50, 148 * 12, 100, {"SDR_K2_OVERLAP": "1"}),
+    ("k2 cfg2 N=2048 L=50, K2 on a second stream, low priority", 2048, 192000, 50, 148 * 12, 100, {"SDR_K2_OVERLAP": "1", "SDR_K2_PRIO": "low"}),
 ]
 
 
