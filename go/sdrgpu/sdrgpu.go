@@ -21,7 +21,8 @@ import (
 	"unsafe"
 )
 
-// Engine owns one GPU engine; like rx.Receiver.run it must be used from one goroutine.
+// Engine owns one GPU engine.  The C ABI serialises concurrent callers internally, so several receiver goroutines may
+// share one Engine; a stream and a ticket still have one owner at a time (like rx.Receiver.run owns its state).
 type Engine struct {
 	h         *C.sdr_engine
 	blockSize int
@@ -83,7 +84,23 @@ type Work struct {
 	EdgeWidth     int
 	PeakThreshold float32
 	ListenerBins  []int32
+	// SignalDebounce is SpectralDemodulator.SetSignalDebounce (cw/spectral.go:33-35); the BoolDebouncer of every listener
+	// position runs on the device and Result.Key returns the debounced state.  0 or 1 = pass-through.
+	SignalDebounce int
+	// ListenerFlags (optional, one per bin): FlagActive for a position with an attached listener, | FlagReset when a new
+	// listener was bound to the position since the previous submit.  nil = all active, none reset.  Keep a listener at
+	// the same position (its pool slot) for as long as it is bound.
+	ListenerFlags []uint8
 }
+
+const (
+	FlagActive = uint8(C.SDR_LISTENER_ACTIVE)
+	FlagReset  = uint8(C.SDR_LISTENER_RESET)
+	// submit flags
+	NoTaps    = int(C.SDR_NO_TAPS)
+	NoRawKeys = int(C.SDR_NO_RAW_KEYS)
+	NoPeaks   = int(C.SDR_NO_PEAKS)
+)
 
 type Ticket int64
 
@@ -110,6 +127,13 @@ func (e *Engine) Submit(works []Work, flags int) (Ticket, error) {
 			pins = append(pins, p)
 			copy(unsafe.Slice((*int32)(p), len(w.ListenerBins)), w.ListenerBins)
 			cw[i].listener_bins = (*C.int)(p)
+		}
+		cw[i].signal_debounce = C.int(w.SignalDebounce)
+		if len(w.ListenerFlags) == len(w.ListenerBins) && len(w.ListenerFlags) > 0 {
+			p := C.malloc(C.size_t(len(w.ListenerFlags)))
+			pins = append(pins, p)
+			copy(unsafe.Slice((*uint8)(p), len(w.ListenerFlags)), w.ListenerFlags)
+			cw[i].listener_flags = (*C.uint8_t)(p)
 		}
 	}
 	var t C.sdr_ticket
@@ -146,6 +170,25 @@ func (r *Result) Tap(b, l int) float32 {
 	return unsafe.Slice((*float32)(unsafe.Pointer(r.r.taps)), s*int(r.r.n_blocks))[b*s+l]
 }
 
+// Key is the debounced key state of listener position l in block b (cw/spectral.go:48-50): what cw.Decoder.Tick takes.
+func (r *Result) Key(b, l int) bool {
+	kw := int(r.r.key_words)
+	words := unsafe.Slice((*uint32)(unsafe.Pointer(r.r.key_bits)), kw*int(r.r.n_blocks))
+	return (words[b*kw+l/32]>>(uint(l)%32))&1 != 0
+}
+
+// WorkBlocks returns the block range [from, to) of work w inside this result (several receivers per submit).
+func (r *Result) WorkBlocks(w int) (int, int) {
+	off := unsafe.Slice((*C.int)(unsafe.Pointer(r.r.work_block_offset)), int(r.r.n_works)+1)
+	return int(off[w]), int(off[w+1])
+}
+
+// WorkFlushes returns the flush range [from, to) of work w.
+func (r *Result) WorkFlushes(w int) (int, int) {
+	off := unsafe.Slice((*C.int)(unsafe.Pointer(r.r.work_flush_offset)), int(r.r.n_works)+1)
+	return int(off[w]), int(off[w+1])
+}
+
 // Peaks returns the dsp.FindPeaks list of flush f (bin order).
 func (r *Result) Peaks(f int) []C.sdr_peak {
 	mp := int(r.r.max_peaks_per_flush)
@@ -155,4 +198,70 @@ func (r *Result) Peaks(f int) []C.sdr_peak {
 	}
 	all := unsafe.Slice((*C.sdr_peak)(unsafe.Pointer(r.r.flush_peaks)), mp*int(r.r.n_flushes))
 	return all[f*mp : f*mp+n]
+}
+
+// Source is what the dispatcher needs from a receiver: rx.Receiver implements it with the frames queued in r.in
+// (rx/receiver.go:315-334) and the loop body of run() after the FFT (rx/receiver.go:383-461).
+type Source interface {
+	// Stage copies the queued frames -- at most up to the next flush, listeners change there -- into dst (pinned
+	// memory) and describes them; it returns false when nothing is queued.
+	Stage(dst []float32) (Work, bool)
+	// Consume handles the receiver's slice of a result: work index w of res.
+	Consume(res *Result, w int)
+}
+
+// Dispatcher drains the queues of many receivers into ONE Submit per tick: one H2D copy (the works are staged back to
+// back in one pinned arena), one spectral launch over every stream, one result.  It is the Go counterpart of
+// rx::Dispatcher in sdrainer_b200/host/sdrhost.hpp (tested there against 64 oracle receivers).
+type Dispatcher struct {
+	eng     *Engine
+	arena   []float32
+	sources []Source
+}
+
+func NewDispatcher(eng *Engine, maxReceivers int) (*Dispatcher, error) {
+	arena, err := eng.PinnedFloats(maxReceivers * 100 * 2 * eng.blockSize)
+	if err != nil {
+		return nil, err
+	}
+	return &Dispatcher{eng: eng, arena: arena}, nil
+}
+
+func (d *Dispatcher) Add(s Source) { d.sources = append(d.sources, s) }
+
+// Tick processes everything queued; it returns the number of Submit calls it made.
+func (d *Dispatcher) Tick() (int, error) {
+	submits := 0
+	for {
+		works := make([]Work, 0, len(d.sources))
+		owners := make([]Source, 0, len(d.sources))
+		off := 0
+		for _, s := range d.sources {
+			w, ok := s.Stage(d.arena[off:])
+			if !ok {
+				continue
+			}
+			off += len(w.IQ)
+			works = append(works, w)
+			owners = append(owners, s)
+		}
+		if len(works) == 0 {
+			return submits, nil
+		}
+		t, err := d.eng.Submit(works, NoTaps|NoRawKeys)
+		if err != nil {
+			return submits, err
+		}
+		submits++
+		res, err := d.eng.Collect(t)
+		if err != nil {
+			return submits, err
+		}
+		for i, s := range owners {
+			s.Consume(res, i)
+		}
+		if err := d.eng.Release(t); err != nil {
+			return submits, err
+		}
+	}
 }

@@ -93,10 +93,10 @@ def _compare_with_oracle(oracle, spec, iq, bins, outs, edge=70, peak_thr=15.0):
     keys = _concat(outs, "keys")[:, :len(bins)]
     # (iv) noise-floor scalars.  The window choice is a decision: same window => tiny relative error
     pu.check_scalars(floor, r.noise[:, 0], what="psdNoiseFloor")
-    pu.check_scalars(var, r.noise[:, 1], rel=2e-3, what="noise variance")
+    pu.check_scalars(var, r.noise[:, 1], what="noise variance")  # <= 4e-5 measured (profiles/r2_error_table.md)
     # thresholds are dB values around 20..50: compare absolutely
-    assert np.abs(thr[:, :3] - r.thresholds).max() < 2e-3
-    assert np.abs(thr[:, 3] - (r.thresholds[:, 0] + r.thresholds[:, 1])).max() < 2e-3
+    assert np.abs(thr[:, :3] - r.thresholds).max() < 1e-4  # <= 1.1e-5 dB measured (profiles/r2_error_table.md)
+    assert np.abs(thr[:, 3] - (r.thresholds[:, 0] + r.thresholds[:, 1])).max() < 1e-4
     # taps on keyed-down blocks are noise bins (fp32 error scales with block energy): compare in PSD domain
     lin_g, lin_r = 10 ** (taps.astype(np.float64) / 10), 10 ** (r.taps.astype(np.float64) / 10)
     blockmax = lin_r.max(axis=1, keepdims=True)
@@ -180,7 +180,7 @@ def test_multi_stream_batch_equals_individual(capi, oracle):
         b0, b1 = res.work_block_offset[i], res.work_block_offset[i + 1]
         r = oracle.process_stream(iqs[i], n, edge_width=edges[i], listener_bins=binss[i], sample_rate=192000)
         pu.check_scalars(res.psd_noise_floor[b0:b1], r.noise[:, 0], what=f"stream {i} floor")
-        assert np.abs(res.thresholds[b0:b1, :3] - r.thresholds).max() < 2e-3
+        assert np.abs(res.thresholds[b0:b1, :3] - r.thresholds).max() < 1e-4
         pu.check_keys(res.keys[b0:b1, :len(binss[i])], r.taps, r.thresholds[:, 0] + r.thresholds[:, 1])
         f0, f1 = res.work_flush_offset[i], res.work_flush_offset[i + 1]
         assert f1 - f0 == r.n_flush
@@ -296,7 +296,7 @@ def test_committed_golden_vectors_without_the_oracle(capi):
         bins = [int(b) for b in g[tag + "_bins"]]
         out = _run_batch(capi, spec, iq, bins)[0]
         pu.check_scalars(out.psd_noise_floor, g[tag + "_noise"][:, 0], what="floor")
-        assert np.abs(out.thresholds[:, :3] - g[tag + "_thresholds"]).max() < 2e-3
+        assert np.abs(out.thresholds[:, :3] - g[tag + "_thresholds"]).max() < 1e-4
         ref_taps = g[tag + "_taps"]
         ref_listen = g[tag + "_thresholds"][:, 0] + g[tag + "_thresholds"][:, 1]
         pu.check_keys(out.keys[:, :len(bins)], ref_taps, ref_listen)
@@ -352,7 +352,7 @@ def test_cfg3_shape_8192_with_200_listeners(capi, oracle):
     thr = _concat(outs, "thresholds")
     keys = _concat(outs, "keys")[:, :len(bins)]
     pu.check_scalars(floor, r.noise[:, 0], what="psdNoiseFloor")
-    assert np.abs(thr[:, :3] - r.thresholds).max() < 2e-3
+    assert np.abs(thr[:, :3] - r.thresholds).max() < 1e-4
     pu.check_keys(keys, r.taps, r.thresholds[:, 0] + r.thresholds[:, 1])
     gp = [pu.peak_keys(o.peaks(f)) for o in outs for f in range(o.n_flushes)]
     assert len(gp) == r.n_flush == 2
@@ -458,7 +458,7 @@ def test_large_block_ragged_multi_stream_bit_identical_and_oracle(capi, oracle, 
             assert a.shape == b.shape and np.array_equal(a, b, equal_nan=True), (i, name)
         r = oracle.process_stream(iqs[i], n, edge_width=70, peak_threshold=15.0, listener_bins=binss[i], sample_rate=fs)
         pu.check_scalars(per_stream(one, i, "psd_noise_floor"), r.noise[:, 0], what="psdNoiseFloor")
-        pu.check_scalars(per_stream(one, i, "noise_variance"), r.noise[:, 1], rel=2e-3, what="noise variance")
+        pu.check_scalars(per_stream(one, i, "noise_variance"), r.noise[:, 1], what="noise variance")
         keys = per_stream(one, i, "keys")[:, :len(binss[i])]
         pu.check_keys(keys, r.taps, r.thresholds[:, 0] + r.thresholds[:, 1])
         fc = per_stream(one, i, "flush_cum")

@@ -74,8 +74,10 @@ def main():
     O.lib()
     capi.lib()
     rows = [one(n) for n in (512, 1024, 2048, 4096, 8192, 16384, 32768, 65536)]
-    os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
-    with open(os.path.join(ROOT, "profiles", "r2_error_table.json"), "w") as f:
+    # under gpurun only gpurun_out/ travels back: write there when it exists, else straight into profiles/
+    out_dir = os.path.join(ROOT, "gpurun_out") if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else os.path.join(ROOT, "profiles")
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, "r2_error_table.json"), "w") as f:
         json.dump(rows, f, indent=1)
     lines = ["# fp32 GPU path vs float64 oracle, per block size and bin class (tools/error_table.py, measured on B200)", "",
              "Synthetic stream per size: Gaussian noise sigma 1e-4 + keyed tones (amplitude log-uniform 1e-3..3e-2), 104 blocks, edge 70.",
@@ -94,7 +96,7 @@ def main():
                      f"{r['psd_noise_floor_rel_max']:.1e} | {r['noise_variance_rel_max']:.1e} | {r['thresholds_db_abs_max']:.1e} | "
                      f"{r['flush_cum_abs_max']:.2e} / {'-' if loud is None else format(loud, '.1e')} | {r['key_flips']} ({r['key_flip_max_margin_db']:.1e}) | "
                      f"{'identical' if r['peak_list_identical'] else 'differs'} |")
-    with open(os.path.join(ROOT, "profiles", "r2_error_table.md"), "w") as f:
+    with open(os.path.join(out_dir, "r2_error_table.md"), "w") as f:
         f.write("\n".join(lines) + "\n")
     print("\n".join(lines))
 
