@@ -291,30 +291,53 @@ __global__ void __launch_bounds__(K2_THREADS) k2_keys_kernel(const K2Args a) {
     uint8_t *__restrict__ keys = a.keys ? a.keys + (size_t)w.block_out * a.tap_stride : nullptr;
     uint32_t *__restrict__ kbits = a.key_bits + (size_t)w.block_out * a.key_words;
     if (w.debounce < 2) {
-        // the kernel is pure latency (one tap row per listener group and block): every warp keeps all sixteen rows it owns
-        // in flight at once
-        constexpr int RPW = K2_KEY_ROWS / NWQ;  // rows per warp
-        const int row0 = blockIdx.x * K2_KEY_ROWS + wq * RPW;
-        const int nrow = min(RPW, w.n_blocks - row0);
+        // The CTA's 64 rows are one contiguous run of floats: every thread takes whole float4s (tap_stride is a multiple of
+        // four, so a float4 never straddles a row), all of them in flight at once, compares four listeners per load and
+        // writes their raw key bytes as one 32-bit store; the packed words are put together through shared memory.
+        __shared__ float s_thr[K2_KEY_ROWS];
+        __shared__ uint8_t s_act[256];                    // per listener: position active
+        __shared__ uint8_t s_nib[K2_KEY_ROWS][64 + 4];    // four key bits per float4 of a row
+        const int row0 = blockIdx.x * K2_KEY_ROWS;
+        const int nrow = min(K2_KEY_ROWS, w.n_blocks - row0);
         if (nrow <= 0) return;
-        float t[RPW];
+        const int q4 = a.tap_stride >> 2;
+        for (int i = tid; i < nrow; i += K2_THREADS) s_thr[i] = thr[(size_t)(row0 + i) * 4];
+        for (int l = tid; l < a.tap_stride; l += K2_THREADS)
+            s_act[l] = (l < L && (w.lflags_off < 0 || (a.lflags[w.lflags_off + l] & SDR_LISTENER_ACTIVE))) ? 1 : 0;
+        __syncthreads();
+        const float4 *t4 = reinterpret_cast<const float4 *>(taps + (size_t)row0 * a.tap_stride);
+        uchar4 *k4 = keys ? reinterpret_cast<uchar4 *>(keys + (size_t)row0 * a.tap_stride) : nullptr;
+        const int total = nrow * q4;
+        for (int e0 = tid; e0 < total; e0 += 8 * K2_THREADS) {
+            float4 v[8];
 #pragma unroll
-        for (int u = 0; u < RPW; u++) t[u] = (u < nrow) ? thr[(size_t)(row0 + u) * 4] : 0.f;
-        for (int lg = 0; lg < a.key_words; lg++) {
-            const int l = lg * 32 + lane;
-            const bool active = l < L && (w.lflags_off < 0 || (a.lflags[w.lflags_off + l] & SDR_LISTENER_ACTIVE));
-            float v[RPW];
+            for (int u = 0; u < 8; u++) {
+                const int e = e0 + u * K2_THREADS;
+                v[u] = e < total ? t4[e] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
-            for (int u = 0; u < RPW; u++) v[u] = (active && u < nrow) ? taps[(size_t)(row0 + u) * a.tap_stride + l] : 0.f;
-#pragma unroll
-            for (int u = 0; u < RPW; u++) {
-                if (u < nrow) {  // uniform across the warp
-                    const bool raw = active && v[u] > t[u];
-                    if (keys && l < L) keys[(size_t)(row0 + u) * a.tap_stride + l] = raw ? 1 : 0;
-                    const uint32_t word = __ballot_sync(0xffffffffu, raw);
-                    if (lane == 0) kbits[(size_t)(row0 + u) * a.key_words + lg] = word;
+            for (int u = 0; u < 8; u++) {
+                const int e = e0 + u * K2_THREADS;
+                if (e < total) {
+                    const int row = e / q4, c4 = e - row * q4, l = 4 * c4;
+                    const float t = s_thr[row];
+                    const unsigned b0 = (s_act[l] && v[u].x > t) ? 1u : 0u, b1 = (s_act[l + 1] && v[u].y > t) ? 1u : 0u;
+                    const unsigned b2 = (s_act[l + 2] && v[u].z > t) ? 1u : 0u, b3 = (s_act[l + 3] && v[u].w > t) ? 1u : 0u;
+                    if (k4) k4[e] = make_uchar4((unsigned char)b0, (unsigned char)b1, (unsigned char)b2, (unsigned char)b3);
+                    s_nib[row][c4] = (uint8_t)(b0 | (b1 << 1) | (b2 << 2) | (b3 << 3));
                 }
             }
+        }
+        __syncthreads();
+        for (int i = tid; i < nrow * a.key_words; i += K2_THREADS) {
+            const int row = i / a.key_words, lg = i - row * a.key_words;
+            uint32_t word = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int c4 = lg * 8 + j;
+                if (c4 < q4) word |= (uint32_t)s_nib[row][c4] << (4 * j);
+            }
+            kbits[(size_t)(row0 + row) * a.key_words + lg] = word;
         }
         return;
     }
