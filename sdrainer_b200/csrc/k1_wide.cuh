@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
                 v[n1] = __fmul2_rn(v[n1], make_float2(w, w));
             }
         }
-        compute_sync();  // the tile is in registers: A can take the outgoing tile; S is free (consume's tile reads are done)
+        compute_sync();  // the tile is in registers: A can take the outgoing tile; S is free (consume's plane reads are done)
         {
             HwTwiddle t;
             load_hw_twiddle(t);
@@ -389,7 +389,10 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
 #pragma unroll
             for (int p = 0; p < 16; p++) dst[(r0 + f) + N1 * ((hl + 16 * OutIdx<16>::of(p) + 128) & 255)] = cum[p];
         }
-        compute_sync();  // the |X|^2 / dB planes are read: S may be overwritten
+        // The planes must be read before the next transform's transposes overwrite S.  When a produce follows, its own
+        // barrier (after the column-tile reads, before the transform) already orders that, and the warps without
+        // window-sum work start reading the next column tile meanwhile; only a consume that follows directly needs one.
+        if (ip.nb == 0) compute_sync();
         ic.next(a.segs, a.n_segs, n_teams);
     }
 }
