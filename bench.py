@@ -258,7 +258,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.streams, note=f"CPU arm: each step is a bounded sample of {cores * per} streams of this workload"),
+        "config": workload_config(args.streams),
+        "note": f"CPU arm: each step is a bounded sample of {cores * per} streams of this workload (the metric is a rate)",
         "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -604,7 +605,8 @@ def run_realtime(args, capi, torch, iq, bins_all, local_rank, world, dist, devic
     from sdrainer_b200 import hostapi
     B = 10                                   # blocks per stream per batch: 106.7 ms of signal (<= 100 ms-class batches)
     signal_s = B * N / FS
-    cap = args.rt_cap if args.rt_cap else (32768 if world == 1 else 16384)
+    # per-GPU probe ceiling: 2 x cap x 160 KB of pinned ring per rank (10.7 GB at 32768)
+    cap = args.rt_cap if args.rt_cap else (32768 if world <= 2 else 24576 if world <= 4 else 20480)
     # host threads of this rank: the CPUs it is bound to (NUMA-local to the GPU), an equal share of the box at N > 1
     threads = max(2, min(len(os.sched_getaffinity(0)), (os.cpu_count() or 2) // world))
     nt = min(16, iq.shape[0])
