@@ -95,6 +95,7 @@ struct Slot {
     int n_works = 0, n_blocks = 0, n_flushes = 0, launches = 0;
     cudaEvent_t ev_desc = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_k0 = nullptr, ev_km = nullptr, ev_k2s = nullptr, ev_k1 = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_thr = nullptr, ev_peaks = nullptr;
 };
 
 }  // namespace
@@ -118,6 +119,7 @@ struct sdr_engine {
     // (K1 never reads what K2 writes; K2s stay ordered among themselves, which keeps the per-stream rolling means
     // sequential).  Opt-in with SDR_K2_OVERLAP=1: see the measurement at the stream's creation.
     cudaStream_t s_post = nullptr;
+    cudaStream_t s_aux = nullptr;  // k2_peaks runs here, next to k2_keys on the post stream (SDR_K2_AUX=0: back to back)
     bool own_post = false;
     cudaEvent_t ev_post = nullptr;  // last K2 (sdr_engine_fence)
     bool own_streams = true;
@@ -147,6 +149,7 @@ struct sdr_engine {
     // falls back to k1_mid_kernel<32> / the two-kernel path), =force takes it for every launch, whatever the segment count
     int k1_mid8k = 0;  // 0 off, 1 when the launch has enough segments, 2 always
     int k1m8_stages = 2;
+    bool k1m8_groups = true;  // two decoupled 256-thread groups (k1_mid8k2_kernel); SDR_K1_MID8K_GROUPS=0: one 512-thread group
     float *d_window = nullptr;
     float *d_cum_state = nullptr;
     RollingState *d_rolling = nullptr;
@@ -528,7 +531,15 @@ const void *k1m8_fn(bool dbg, bool win) {
 const void *k1m8_fn(int stages, bool dbg, bool win) { return stages == 1 ? k1m8_fn<1>(dbg, win) : k1m8_fn<2>(dbg, win); }
 int k1m8_smem(int stages) { return stages == 1 ? K1Mid8kGeom<1>::SMEM_BYTES : K1Mid8kGeom<2>::SMEM_BYTES; }
 
-cudaError_t launch_k1_mid8k(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st) {
+template <int NSTAGE>
+const void *k1m8g_fn(bool dbg, bool win) {
+    if (dbg) return win ? (const void *)k1_mid8k2_kernel<NSTAGE, true, true> : (const void *)k1_mid8k2_kernel<NSTAGE, true, false>;
+    return win ? (const void *)k1_mid8k2_kernel<NSTAGE, false, true> : (const void *)k1_mid8k2_kernel<NSTAGE, false, false>;
+}
+const void *k1m8g_fn(int stages, bool dbg, bool win) { return stages == 1 ? k1m8g_fn<1>(dbg, win) : k1m8g_fn<2>(dbg, win); }
+
+// nfb: per-block window-sum buffers of the slot (decoupled-group variant; the finish kernel follows)
+cudaError_t launch_k1_mid8k(const sdr_engine *e, const K1Args &a, const Mid8kNf &nfb, int n_blocks, bool dbg, cudaStream_t st, int *n_launches) {
     // one CTA per SM walks the segment list with stride grid: whole rounds, no straggler
     int grid = a.n_segs;
     if (grid > e->sm_count) {
@@ -538,8 +549,27 @@ cudaError_t launch_k1_mid8k(const sdr_engine *e, const K1Args &a, bool dbg, cuda
     if (grid < 1) grid = 1;
     K1Args args = a;
     const float2 *tws = e->d_tw_mid, *tw256 = e->d_tw256m;
-    void *params[] = {&args, &tws, &tw256};
-    return cudaLaunchKernel(k1m8_fn(e->k1m8_stages, dbg, a.window != nullptr), dim3(grid), dim3(512), params, k1m8_smem(e->k1m8_stages), st);
+    if (!e->k1m8_groups) {
+        void *params[] = {&args, &tws, &tw256};
+        *n_launches = 1;
+        return cudaLaunchKernel(k1m8_fn(e->k1m8_stages, dbg, a.window != nullptr), dim3(grid), dim3(512), params, k1m8_smem(e->k1m8_stages), st);
+    }
+    Mid8kNf nfa = nfb;
+    void *params[] = {&args, &tws, &tw256, &nfa};
+    cudaError_t rc = cudaLaunchKernel(k1m8g_fn(e->k1m8_stages, dbg, a.window != nullptr), dim3(grid), dim3(512), params, k1m8_smem(e->k1m8_stages), st);
+    if (rc != cudaSuccess) return rc;
+    LargeFinishArgs fin{};
+    fin.nf_part = nfb.nf_part;
+    fin.xto = nfb.xto;
+    fin.nf_edge = nfb.nf_edge;
+    fin.psd_floor = a.psd_floor;
+    fin.variance = a.variance;
+    fin.n_blocks = n_blocks;
+    fin.n_cta = 2;
+    fin.n = 8192;
+    large_nf_finish_kernel<<<(n_blocks + 3) / 4, 128, 0, st>>>(fin);
+    *n_launches = 2;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_k1_mid(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st) {
@@ -697,6 +727,8 @@ void free_slot(Slot &s) {
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
     if (s.ev_km) cudaEventDestroy(s.ev_km);
     if (s.ev_k2s) cudaEventDestroy(s.ev_k2s);
+    if (s.ev_thr) cudaEventDestroy(s.ev_thr);
+    if (s.ev_peaks) cudaEventDestroy(s.ev_peaks);
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
     s = Slot();
@@ -763,6 +795,8 @@ int alloc_slot(sdr_engine *e, Slot &s) {
     CK(e, cudaEventCreate(&s.ev_k0));
     CK(e, cudaEventCreate(&s.ev_km));
     CK(e, cudaEventCreate(&s.ev_k2s));
+    CK(e, cudaEventCreateWithFlags(&s.ev_thr, cudaEventDisableTiming));
+    CK(e, cudaEventCreateWithFlags(&s.ev_peaks, cudaEventDisableTiming));
     CK(e, cudaEventCreate(&s.ev_k1));
     CK(e, cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
     return SDR_OK;
@@ -926,6 +960,10 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
             e->own_post = true;
         }
     }
+    {
+        const char *av = getenv("SDR_K2_AUX");
+        if (!(av && av[0] == '0')) CKC(cudaStreamCreateWithFlags(&e->s_aux, cudaStreamNonBlocking));
+    }
     if (cfg->cuda_stream) {
         e->own_streams = false;
         e->s_compute = e->s_h2d = e->s_d2h = (cudaStream_t)cfg->cuda_stream;
@@ -1054,8 +1092,12 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
             e->k1_mid8k = (v8 && v8[0] == '0') ? 0 : (v8 && v8[0] == 'f') ? 2 : 1;
             const char *st = getenv("SDR_K1_MID8K_STAGES");
             e->k1m8_stages = (st && st[0] == '1') ? 1 : 2;
+            const char *gv = getenv("SDR_K1_MID8K_GROUPS");
+            e->k1m8_groups = !(gv && gv[0] == '0');
             for (int dbgv = 0; dbgv < 2 && e->k1_mid8k; dbgv++)
                 if (cudaFuncSetAttribute(k1m8_fn(e->k1m8_stages, dbgv != 0, e->d_window != nullptr), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         k1m8_smem(e->k1m8_stages)) != cudaSuccess ||
+                    cudaFuncSetAttribute(k1m8g_fn(e->k1m8_stages, dbgv != 0, e->d_window != nullptr), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          k1m8_smem(e->k1m8_stages)) != cudaSuccess)
                     e->k1_mid8k = 0;
             cudaGetLastError();
@@ -1106,6 +1148,7 @@ void sdr_engine_destroy(sdr_engine *e) {
     cudaFree(e->d_scratch);
     if (e->s_desc) cudaStreamDestroy(e->s_desc);
     if (e->own_post && e->s_post) cudaStreamDestroy(e->s_post);
+    if (e->s_aux) cudaStreamDestroy(e->s_aux);
     if (e->ev_post) cudaEventDestroy(e->ev_post);
     if (e->own_streams) {
         if (e->s_compute) cudaStreamDestroy(e->s_compute);
@@ -1447,8 +1490,9 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     } else if (e->N == 8192 && block_off <= e->round_blocks && (e->k1_mid8k == 2 || (e->k1_mid8k == 1 && n_segs >= e->sm_count / 3))) {
         // TMA-staged single pass, one 512-thread CTA per SM (k1_mid8k.cuh).  Below ~SMs/3 segments the block-parallel
         // two-kernel path (which does not serialise the blocks of a stream) is faster.
-        CK(e, launch_k1_mid8k(e, a1, dbg, e->s_compute));
-        e->last_kernel = "k1_mid8k_kernel";
+        const Mid8kNf nfb{s.d_nf_part, s.d_xto, s.d_nf_edge};
+        CK(e, launch_k1_mid8k(e, a1, nfb, block_off, dbg, e->s_compute, &k1_launches));
+        e->last_kernel = e->k1m8_groups ? "k1_mid8k2_kernel" : "k1_mid8k_kernel";
     } else if (e->k1_mid && e->N == 8192 && block_off <= e->round_blocks && n_segs >= 2 * e->sm_count) {
         // enough segments to fill the GPU with segment-sequential CTAs: fused single pass (k1_mid.cuh)
         CK(e, launch_k1_mid(e, a1, dbg, e->s_compute));
@@ -1516,9 +1560,22 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     int k2_launches = 2;
     k2_thresholds_kernel<<<n_works, K2_THREADS, 0, e->s_post>>>(a2);
     CK(e, cudaGetLastError());
+    // keys and peaks both depend on the thresholds only: the peak scan goes to a side stream so that the two small,
+    // latency-bound grids share the GPU instead of running back to back
+    const bool do_peaks = n_flushes > 0 && !(flags & SDR_NO_PEAKS);
+    if (do_peaks && e->s_aux) {
+        CK(e, cudaEventRecord(s.ev_thr, e->s_post));
+        CK(e, cudaStreamWaitEvent(e->s_aux, s.ev_thr, 0));
+        k2_peaks_kernel<<<n_flushes, K2_THREADS, 0, e->s_aux>>>(a2);
+        CK(e, cudaGetLastError());
+        CK(e, cudaEventRecord(s.ev_peaks, e->s_aux));
+        k2_launches = 3;
+    }
     k2_keys_kernel<<<dim3((max_work_blocks + K2_KEY_ROWS - 1) / K2_KEY_ROWS, n_works), K2_THREADS, 0, e->s_post>>>(a2);
     CK(e, cudaGetLastError());
-    if (n_flushes > 0 && !(flags & SDR_NO_PEAKS)) {
+    if (do_peaks && e->s_aux) {
+        CK(e, cudaStreamWaitEvent(e->s_post, s.ev_peaks, 0));
+    } else if (do_peaks) {
         k2_peaks_kernel<<<n_flushes, K2_THREADS, 0, e->s_post>>>(a2);
         CK(e, cudaGetLastError());
         k2_launches = 3;

@@ -263,4 +263,229 @@ __global__ void __launch_bounds__(512, 1) k1_mid8k_kernel(const K1Args a, const 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// k1_mid8k2_kernel: the same transform as two DECOUPLED groups of 256 threads.  Parity h of the column split owns the
+// rows k1 = 2 fl + h in pass B as well, so group h (warps 8h .. 8h+7) never touches the other group's half of E: the
+// groups only share the TMA stages (both read every stage; the second one to finish a stage re-arms its copy) and run
+// out of phase like two CTAs would -- one group's barrier waits and shared-memory bursts are the other's compute time.
+// The window sums of the two groups meet in global memory (nf_part[block][h][window]); large_nf_finish_kernel adds them
+// and runs dsp.FindNoiseFloor's selection after the launch.
+struct Mid8kNf {
+    double2 *nf_part;  // [blocks][2][10] (sum x, sum x^2) of the group's rows per noise window
+    float *xto;        // [blocks][10] psd[first bin of the next window]
+    int *nf_edge;      // [blocks]
+};
+
+template <int NSTAGE, bool DEBUG_STORE, bool HAS_WINDOW>
+__global__ void __launch_bounds__(512, 1) k1_mid8k2_kernel(const K1Args a, const float2 *__restrict__ tw_step,
+                                                            const float2 *__restrict__ tw256, const Mid8kNf nf) {
+    using Gm = K1Mid8kGeom<NSTAGE>;
+    constexpr int N = Gm::N;
+    extern __shared__ __align__(128) unsigned char m8_smem[];
+    float2 *E = reinterpret_cast<float2 *>(m8_smem + Gm::OFF_E);      // [32][HW_PITCH]
+    float *Ef = reinterpret_cast<float *>(m8_smem + Gm::OFF_E);       // |X|^2 of bin kk at Ef[(kk & 31) * 2*HW_PITCH + (kk >> 5)]
+    float2 *TW = reinterpret_cast<float2 *>(m8_smem + Gm::OFF_TW);    // [15][16] W_256^(hl k)
+    uint64_t *FULL = reinterpret_cast<uint64_t *>(m8_smem + Gm::OFF_BAR);
+    int *DONE = reinterpret_cast<int *>(m8_smem + Gm::OFF_NF);        // [NSTAGE] groups that have consumed the stage
+
+    const int tid = threadIdx.x, h = tid >> 8, tg = tid & 255;        // group h (warp-uniform), thread tg of the group
+    const int lane = tg & 31, wg = tg >> 5;
+    const int c = tg;                                                  // pass A: column c, output parity h
+    const int fl = tg >> 4, hl = tg & 15, k1row = 2 * fl + h;         // pass B: row k1row, lane hl of its half-warp
+    const float db_offset = (float)(13.0102999566398120 - 20.0 * 13.0 * 0.30102999566398120);  // 10 log10(20) - 20 log10(N)
+    auto to_db = [&](float psd) -> float { return __fadd_rn(fmaf(3.01029995663981195f, fast_log2(psd), db_offset), 120.0f); };
+    auto psd_at = [&](int kk) -> float { return Ef[(kk & 31) * (2 * HW_PITCH) + (kk >> 5)]; };
+    auto group_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + h) : "memory"); };
+    const float2 sgn = h ? make_float2(-1.f, -1.f) : make_float2(1.f, 1.f);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; s++) {
+            mbar_init(&FULL[s], 1);
+            DONE[s] = 0;
+        }
+        fence_mbar_init();
+    }
+    if (tid < 240) TW[tid] = __ldg(&tw256[((tid & 15) * ((tid >> 4) + 1)) & 255]);
+    float2 tws[16];
+#pragma unroll
+    for (int p = 0; p < 16; p++) tws[p] = __ldg(&tw_step[(2 * OutIdx<16>::of(p) + h) * 256 + c]);
+    __syncthreads();
+
+    // producer iterator: BOTH group leaders walk the same item sequence (one step per consumed stage); whichever group
+    // finishes a stage second issues the copy its iterator points at
+    int pseg = blockIdx.x, pblk = 0, pn = 0;
+    if (pseg < a.n_segs) pn = __ldg(&a.segs[pseg].n_blocks);
+    auto advance = [&](bool issue, int s) {
+        if (pseg >= a.n_segs) return;
+        if (issue) {
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(a.segs[pseg].iq) + (size_t)pblk * Gm::STAGE_BYTES;
+            mbar_expect_tx(&FULL[s], Gm::STAGE_BYTES);
+            tma_load_1d(m8_smem + (size_t)s * Gm::STAGE_BYTES, src, Gm::STAGE_BYTES, &FULL[s]);
+        }
+        if (++pblk == pn) {
+            pseg += gridDim.x;
+            pblk = 0;
+            if (pseg < a.n_segs) pn = a.segs[pseg].n_blocks;
+        }
+    };
+    if (tg == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; s++) advance(h == 0, s);
+    }
+    uint32_t item = 0;
+
+    for (int seg = blockIdx.x; seg < a.n_segs; seg += gridDim.x) {
+        const Segment sg = a.segs[seg];
+        const WorkParams wp = a.works[sg.work];
+        const int L = wp.n_listeners;
+        const int *lbins = a.listener_bins + wp.listener_off;
+        const int e = wp.edge_width;
+        const int ws = nf_window_size(N, e), n_win = nf_window_count(N, e);
+        // noise floor: warps 0-4 of the group; lane -> (window 2 wg + lane/16, row 2 (lane % 16) + h); the window's bins in
+        // that row are the positions [nf_p0, nf_p0 + nf_n) (bin kk = k1 + 32 p)
+        int nf_p0 = 0, nf_n = 0;
+        const int nf_w = 2 * wg + (lane >> 4), nf_row = 2 * (lane & 15) + h;
+        if (wg < 5) {
+            const int lo = e + nf_w * ws, hi = lo + ws;
+            nf_p0 = lo < nf_row ? 0 : (lo - nf_row + 31) >> 5;
+            const int p1 = hi <= nf_row ? 0 : min(256, (hi - nf_row + 31) >> 5);
+            nf_n = max(p1 - nf_p0, 0);
+        }
+        float cum[16];
+#pragma unroll
+        for (int p = 0; p < 16; p++) {
+            const int kk = k1row + 32 * ((hl + 16 * OutIdx<16>::of(p) + 128) & 255);
+            cum[p] = sg.state_in >= 0 ? a.cum_state[(size_t)sg.state_in * N + kk] : 0.f;
+        }
+
+        for (int blk = 0; blk < sg.n_blocks; blk++, item++) {
+            const int s = item % NSTAGE;
+            const uint32_t parity = (item / NSTAGE) & 1u;
+            const float2 *IN = reinterpret_cast<const float2 *>(m8_smem + (size_t)s * Gm::STAGE_BYTES);
+            const int ob = sg.block_out + blk;
+            mbar_wait(&FULL[s], parity);
+
+            // ---------------- pass A: column c, outputs k1 = 2j + h ----------------
+            float2 v[16];
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const int m = (q & 3) * 4 + (q >> 2);
+                float2 x0 = IN[m * 256 + c], x1 = IN[(m + 16) * 256 + c];
+                if (HAS_WINDOW) {
+                    const float w0 = __ldg(&a.window[m * 256 + c]), w1 = __ldg(&a.window[(m + 16) * 256 + c]);
+                    x0 = __fmul2_rn(x0, make_float2(w0, w0));
+                    x1 = __fmul2_rn(x1, make_float2(w1, w1));
+                }
+                v[m] = __ffma2_rn(x1, sgn, x0);
+            }
+            if (h) {
+                v[1] = mul_w64<2>(v[1]);
+                v[2] = mul_w64<4>(v[2]);
+                v[3] = mul_w64<6>(v[3]);
+                v[4] = mul_w64<8>(v[4]);
+                v[5] = mul_w64<10>(v[5]);
+                v[6] = mul_w64<12>(v[6]);
+                v[7] = mul_w64<14>(v[7]);
+                v[8] = mul_w64<16>(v[8]);
+                v[9] = mul_w64<18>(v[9]);
+                v[10] = mul_w64<20>(v[10]);
+                v[11] = mul_w64<22>(v[11]);
+                v[12] = mul_w64<24>(v[12]);
+                v[13] = mul_w64<26>(v[13]);
+                v[14] = mul_w64<28>(v[14]);
+                v[15] = mul_w64<30>(v[15]);
+            }
+            dft16(v);
+#pragma unroll
+            for (int p = 0; p < 16; p++) v[p] = cmul(v[p], tws[p]);
+            // G0: the group has consumed stage s and finished the previous block's reads of its half of E
+            group_sync();
+            if (tg == 0) {
+                __threadfence_block();
+                const bool second = atomicAdd(&DONE[s], 1) == 1;  // the other group is done with the stage too
+                if (second) {
+                    atomicExch(&DONE[s], 0);
+                    __threadfence_block();
+                    fence_proxy_async();
+                }
+                advance(second, s);
+            }
+#pragma unroll
+            for (int p = 0; p < 16; p++) E[(2 * OutIdx<16>::of(p) + h) * HW_PITCH + c] = v[p];
+            group_sync();  // G1: the group's sixteen rows of E are complete
+
+            // ---------------- pass B: half-warp = row k1row ----------------
+            {
+                HwTwiddle t;
+#pragma unroll
+                for (int k = 1; k < 16; k++) t.w[k - 1] = TW[(k - 1) * 16 + hl];
+                float2 *col = E + k1row * HW_PITCH;
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    const int n1 = (q & 3) * 4 + (q >> 2);
+                    v[n1] = col[16 * n1 + hl];
+                }
+                fft256_halfwarp_regs(v, col, t, hl);
+                __syncwarp();
+                float *prow = reinterpret_cast<float *>(col);
+#pragma unroll
+                for (int p = 0; p < 16; p++) {
+                    const int k2s = hl + ((16 * OutIdx<16>::of(p) + 128) & 255);  // fftshift (dsp/fft.go:54-57)
+                    const float psd = fmaf(v[p].x, v[p].x, v[p].y * v[p].y);      // dsp/fft.go:71-73
+                    const float db = to_db(psd);                                   // rx/receiver.go:376-378
+                    cum[p] = __fadd_rn(cum[p], db);                                // rx/receiver.go:404-406
+                    prow[k2s] = psd;
+                    if (DEBUG_STORE) {
+                        const int kk = k1row + 32 * k2s;
+                        a.dbg_spectrum[(size_t)ob * N + kk] = db;
+                        a.dbg_psd[(size_t)ob * N + kk] = psd;
+                    }
+                }
+            }
+            group_sync();  // G2: |X|^2 of the group's rows complete
+
+            // ---------------- dsp.FindNoiseFloor (dsp/fft.go:215-252): this group's share of the window sums ----------------
+            if (wg < 5) {
+                // rows 2 j + h and 2 (j + 8) + h share their banks (row pitch 2*273 words): the lanes of the upper eight rows
+                // walk their share rotated by one element
+                const float *pp = Ef + nf_row * (2 * HW_PITCH) + nf_p0;
+                const int rot = (lane >> 3) & 1;
+                float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+#pragma unroll
+                for (int i = 0; i + 1 < Gm::NFMAX; i += 2) {
+                    const int j0 = (i + rot == Gm::NFMAX) ? 0 : i + rot, j1 = (i + 1 + rot == Gm::NFMAX) ? 0 : i + 1 + rot;
+                    const float x0 = (j0 < nf_n) ? pp[j0] : 0.f, x1 = (j1 < nf_n) ? pp[j1] : 0.f;
+                    s1a += x0;
+                    s2a = fmaf(x0, x0, s2a);
+                    s1b += x1;
+                    s2b = fmaf(x1, x1, s2b);
+                }
+                double d1 = (double)(s1a + s1b), d2 = (double)(s2a + s2b);
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) {
+                    d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+                    d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+                }
+                if ((lane & 15) == 0) nf.nf_part[((size_t)ob * 2 + h) * 10 + nf_w] = make_double2(d1, d2);
+            } else if (wg == 5) {
+                if (lane < n_win) {  // x_to = psd[e + (w+1)*ws] (dsp/fft.go:238-243): the group that owns the bin's row writes it
+                    const int kk = e + (lane + 1) * ws;
+                    if ((kk & 1) == h) nf.xto[(size_t)ob * 10 + lane] = psd_at(kk);
+                }
+                if (lane == 31 && h == 0) nf.nf_edge[ob] = e;
+            } else {
+                // listener taps (rx/receiver.go:393) on the bins of this group's rows
+                for (int l = tg - 192; l < L; l += 64) {
+                    const int kk = __ldg(&lbins[l]);
+                    if ((kk & 1) == h) a.taps[(size_t)ob * a.tap_stride + l] = to_db(psd_at(kk));
+                }
+            }
+        }
+        float *dst = (sg.flush_idx >= 0) ? a.flush_cum + (size_t)sg.flush_idx * N : a.cum_state + (size_t)sg.state_out * N;
+#pragma unroll
+        for (int p = 0; p < 16; p++) dst[k1row + 32 * ((hl + 16 * OutIdx<16>::of(p) + 128) & 255)] = cum[p];
+    }
+}
+
 }  // namespace sdr
