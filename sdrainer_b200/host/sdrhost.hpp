@@ -876,6 +876,7 @@ class Receiver {
         l->SetAttachmentTimeout(attachmentTimeout_);
         l->SetSilenceTimeout(silenceTimeout_);
         l->SetSignalDebounce(signalDebounce_);
+        l->recordKeys = recordReports;  // the per-listener key log is a test hook like the block reports
         attachBlocks_.push_back(blockIndex_);
         if (slots_.empty()) slots_.assign((size_t)listeners_.Size(), nullptr);
         for (size_t sl = 0; sl < slots_.size(); sl++)
