@@ -12,7 +12,7 @@
 //           16x17 transpose through the row's own storage, radix-16): lane hl ends with X[h + 2*k2], k2 = hl + 16 q;
 //   epilogue in registers (|X|^2, dB, 16 cumulation bins per lane); |X|^2 goes to a 512-float plane in natural
 //           (fftshifted) bin order for the noise windows, x_to and the taps.
-// Noise floor: the lane-share scheme of k1_pair.cuh -- 17 consecutive bins per lane (odd stride: bank-conflict free for
+// Noise floor: lane shares -- 17 consecutive bins per lane (odd stride: bank-conflict free for
 // every edge width), split at the one window boundary a share can contain, window sums gathered by lanes 0..9 and the
 // sequential selection batched NFB blocks at a time -- all inside the warp (__syncwarp only).
 #pragma once
