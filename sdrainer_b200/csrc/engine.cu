@@ -1444,7 +1444,9 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
 
     // N = 65536 with enough segments for whole teams: the single-pass kernel; its per-segment tensor maps travel with
     // the descriptors.  Below 4 segments the block-parallel two-kernel path fills the GPU better.
-    const bool use_wide = e->N == 65536 && (e->k1_wide == 2 || (e->k1_wide == 1 && n_segs >= 4));
+    // (a batch cut into rounds -- SDR_LARGE_ROUND_MB -- has segments that hand a partial window to each other inside one
+    // launch: only the round-by-round two-kernel path orders those)
+    const bool use_wide = e->N == 65536 && block_off <= e->round_blocks && (e->k1_wide == 2 || (e->k1_wide == 1 && n_segs >= 4));
     if (use_wide) {
         CUtensorMap *maps = reinterpret_cast<CUtensorMap *>(s.h_desc + dl.segmaps);
         for (int i = 0; i < n_segs; i++)
