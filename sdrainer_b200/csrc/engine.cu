@@ -1646,7 +1646,11 @@ int sdr_collect(sdr_engine *e, sdr_ticket t, int blocking, sdr_result *out) {
         CK(e, st);
     }
     if (s.h_wide_err && *s.h_wide_err) {
+        // report it once for this ticket and re-arm the flag: the slot is usable again after sdr_release
+        *s.h_wide_err = 0;
+        cudaMemsetAsync(s.d_wide_err, 0, sizeof(int), e->s_compute);
         e->err = "k1_wide: a dependency wait ran out (the batch's results are invalid)";
+        s.collected = true;
         return SDR_ECUDA;
     }
     s.collected = true;
