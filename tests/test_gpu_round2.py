@@ -400,3 +400,22 @@ def test_stockham_block_sizes_against_the_oracle(capi, oracle, n):
     assert loud.any() and np.abs(cum - r.flush_cum[0])[loud].max() < 0.1
     assert np.abs(cum - r.flush_cum[0]).max() < 2.0  # noise-level bins next to 24 carriers, summed over 100 blocks
     pu.check_peaks(pu.peak_keys(outs[1].peaks(0)), [p.key() for p in r.peaks[0]], r.flush_cum[0], r.thresholds[99, 2])
+
+
+def test_realtime_harness_runs_the_whole_loop(capi, host):
+    """host/realtime.hpp at toy size: ring copy -> one sdr_submit for all streams -> collect -> Decoder.Tick per key bit.
+    Keyed tones on the listener bins must produce key-downs and decoded characters, with and without the ring copy."""
+    n, fs, L, S, B = 2048, 192000, 6, 24, 10
+    spec = synth.StreamSpec(sample_rate=fs, block_size=n, n_blocks=120, seed=31,
+                            tones=synth.make_tones(np.random.default_rng(31), L, n, 70, wpm_range=(28.0, 36.0)))
+    iq = synth.generate(spec)
+    src = np.stack([iq.reshape(120, 2 * n), iq.reshape(120, 2 * n)[::-1].copy()])  # two templates
+    bins = np.array([[t.bin for t in spec.tones]] * 2, np.int32)
+    with capi.Engine(n, max_streams=S, max_listeners=L, max_blocks_per_batch=S * B, max_peaks_per_flush=64, n_slots=2) as eng:
+        h = host.RealtimeHarness(eng, fs, n, L, S, B, 3, src, bins, debounce=1)
+        a = h.run(S, 14, ring_copy=True)
+        b = h.run(S // 2, 14, ring_copy=False)
+        h.close()
+    assert a["ticks"] == S * B * L * 12 and b["ticks"] == (S // 2) * B * L * 12  # 12 steady-state batches of 14
+    assert a["key_downs"] > 0.05 * a["ticks"] and a["chars"] > 0
+    assert a["batch_s"] > 0 and a["gpu_ms"] > 0 and b["copy_s"] < a["copy_s"] + 1e-3
