@@ -6,16 +6,25 @@
 // A 512 KB block fits neither a CTA nor (usefully) a cluster, so the 256 x 256 four-step transform keeps its
 // intermediate -- but in a small ring that never leaves the 126 MB L2, inside ONE persistent launch:
 //   * a TEAM of 16 CTAs owns a segment (<= 100 consecutive blocks of one stream) and walks its blocks in order;
-//   * per step every CTA of the team does two things.  CONSUME step i: its row tile (16 rows x 256 of the intermediate,
-//     32 KB contiguous, one cp.async.bulk) -> half-warp 256-point transforms -> |X|^2, dB, cumulation in registers
-//     (16 bins per thread for the whole segment), this CTA's share of the ten noise-window sums, x_to, its taps.
-//     PRODUCE step i + D: its column tile of the IQ block (16 columns x 256 rows: ONE tensor-map TMA load,
-//     cp.async.bulk.tensor.3d -> SASS UTMALDG, 128-byte swizzle) -> half-warp 256-point transforms -> twiddle W_N^(c k)
-//     -> swizzled tile in shared memory -> ONE tensor-map TMA store (UTMASTG) into ring slot (i + D) mod R;
-//   * a global counter per step (`ready`) is released by each producer after its store has completed and acquired by
-//     thread 0 of each consumer before it issues the row-tile load: the only inter-CTA synchronisation.  All CTAs of
-//     the launch are co-resident (cooperative launch), every wait is on work that only depends on earlier steps, so
-//     the schedule cannot deadlock; waits are bounded all the same and report through `err`.
+//   * per step every CTA of the team does two things.  PRODUCE step i + D - 1: its column tile of the IQ block (16
+//     columns x 256 rows: ONE tensor-map TMA load, cp.async.bulk.tensor.3d -> SASS UTMALDG, 128-byte swizzle,
+//     L2 evict-first) -> half-warp 256-point transforms -> twiddle W_N^(c k) -> swizzled tile in shared memory -> ONE
+//     tensor-map TMA store (UTMASTG) into ring slot (i + D - 1) mod R.  CONSUME step i: its row tile (16 rows x 256 of
+//     the intermediate, 32 KB contiguous, one cp.async.bulk) -> half-warp 256-point transforms -> |X|^2, dB, cumulation
+//     in registers (16 bins per thread for the whole segment), this CTA's share of the ten noise-window sums, x_to, its
+//     taps; the tile's lines are then discarded from L2 (they are dead until the slot is rewritten);
+//   * warps 0-7 compute; warp 8 is the DMA warp: it owns every wait on another CTA, every TMA issue and every
+//     publication, the compute warps only wait on shared-memory mbarriers;
+//   * a global counter per step (`ready`) is released by each producer's DMA thread after its tile store has completed
+//     and acquired by each consumer's DMA thread before it requests the row tile: the only inter-CTA synchronisation.
+//     All CTAs of the launch are co-resident (cooperative launch) and every wait is on work of EARLIER steps only:
+//       - step j is produced in iteration j - D + 1 and published right after its store completes; its row tile is
+//         requested in iteration j - 1 (after B was read there), i.e. D - 2 >= 1 iterations later: no CTA waits on
+//         itself, the team only has to stay within D - 2 iterations of each other;
+//       - ring safety: when a CTA stores step j = i + D - 1 (iteration i) it has seen ready[i] complete, so every
+//         team mate finished producing step i, i.e. finished CONSUMING steps <= i - D and may have the row tile of step
+//         i - D + 1 in flight; the slot's previous occupant is step j - R, safe iff j - R <= i - D, i.e. R >= 2 D - 1.
+//     Waits are bounded all the same and report through `err` (sdr_collect turns it into SDR_ECUDA).
 // HBM sees the IQ once (8 N per block), the ten partial window sums per CTA and block, and the cumulation once per 100
 // blocks; the intermediate (8 N written + 8 N read per block) is L2 traffic: R x 512 KB per team.
 // The two-kernel path of k1_large.cuh (32 N bytes of HBM traffic per block) remains for launches with too few segments
@@ -46,16 +55,15 @@ struct WideArgs {
     float *xto;                   // [blocks][10]
     int *nf_edge;                 // [blocks]
     float db_offset;              // 10*log10(20/N^2)
-    int lookahead;                // D >= 3: step i + D - 1 is produced in iteration i and published at its end; its row tile
-                                  // is requested early in iteration i + D - 2
+    int lookahead;                // D >= 3: step i + D - 1 is produced in iteration i; its row tile is requested in iteration i + D - 2
     int ring;                     // R >= 2 D - 1 slots per team
     int discard;                  // drop consumed row tiles from L2 (discard.global.L2) instead of letting them be written back
 };
 
 constexpr int K1W_OFF_A = 0;                                   // IQ column tile, later the outgoing tile (1024-byte aligned: 128B swizzle)
 constexpr int K1W_OFF_B = K1W_OFF_A + K1W_TILE_BYTES;          // row tile of the intermediate
-constexpr int K1W_OFF_S = K1W_OFF_B + K1W_TILE_BYTES;          // [16][HW_PITCH] transpose scratch, then the (psd, dB) tile
-constexpr int K1W_OFF_TW = K1W_OFF_S + 16 * HW_PITCH * 8;     // W_256^m
+constexpr int K1W_OFF_S = K1W_OFF_B + K1W_TILE_BYTES;          // [16][HW_PITCH] transpose scratch, then the |X|^2 / dB planes
+constexpr int K1W_OFF_TW = K1W_OFF_S + 16 * HW_PITCH * 8;     // [15][16] W_256^(hl k)
 constexpr int K1W_OFF_TQ = K1W_OFF_TW + 256 * 8;             // [16][17] W_N^(16 c q)
 constexpr int K1W_OFF_MISC = K1W_OFF_TQ + 16 * 17 * 8;
 constexpr int K1W_SMEM_BYTES = K1W_OFF_MISC + 128;
