@@ -338,6 +338,7 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
         // fftshifted order (dsp/fft.go:54-57): |X|^2 at prow[k2s], dB at prow[256 + k2s], k2s = (k2 + 128) & 255, i.e.
         // bin kk = (r0 + f) + 256 k2s
         float *prow = reinterpret_cast<float *>(col);
+        const bool need_db = L > 0 || a.dbg_psd != nullptr;  // uniform: a peak scan without listeners (config 5) skips the stores
 #pragma unroll
         for (int p = 0; p < 16; p++) {
             const float psd = fmaf(v[p].x, v[p].x, v[p].y * v[p].y);                                      // dsp/fft.go:71-73
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
             cum[p] = __fadd_rn(cum[p], db);                                                                // rx/receiver.go:404-406
             const int k2s = hl + ((16 * OutIdx<16>::of(p) + 128) & 255);
             prow[k2s] = psd;
-            prow[256 + k2s] = db;
+            if (need_db) prow[256 + k2s] = db;  // only the taps (and the parity store) read the dB plane
         }
         compute_sync();
         const float *Sf = reinterpret_cast<const float *>(S);  // row j of the tile: Sf[j * 2*HW_PITCH + (0 | 256) + k2s]
