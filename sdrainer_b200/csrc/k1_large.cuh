@@ -171,6 +171,45 @@ __global__ void __launch_bounds__(SUBFFT_F *L / 4) sub_fft_kernel(const SubFftAr
 // as K1 (fft_radix.cuh); no CTA barrier inside the transform.
 constexpr int HW_PITCH = 273;  // complex slots per column: >= 16*17 (transpose), odd multiple-of-16 remainder 1
 
+// Once a row's transform is done, its (dead) transpose column takes the row's |X|^2 (and dB) as a float plane.  With
+// the plain pitch (2*HW_PITCH = 546 words == 2 mod 32) the two half-warps of a warp -- rows j and j + 1 -- store to
+// banks that overlap in 14 of 16 positions (two wavefronts per STS) and the sixteen rows a noise-window share reads
+// side by side fall on all even banks, so two shares in one warp collide whenever their offsets differ by an even
+// number.  The plane of row j therefore starts at bank beta(j) = 2 (j / 2) + 16 (j % 2): neighbouring rows are exactly
+// 16 banks apart (one wavefront per warp-wide STS.32) and the sixteen rows still cover sixteen distinct (even) banks.
+// row_word0: word offset of the row's column in the scratch; j: the row's index among the sixteen rows that are stored /
+// read together.  The skew is < 32 words and the planes take 512: both fit the column's 2*HW_PITCH words.
+static_assert(2 * HW_PITCH >= 512 + 32, "planes + skew must fit the row's own column");
+__device__ __forceinline__ int plane_skew(int row_word0, int j) { return (2 * (j >> 1) + 16 * (j & 1) - row_word0) & 31; }
+
+// One thread's share of a noise-window sum (dsp/fft.go:226-236): the window's positions in one row, float32 inside the
+// share.  pp points at position P of the row, the same P for the sixteen rows of the half-warp (so their banks stay
+// beta(j) + const); the row's positions are the indices [lo, hi) with lo in {0, 1} and hi <= NFMAX - 1.  rot in {0, 1}
+// makes the lane walk its indices rotated by one (index i + rot, the last one wraps to 0): the upper half-warp uses it
+// when its P has the same parity as the lower one's, which puts the two halves on disjoint (even / odd) banks.
+template <int NFMAX>
+__device__ __forceinline__ void nf_row_share(const float *pp, int lo, int hi, int rot, float &s1, float &s2) {
+    static_assert(NFMAX % 2 == 0, "pairs");
+    const float *pr = pp + rot;
+    const int hi_r = hi - rot;  // i + rot < hi  <=>  i < hi_r
+    const bool first_ok = lo == 0 && hi > 0;
+    float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+#pragma unroll
+    for (int i = 0; i < NFMAX; i += 2) {
+        float x0, x1;
+        if (i == 0) x0 = (rot ? 0 < hi_r : first_ok) ? pr[0] : 0.f;
+        else x0 = (i < hi_r) ? pr[i] : 0.f;
+        if (i + 1 == NFMAX - 1) x1 = rot ? (first_ok ? pp[0] : 0.f) : ((i + 1 < hi_r) ? pr[i + 1] : 0.f);
+        else x1 = (i + 1 < hi_r) ? pr[i + 1] : 0.f;
+        s1a += x0;
+        s2a = fmaf(x0, x0, s2a);
+        s1b += x1;
+        s2b = fmaf(x1, x1, s2b);
+    }
+    s1 = s1a + s1b;
+    s2 = s2a + s2b;
+}
+
 struct HwTwiddle {
     float2 w[15];  // W256^(hl * k1), k1 = 1..15
 };

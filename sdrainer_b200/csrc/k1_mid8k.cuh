@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(512, 1) k1_mid8k2_kernel(const K1Args a, const
     constexpr int N = Gm::N;
     extern __shared__ __align__(128) unsigned char m8_smem[];
     float2 *E = reinterpret_cast<float2 *>(m8_smem + Gm::OFF_E);      // [32][HW_PITCH]
-    float *Ef = reinterpret_cast<float *>(m8_smem + Gm::OFF_E);       // |X|^2 of bin kk at Ef[(kk & 31) * 2*HW_PITCH + (kk >> 5)]
+    float *Ef = reinterpret_cast<float *>(m8_smem + Gm::OFF_E);       // |X|^2 of bin kk at Ef[plane_of(kk & 31) + (kk >> 5)]
     float2 *TW = reinterpret_cast<float2 *>(m8_smem + Gm::OFF_TW);    // [15][16] W_256^(hl k)
     uint64_t *FULL = reinterpret_cast<uint64_t *>(m8_smem + Gm::OFF_BAR);
     int *DONE = reinterpret_cast<int *>(m8_smem + Gm::OFF_NF);        // [NSTAGE] groups that have consumed the stage
@@ -294,7 +294,9 @@ __global__ void __launch_bounds__(512, 1) k1_mid8k2_kernel(const K1Args a, const
     const int fl = tg >> 4, hl = tg & 15, k1row = 2 * fl + h;         // pass B: row k1row, lane hl of its half-warp
     const float db_offset = (float)(13.0102999566398120 - 20.0 * 13.0 * 0.30102999566398120);  // 10 log10(20) - 20 log10(N)
     auto to_db = [&](float psd) -> float { return __fadd_rn(fmaf(3.01029995663981195f, fast_log2(psd), db_offset), 120.0f); };
-    auto psd_at = [&](int kk) -> float { return Ef[(kk & 31) * (2 * HW_PITCH) + (kk >> 5)]; };
+    // the |X|^2 plane of row r = 2 fl + h starts at word plane_of(r) of E, inside the row's own column (k1_large.cuh: plane_skew)
+    auto plane_of = [](int r) { return r * (2 * HW_PITCH) + plane_skew(r * (2 * HW_PITCH), r >> 1); };
+    auto psd_at = [&](int kk) -> float { return Ef[plane_of(kk & 31) + (kk >> 5)]; };
     auto group_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + h) : "memory"); };
     const float2 sgn = h ? make_float2(-1.f, -1.f) : make_float2(1.f, 1.f);
 
@@ -343,14 +345,20 @@ __global__ void __launch_bounds__(512, 1) k1_mid8k2_kernel(const K1Args a, const
         const int e = wp.edge_width;
         const int ws = nf_window_size(N, e), n_win = nf_window_count(N, e);
         // noise floor: warps 0-4 of the group; lane -> (window 2 wg + lane/16, row 2 (lane % 16) + h); the window's bins in
-        // that row are the positions [nf_p0, nf_p0 + nf_n) (bin kk = k1 + 32 p)
-        int nf_p0 = 0, nf_n = 0;
+        // that row are the positions [first(row), last(row)) (bin kk = k1 + 32 p).  The sixteen rows of a window are read
+        // from the position nf_p of the group's LAST row (the smallest first()), which keeps their banks plane_of's; the
+        // row's own range is [nf_lo, nf_hi) relative to it, nf_lo in {0, 1} (k1_large.cuh: nf_row_share)
+        int nf_p = 0, nf_lo = 0, nf_hi = 0, nf_rot = 0;
         const int nf_w = 2 * wg + (lane >> 4), nf_row = 2 * (lane & 15) + h;
         if (wg < 5) {
-            const int lo = e + nf_w * ws, hi = lo + ws;
-            nf_p0 = lo < nf_row ? 0 : (lo - nf_row + 31) >> 5;
+            auto first = [&](int w, int k1) { const int lo = e + w * ws; return lo < k1 ? 0 : (lo - k1 + 31) >> 5; };
+            const int hi = e + (nf_w + 1) * ws;
+            nf_p = first(nf_w, 30 + h);
+            nf_lo = first(nf_w, nf_row) - nf_p;
             const int p1 = hi <= nf_row ? 0 : min(256, (hi - nf_row + 31) >> 5);
-            nf_n = max(p1 - nf_p0, 0);
+            nf_hi = max(p1 - nf_p, 0);
+            // the window of the upper half-warp walks rotated when its start has the parity of the lower one's
+            nf_rot = (lane >> 4) & ~(first(2 * wg + 1, 30 + h) - first(2 * wg, 30 + h)) & 1;
         }
         float cum[16];
 #pragma unroll
@@ -428,7 +436,7 @@ __global__ void __launch_bounds__(512, 1) k1_mid8k2_kernel(const K1Args a, const
                 }
                 fft256_halfwarp_regs(v, col, t, hl);
                 __syncwarp();
-                float *prow = reinterpret_cast<float *>(col);
+                float *prow = Ef + plane_of(k1row);  // inside the row's own (dead) column
 #pragma unroll
                 for (int p = 0; p < 16; p++) {
                     const int k2s = hl + ((16 * OutIdx<16>::of(p) + 128) & 255);  // fftshift (dsp/fft.go:54-57)
@@ -447,21 +455,9 @@ __global__ void __launch_bounds__(512, 1) k1_mid8k2_kernel(const K1Args a, const
 
             // ---------------- dsp.FindNoiseFloor (dsp/fft.go:215-252): this group's share of the window sums ----------------
             if (wg < 5) {
-                // rows 2 j + h and 2 (j + 8) + h share their banks (row pitch 2*273 words): the lanes of the upper eight rows
-                // walk their share rotated by one element
-                const float *pp = Ef + nf_row * (2 * HW_PITCH) + nf_p0;
-                const int rot = (lane >> 3) & 1;
-                float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-#pragma unroll
-                for (int i = 0; i + 1 < Gm::NFMAX; i += 2) {
-                    const int j0 = (i + rot == Gm::NFMAX) ? 0 : i + rot, j1 = (i + 1 + rot == Gm::NFMAX) ? 0 : i + 1 + rot;
-                    const float x0 = (j0 < nf_n) ? pp[j0] : 0.f, x1 = (j1 < nf_n) ? pp[j1] : 0.f;
-                    s1a += x0;
-                    s2a = fmaf(x0, x0, s2a);
-                    s1b += x1;
-                    s2b = fmaf(x1, x1, s2b);
-                }
-                double d1 = (double)(s1a + s1b), d2 = (double)(s2a + s2b);
+                float s1, s2;
+                nf_row_share<28>(Ef + plane_of(nf_row) + nf_p, nf_lo, nf_hi, nf_rot, s1, s2);  // <= 26 positions per row, + 1, even
+                double d1 = (double)s1, d2 = (double)s2;
 #pragma unroll
                 for (int o = 8; o > 0; o >>= 1) {
                     d1 += __shfl_xor_sync(0xffffffffu, d1, o);

@@ -62,12 +62,13 @@ struct WideArgs {
 
 constexpr int K1W_OFF_A = 0;                                   // IQ column tile, later the outgoing tile (1024-byte aligned: 128B swizzle)
 constexpr int K1W_OFF_B = K1W_OFF_A + K1W_TILE_BYTES;          // row tile of the intermediate
-constexpr int K1W_OFF_S = K1W_OFF_B + K1W_TILE_BYTES;          // [16][HW_PITCH] transpose scratch, then the |X|^2 / dB planes
-constexpr int K1W_OFF_TW = K1W_OFF_S + 16 * HW_PITCH * 8;     // [15][16] W_256^(hl k)
+constexpr int K1W_PITCH_P = 280;                               // column pitch of the PRODUCE transposes (== 8 mod 16, see produce)
+constexpr int K1W_OFF_S = K1W_OFF_B + K1W_TILE_BYTES;          // transpose scratch ([16][K1W_PITCH_P] produce, [16][HW_PITCH] consume), then the |X|^2 / dB planes
+constexpr int K1W_OFF_TW = K1W_OFF_S + 16 * K1W_PITCH_P * 8;  // [15][16] W_256^(hl k)
 constexpr int K1W_OFF_TQ = K1W_OFF_TW + 256 * 8;             // [16][17] W_N^(16 c q)
 constexpr int K1W_OFF_MISC = K1W_OFF_TQ + 16 * 17 * 8;
 constexpr int K1W_SMEM_BYTES = K1W_OFF_MISC + 128;
-constexpr int K1W_NFMAX = 26;                                  // positions of one noise window in one row: ceil(6553 / 256)
+constexpr int K1W_NFMAX = 28;                                  // positions of one noise window in one row: ceil(6553 / 256) = 26, + 1 (common start), even
 constexpr int K1W_THREADS = 288;                               // eight compute warps + the DMA warp
 
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
@@ -227,14 +228,22 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
     }
 
     // ================================ compute warps ================================
-    const int hl = tid & 15, f = tid >> 4, lane = tid & 31, warp = tid >> 5;
-    // byte offset of element (row hl + 16 j, column f) in a 128B-swizzled [256][16] tile, minus j * 2048
-    const int swz_off = hl * 128 + ((((f >> 1) ^ (hl & 7))) << 4) + ((f & 1) << 3);
-    const float2 tw_base = __ldg(&wa.tw_step[(size_t)(c0 + f) * 256 + hl]);  // W_N^(c hl)
+    const int hl = tid & 15, f = tid >> 4, lane = tid & 31, warp = tid >> 5;  // consume: half-warp f = row r0 + f
+    // PRODUCE runs the same two transforms per warp (columns 2 warp, 2 warp + 1) with another lane assignment: lanes
+    // 0-7 / 8-15 of each 16-lane half are elements hp .. hp + 7 of the even / odd column (hp = 0 or 8).  A 64-bit
+    // shared-memory access is served per 16 lanes; in the 128B-swizzled tile the elements hl and hl + 8 of one column
+    // share their banks (two wavefronts per half), whereas elements hp .. hp + 7 of two neighbouring columns cover the
+    // 128-byte line exactly once.  The transposes of these transforms use the column pitch K1W_PITCH_P (== 8 mod 16), which
+    // keeps them conflict-free under this assignment (the even / odd column's eight lanes take slots s .. s + 7 / s + 8 ..
+    // s + 15 mod 16).
+    const int hlp = (lane & 7) | ((lane >> 4) << 3), fp = 2 * warp + ((lane >> 3) & 1);
+    // byte offset of element (row hlp + 16 j, column fp) in a 128B-swizzled [256][16] tile, minus j * 2048
+    const int swz_off = hlp * 128 + ((((fp >> 1) ^ (hlp & 7))) << 4) + ((fp & 1) << 3);
+    const float2 tw_base = __ldg(&wa.tw_step[(size_t)(c0 + fp) * 256 + hlp]);  // W_N^(c hl)
     // the fifteen W256^(hl k) of the half-warp transform are re-read from shared memory per transform
-    auto load_hw_twiddle = [&](HwTwiddle &t) {
+    auto load_hw_twiddle = [&](HwTwiddle &t, int l16) {
 #pragma unroll
-        for (int k = 1; k < 16; k++) t.w[k - 1] = TW[(k - 1) * 16 + hl];
+        for (int k = 1; k < 16; k++) t.w[k - 1] = TW[(k - 1) * 16 + l16];
     };
 
     WideIter ic, ip;
@@ -250,25 +259,25 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
 #pragma unroll
         for (int q = 0; q < 16; q++) {
             const int n1 = (q & 3) * 4 + (q >> 2);
-            v[n1] = *reinterpret_cast<const float2 *>(A + swz_off + n1 * 2048);  // x[(16 n1 + hl) * 256 + c0 + f]
+            v[n1] = *reinterpret_cast<const float2 *>(A + swz_off + n1 * 2048);  // x[(16 n1 + hlp) * 256 + c0 + fp]
         }
         if (a.window) {
 #pragma unroll
             for (int n1 = 0; n1 < 16; n1++) {
-                const float w = __ldg(&a.window[(16 * n1 + hl) * 256 + c0 + f]);
+                const float w = __ldg(&a.window[(16 * n1 + hlp) * 256 + c0 + fp]);
                 v[n1] = __fmul2_rn(v[n1], make_float2(w, w));
             }
         }
         compute_sync();  // the tile is in registers: A can take the outgoing tile; S is free (consume's plane reads are done)
         {
             HwTwiddle t;
-            load_hw_twiddle(t);
-            fft256_halfwarp_regs(v, S + f * HW_PITCH, t, hl);
+            load_hw_twiddle(t, hlp);
+            fft256_halfwarp_regs(v, S + fp * K1W_PITCH_P, t, hlp);
         }
 #pragma unroll
-        for (int p = 0; p < 16; p++) {  // Z[k][c0 + f], k = hl + 16 q, swizzled like the TMA box
+        for (int p = 0; p < 16; p++) {  // Z[k][c0 + fp], k = hlp + 16 q, swizzled like the TMA box
             const int q = OutIdx<16>::of(p);
-            *reinterpret_cast<float2 *>(A + swz_off + q * 2048) = cmul(cmul(v[p], tw_base), TQ[f * 17 + q]);
+            *reinterpret_cast<float2 *>(A + swz_off + q * 2048) = cmul(cmul(v[p], tw_base), TQ[fp * 17 + q]);
         }
         fence_proxy_async();  // generic-proxy writes of the tile before the async-proxy (TMA) read
         mbar_arrive(OUT_RDY);
@@ -281,7 +290,13 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
     }
 
     float cum[16];
-    int e = 0, ws = 1, n_win = 9, L = 0, nf_p0 = 0, nf_n = 0;
+    int e = 0, ws = 1, n_win = 9, L = 0, nf_p = 0, nf_lo = 0, nf_hi = 0, nf_rot = 0;
+    // S belongs to the warps in private slices of 2 * K1W_PITCH_P complex slots (no barrier separates one warp's produce
+    // transposes from another warp's consume transposes): produce puts its two columns at pitch K1W_PITCH_P, consume at
+    // pitch HW_PITCH inside the same slice.  The |X|^2 / dB planes of row j start at word plane_of(j) of S, inside the
+    // row's own consume column (k1_large.cuh: plane_skew)
+    auto col_of = [](int j) { return (j >> 1) * (2 * K1W_PITCH_P) + (j & 1) * HW_PITCH; };  // complex slots
+    auto plane_of = [&](int j) { return 2 * col_of(j) + plane_skew(2 * col_of(j), j); };    // words
     const int *lbins = nullptr;
 
     while (ic.nb != 0) {
@@ -296,14 +311,20 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
             L = wp.n_listeners;
             lbins = a.listener_bins + wp.listener_off;
             // noise floor: thread (window w = 2 warp + lane/16, row j = lane % 16) of warps 0-4; the window's bins in row
-            // k1 = r0 + j are the positions [nf_p0, nf_p0 + nf_n) (bin kk = k1 + 256 p)
-            nf_p0 = nf_n = 0;
+            // k1 = r0 + j are the positions [first(k1), last(k1)) (bin kk = k1 + 256 p).  All sixteen rows of a window are
+            // read from the position nf_p of the LAST row (the smallest first()), so that their banks stay plane_of's; the
+            // row's own range is [nf_lo, nf_hi) relative to it, nf_lo in {0, 1} (k1_large.cuh: nf_row_share)
+            nf_p = nf_lo = nf_hi = nf_rot = 0;
             if (warp < 5) {
+                auto first = [&](int w, int k1) { const int lo = e + w * ws; return lo < k1 ? 0 : (lo - k1 + 255) >> 8; };
                 const int w = 2 * warp + (lane >> 4), k1 = r0 + (lane & 15);
-                const int lo = e + w * ws, hi = lo + ws;
-                nf_p0 = lo < k1 ? 0 : (lo - k1 + 255) >> 8;
+                const int hi = e + (w + 1) * ws;
+                nf_p = first(w, r0 + 15);
+                nf_lo = first(w, k1) - nf_p;
                 const int p1 = hi <= k1 ? 0 : min(256, (hi - k1 + 255) >> 8);
-                nf_n = max(p1 - nf_p0, 0);
+                nf_hi = max(p1 - nf_p, 0);
+                // the window of the upper half-warp walks rotated when its start has the parity of the lower one's
+                nf_rot = (lane >> 4) & ~(first(2 * warp + 1, r0 + 15) - first(2 * warp, r0 + 15)) & 1;
             }
 #pragma unroll
             for (int p = 0; p < 16; p++) {
@@ -327,17 +348,17 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
         if (wa.discard)
             discard_l2_line(reinterpret_cast<const unsigned char *>(wa.tmp + ((size_t)(team * R + ic.step % R) * N + (size_t)r0 * 256)) + tid * 128);
         mbar_arrive(B_FREE);  // B is in registers: the DMA warp refills it
-        float2 *col = S + f * HW_PITCH;
+        float2 *col = S + col_of(f);
         {
             HwTwiddle t;
-            load_hw_twiddle(t);
+            load_hw_twiddle(t, hl);
             fft256_halfwarp_regs(v, col, t, hl);
         }
         __syncwarp();
         // X[(r0 + f) + 256 k2], k2 = hl + 16*OutIdx<16>(p).  The row's (dead) transpose storage takes two float planes in
         // fftshifted order (dsp/fft.go:54-57): |X|^2 at prow[k2s], dB at prow[256 + k2s], k2s = (k2 + 128) & 255, i.e.
         // bin kk = (r0 + f) + 256 k2s
-        float *prow = reinterpret_cast<float *>(col);
+        float *prow = reinterpret_cast<float *>(S) + plane_of(f);  // inside the row's own column
         const bool need_db = L > 0 || a.dbg_psd != nullptr;  // uniform: a peak scan without listeners (config 5) skips the stores
 #pragma unroll
         for (int p = 0; p < 16; p++) {
@@ -349,14 +370,14 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
             if (need_db) prow[256 + k2s] = db;  // only the taps (and the parity store) read the dB plane
         }
         compute_sync();
-        const float *Sf = reinterpret_cast<const float *>(S);  // row j of the tile: Sf[j * 2*HW_PITCH + (0 | 256) + k2s]
+        const float *Sf = reinterpret_cast<const float *>(S);  // row j of the tile: Sf[plane_of(j) + (0 | 256) + k2s]
         if (a.dbg_psd) {  // parity / scope only: half-warp = 16 consecutive bins
 #pragma unroll
             for (int i = 0; i < 16; i++) {
                 const int k2s = f + 16 * i;
                 const int kk = (r0 + hl) + N1 * k2s;
-                a.dbg_psd[(size_t)ob * N + kk] = Sf[hl * (2 * HW_PITCH) + k2s];
-                a.dbg_spectrum[(size_t)ob * N + kk] = Sf[hl * (2 * HW_PITCH) + 256 + k2s];
+                a.dbg_psd[(size_t)ob * N + kk] = Sf[plane_of(hl) + k2s];
+                a.dbg_spectrum[(size_t)ob * N + kk] = Sf[plane_of(hl) + 256 + k2s];
             }
         }
         // dsp.FindNoiseFloor (dsp/fft.go:215-252), window sums over this CTA's bins: thread (window w, row j) sums the <= 27
@@ -364,17 +385,9 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
         // reduction over the sixteen rows gives this CTA's (sum x, sum x^2) of the window
         if (warp < 5) {
             const int w = 2 * warp + (lane >> 4);
-            const float *pp = Sf + (lane & 15) * (2 * HW_PITCH) + nf_p0;
-            float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-#pragma unroll
-            for (int i = 0; i + 1 < K1W_NFMAX; i += 2) {
-                const float x0 = (i < nf_n) ? pp[i] : 0.f, x1 = (i + 1 < nf_n) ? pp[i + 1] : 0.f;
-                s1a += x0;
-                s2a = fmaf(x0, x0, s2a);
-                s1b += x1;
-                s2b = fmaf(x1, x1, s2b);
-            }
-            double d1 = (double)(s1a + s1b), d2 = (double)(s2a + s2b);
+            float s1, s2;
+            nf_row_share<K1W_NFMAX>(Sf + plane_of(lane & 15) + nf_p, nf_lo, nf_hi, nf_rot, s1, s2);
+            double d1 = (double)s1, d2 = (double)s2;
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) {
                 d1 += __shfl_xor_sync(0xffffffffu, d1, o);
@@ -385,13 +398,13 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
         if (tid < n_win) {  // x_to = psd[e + (w+1)*ws] (dsp/fft.go:238-243) if this CTA owns that bin
             const int kk = e + (tid + 1) * ws;
             const int k1 = kk & (N1 - 1);
-            if (k1 >= r0 && k1 < r0 + 16) wa.xto[(size_t)ob * 10 + tid] = Sf[(k1 - r0) * (2 * HW_PITCH) + (kk >> 8)];
+            if (k1 >= r0 && k1 < r0 + 16) wa.xto[(size_t)ob * 10 + tid] = Sf[plane_of(k1 - r0) + (kk >> 8)];
         }
         if (rank == 0 && tid == 0) wa.nf_edge[ob] = e;
         for (int l = tid; l < L; l += 256) {  // listener taps (rx/receiver.go:393) on bins this CTA owns
             const int kk = __ldg(&lbins[l]);
             const int k1 = kk & (N1 - 1);
-            if (k1 >= r0 && k1 < r0 + 16) a.taps[(size_t)ob * a.tap_stride + l] = Sf[(k1 - r0) * (2 * HW_PITCH) + 256 + (kk >> 8)];
+            if (k1 >= r0 && k1 < r0 + 16) a.taps[(size_t)ob * a.tap_stride + l] = Sf[plane_of(k1 - r0) + 256 + (kk >> 8)];
         }
         if (ic.blk == sg.n_blocks - 1) {  // end of the segment: flush or save the cumulation
             float *dst = (sg.flush_idx >= 0) ? a.flush_cum + (size_t)sg.flush_idx * N : a.cum_state + (size_t)sg.state_out * N;
