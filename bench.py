@@ -415,7 +415,7 @@ def run_gpu(args):
                 "traffic": (tr or {}).get("dram_bytes_per_launch"), "algorithmic_bytes_per_launch": abytes,
                 "k1_ms_per_launch": k1_avg_ms, "k1_share_of_step": k1_avg_ms * args.steps / elapsed_ms,
                 "k2_ms_per_launch": float(np.mean(k2_ms)),
-                "k2_note": "K2 runs on the engine's second stream and overlaps the next batch's K1"}
+                "k2_note": "three launches after K1 on the compute stream (thresholds, keys; the peak scan on a side stream beside them)"}
     if tr:
         roofline["traffic_note"] = tr.get("note")
     # why the HBM fraction stops near 0.6: the arithmetic of a 2048-point fp32 transform + dB +

@@ -386,6 +386,10 @@ struct WideBufs {
     float2 *tmp;
     int *ready, *err, *h_err;
 };
+#ifdef SDR_K1W_TRACE
+static long long *g_k1w_trace = nullptr;  // measurement builds: clock stamps of the last k1_wide launch
+constexpr size_t K1W_TRACE_BYTES = (size_t)32 * 512 * 32 * sizeof(long long);
+#endif
 cudaError_t launch_k1_wide(const sdr_engine *e, const K1Args &a, const LargeFastBufs &lb, const WideBufs &wb, int n_blocks, bool dbg,
                            cudaStream_t st) {
     WideArgs wa{};
@@ -405,6 +409,11 @@ cudaError_t launch_k1_wide(const sdr_engine *e, const K1Args &a, const LargeFast
     wa.lookahead = e->k1w_lookahead;
     wa.ring = e->k1w_ring;
     wa.discard = e->k1w_discard ? 1 : 0;
+#ifdef SDR_K1W_TRACE
+    if (!g_k1w_trace) cudaMalloc((void **)&g_k1w_trace, K1W_TRACE_BYTES);
+    cudaMemsetAsync(g_k1w_trace, 0, K1W_TRACE_BYTES, st);
+    wa.trace = g_k1w_trace;
+#endif
     const int n_teams = a.n_segs < e->k1w_max_teams ? a.n_segs : e->k1w_max_teams;
     cudaError_t rc = cudaMemsetAsync(wb.ready, 0, (size_t)n_blocks * sizeof(int), st);
     if (rc != cudaSuccess) return rc;
@@ -1023,7 +1032,7 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
                 if (dv && atoi(dv) >= 3 && atoi(dv) <= 8) e->k1w_lookahead = atoi(dv);
                 e->k1w_ring = 2 * e->k1w_lookahead;
                 const char *rv = getenv("SDR_K1_WIDE_RING");
-                if (rv && atoi(rv) >= 2 * e->k1w_lookahead - 1 && atoi(rv) <= 16) e->k1w_ring = atoi(rv);
+                if (rv && atoi(rv) >= 2 * e->k1w_lookahead && atoi(rv) <= 16) e->k1w_ring = atoi(rv);  // R >= 2 D (k1_wide.cuh)
                 const char *kv = getenv("SDR_K1_WIDE_DISCARD");
                 e->k1w_discard = !(kv && kv[0] == '0');
                 int occ = 0, coop = 0;
@@ -1040,6 +1049,10 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
                 if (e->k1_wide) {
                     e->encode_tiled = (PFN_cuTensorMapEncodeTiled_v12000)fn;
                     e->k1w_max_teams = occ * e->sm_count / K1W_TEAM;
+                    if (const char *v = getenv("SDR_K1_WIDE_TEAMS")) {  // measurement: fewer teams than fit (e.g. one CTA per SM)
+                        const int t = atoi(v);
+                        if (t >= 1 && t < e->k1w_max_teams) e->k1w_max_teams = t;
+                    }
                     if (e->k1w_max_teams < 1) e->k1_wide = 0;
                 }
             }
@@ -1130,6 +1143,16 @@ void sdr_engine_destroy(sdr_engine *e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     cudaDeviceSynchronize();
+#ifdef SDR_K1W_TRACE
+    if (g_k1w_trace && getenv("SDR_K1_WIDE_TRACE")) {
+        std::vector<long long> h(K1W_TRACE_BYTES / sizeof(long long));
+        cudaMemcpy(h.data(), g_k1w_trace, K1W_TRACE_BYTES, cudaMemcpyDeviceToHost);
+        if (FILE *f = fopen(getenv("SDR_K1_WIDE_TRACE"), "wb")) {
+            fwrite(h.data(), 1, K1W_TRACE_BYTES, f);
+            fclose(f);
+        }
+    }
+#endif
     for (auto &s : e->slots) free_slot(s);
     cudaFree(e->d_tw1);
     cudaFree(e->d_tw2);

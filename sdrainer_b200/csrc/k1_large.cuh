@@ -183,12 +183,49 @@ static_assert(2 * HW_PITCH >= 512 + 32, "planes + skew must fit the row's own co
 __device__ __forceinline__ int plane_skew(int row_word0, int j) { return (2 * (j >> 1) + 16 * (j & 1) - row_word0) & 31; }
 
 // One thread's share of a noise-window sum (dsp/fft.go:226-236): the window's positions in one row, float32 inside the
-// share.  pp points at position P of the row, the same P for the sixteen rows of the half-warp (so their banks stay
-// beta(j) + const); the row's positions are the indices [lo, hi) with lo in {0, 1} and hi <= NFMAX - 1.  rot in {0, 1}
-// makes the lane walk its indices rotated by one (index i + rot, the last one wraps to 0): the upper half-warp uses it
-// when its P has the same parity as the lower one's, which puts the two halves on disjoint (even / odd) banks.
+// share.  base[off] is position P of the row, the same P for the sixteen rows of the half-warp (so their banks stay
+// beta(j) + const); the row's positions are the indices [lo, hi) with lo in {0, 1}.  A window has m = ws / stride or
+// m + 1 positions in every row (m: the caller's uniform minimum, clamped to >= 2), hence hi <= m + 2 and the indices
+// 1 .. m - 1 are inside the window for EVERY lane: they are read without a per-lane test.  rot in {0, 1} makes the lane
+// walk that body rotated by one (index i + rot in step i): the upper half-warp uses it when its P has the parity of the
+// lower one's, which puts the two halves on disjoint (even / odd) banks.  The at most four remaining indices
+// (0, m - 1 or 1, m, m + 1) are tested against [lo, hi).
+template <int M_MAX>
+__device__ __forceinline__ void nf_row_share(const float *base, int off, int lo, int hi, int rot, int m, float &s1, float &s2) {
+    int o = off + rot;
+    asm volatile("" : "+r"(o));  // one address register for the whole body (otherwise re-derived under every predicate)
+    const float *pr = base + o;
+    float2 a1 = make_float2(0.f, 0.f), a2 = a1, b1 = a1, b2 = a1;
+#pragma unroll
+    for (int i = 1; i <= M_MAX - 2; i += 4) {  // body: steps 1 .. m - 2 (uniform bound), two packed chains
+        const float x0 = (i <= m - 2) ? pr[i] : 0.f, x1 = (i + 1 <= m - 2) ? pr[i + 1] : 0.f;
+        const float x2 = (i + 2 <= m - 2) ? pr[i + 2] : 0.f, x3 = (i + 3 <= m - 2) ? pr[i + 3] : 0.f;
+        const float2 p = make_float2(x0, x1), q = make_float2(x2, x3);
+        a1 = __fadd2_rn(a1, p);
+        a2 = __ffma2_rn(p, p, a2);
+        b1 = __fadd2_rn(b1, q);
+        b2 = __ffma2_rn(q, q, b2);
+    }
+    const float *pp = base + off;
+    const int t1 = rot ? 1 : m - 1;
+    const float y0 = (lo == 0 && hi > 0) ? pp[0] : 0.f;
+    const float y1 = (t1 >= lo && t1 < hi) ? pp[t1] : 0.f;
+    const float y2 = (m < hi) ? pp[m] : 0.f;
+    const float y3 = (m + 1 < hi) ? pp[m + 1] : 0.f;
+    const float2 p = make_float2(y0, y1), q = make_float2(y2, y3);
+    a1 = __fadd2_rn(a1, p);
+    a2 = __ffma2_rn(p, p, a2);
+    b1 = __fadd2_rn(b1, q);
+    b2 = __ffma2_rn(q, q, b2);
+    s1 = (a1.x + a1.y) + (b1.x + b1.y);
+    s2 = (a2.x + a2.y) + (b2.x + b2.y);
+}
+
+// The same share with every index tested per lane, scalar chains (k1_mid8k2: measured 2.7 % faster there than the packed
+// form above, which costs that kernel eight more bytes of spill at its 128-register cap).  Indices [lo, hi), hi <= NFMAX - 1;
+// rot as above (index i + rot, the last one wraps to 0).
 template <int NFMAX>
-__device__ __forceinline__ void nf_row_share(const float *pp, int lo, int hi, int rot, float &s1, float &s2) {
+__device__ __forceinline__ void nf_row_share_tested(const float *pp, int lo, int hi, int rot, float &s1, float &s2) {
     static_assert(NFMAX % 2 == 0, "pairs");
     const float *pr = pp + rot;
     const int hi_r = hi - rot;  // i + rot < hi  <=>  i < hi_r

@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(512, 1) k1_mid8k2_kernel(const K1Args a, const
             // ---------------- dsp.FindNoiseFloor (dsp/fft.go:215-252): this group's share of the window sums ----------------
             if (wg < 5) {
                 float s1, s2;
-                nf_row_share<28>(Ef + plane_of(nf_row) + nf_p, nf_lo, nf_hi, nf_rot, s1, s2);  // <= 26 positions per row, + 1, even
+                nf_row_share_tested<28>(Ef + plane_of(nf_row) + nf_p, nf_lo, nf_hi, nf_rot, s1, s2);  // <= 26 positions per row, + 1, even
                 double d1 = (double)s1, d2 = (double)s2;
 #pragma unroll
                 for (int o = 8; o > 0; o >>= 1) {

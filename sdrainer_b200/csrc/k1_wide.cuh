@@ -13,17 +13,19 @@
 //     the intermediate, 32 KB contiguous, one cp.async.bulk) -> half-warp 256-point transforms -> |X|^2, dB, cumulation
 //     in registers (16 bins per thread for the whole segment), this CTA's share of the ten noise-window sums, x_to, its
 //     taps; the tile's lines are then discarded from L2 (they are dead until the slot is rewritten);
-//   * warps 0-7 compute; warp 8 is the DMA warp: it owns every wait on another CTA, every TMA issue and every
-//     publication, the compute warps only wait on shared-memory mbarriers;
+//   * warps 0-7 compute; warps 8 and 9 (one lane each) are the DMA warps: they own every wait on another CTA, every TMA
+//     issue and every publication, the compute warps only wait on shared-memory mbarriers.  Warp 8 stores and publishes
+//     what the CTA produces (and refills A), warp 9 requests what it consumes;
 //   * a global counter per step (`ready`) is released by each producer's DMA thread after its tile store has completed
 //     and acquired by each consumer's DMA thread before it requests the row tile: the only inter-CTA synchronisation.
 //     All CTAs of the launch are co-resident (cooperative launch) and every wait is on work of EARLIER steps only:
-//       - step j is produced in iteration j - D + 1 and published right after its store completes; its row tile is
-//         requested in iteration j - 1 (after B was read there), i.e. D - 2 >= 1 iterations later: no CTA waits on
-//         itself, the team only has to stay within D - 2 iterations of each other;
-//       - ring safety: when a CTA stores step j = i + D - 1 (iteration i) it has seen ready[i] complete, so every
-//         team mate finished producing step i, i.e. finished CONSUMING steps <= i - D and may have the row tile of step
-//         i - D + 1 in flight; the slot's previous occupant is step j - R, safe iff j - R <= i - D, i.e. R >= 2 D - 1.
+//       - step j is produced in iteration j - D + 1 and published as soon as its store completes; its row tile is
+//         requested in iteration j - 1 (once B was read there), D - 2 >= 1 iterations later: the team only has to stay
+//         within D - 2 iterations of each other;
+//       - ring safety: a CTA produces step j = i + D - 1 at the start of iteration i, after it consumed step i - 1, i.e.
+//         after ready[i - 1] was complete: every team mate had produced step i - 1, which it does once it has consumed
+//         (read into registers) every step <= i - D - 1; the row tiles of later steps may be in flight there.  The
+//         slot's previous occupant is step j - R: safe iff j - R <= i - D - 1, i.e. R >= 2 D.
 //     Waits are bounded all the same and report through `err` (sdr_collect turns it into SDR_ECUDA).
 // HBM sees the IQ once (8 N per block), the ten partial window sums per CTA and block, and the cumulation once per 100
 // blocks; the intermediate (8 N written + 8 N read per block) is L2 traffic: R x 512 KB per team.
@@ -56,9 +58,20 @@ struct WideArgs {
     int *nf_edge;                 // [blocks]
     float db_offset;              // 10*log10(20/N^2)
     int lookahead;                // D >= 3: step i + D - 1 is produced in iteration i; its row tile is requested in iteration i + D - 2
-    int ring;                     // R >= 2 D - 1 slots per team
+    int ring;                     // R >= 2 D slots per team
     int discard;                  // drop consumed row tiles from L2 (discard.global.L2) instead of letting them be written back
+#ifdef SDR_K1W_TRACE
+    long long *trace;             // [32 CTAs][512 steps][32] clock64 stamps (tools/wide_trace.py), measurement builds only
+#endif
 };
+#ifdef SDR_K1W_TRACE
+#define K1W_TR(step, slot)                                                                                  \
+    do {                                                                                                    \
+        if (wa.trace && blockIdx.x < 32 && (step) < 512) wa.trace[((size_t)blockIdx.x * 512 + (step)) * 32 + (slot)] = clock64(); \
+    } while (0)
+#else
+#define K1W_TR(step, slot) do { } while (0)
+#endif
 
 constexpr int K1W_OFF_A = 0;                                   // IQ column tile, later the outgoing tile (1024-byte aligned: 128B swizzle)
 constexpr int K1W_OFF_B = K1W_OFF_A + K1W_TILE_BYTES;          // row tile of the intermediate
@@ -68,8 +81,8 @@ constexpr int K1W_OFF_TW = K1W_OFF_S + 16 * K1W_PITCH_P * 8;  // [15][16] W_256^
 constexpr int K1W_OFF_TQ = K1W_OFF_TW + 256 * 8;             // [16][17] W_N^(16 c q)
 constexpr int K1W_OFF_MISC = K1W_OFF_TQ + 16 * 17 * 8;
 constexpr int K1W_SMEM_BYTES = K1W_OFF_MISC + 128;
-constexpr int K1W_NFMAX = 28;                                  // positions of one noise window in one row: ceil(6553 / 256) = 26, + 1 (common start), even
-constexpr int K1W_THREADS = 288;                               // eight compute warps + the DMA warp
+constexpr int K1W_NF_M = 25;                                   // whole positions of one noise window in one row: 6553 / 256
+constexpr int K1W_THREADS = 320;                               // eight compute warps + the two DMA warps
 
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
     uint64_t p;
@@ -136,7 +149,14 @@ __device__ __forceinline__ void discard_l2_line(const void *p) { asm volatile("d
 //   FULL_B   tx barrier: the row tile of the intermediate has landed in B (DMA -> compute)
 //   OUT_RDY  256 arrivals: the outgoing tile is complete in A           (compute -> DMA: store it)
 //   B_FREE   256 arrivals: B has been read into registers               (compute -> DMA: refill it)
-__global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs wa) {
+#ifndef SDR_K1WIDE_MINB
+#define SDR_K1WIDE_MINB 2
+#endif
+#ifdef SDR_K1W_MAXNREG
+__global__ void __maxnreg__(SDR_K1W_MAXNREG) k1_wide_kernel(const WideArgs wa) {
+#else
+__global__ void __launch_bounds__(K1W_THREADS, SDR_K1WIDE_MINB) k1_wide_kernel(const WideArgs wa) {
+#endif
     constexpr int N = 65536, N1 = 256;
     const K1Args &a = wa.a;
     extern __shared__ __align__(1024) unsigned char wd_smem[];
@@ -167,62 +187,72 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
     __syncthreads();
 
     if (tid >= 256) {
-        // ================================ DMA warp ================================
-        if (tid != 256) return;
-        tensormap_acquire(wa.tmp_map);
-        const uint64_t policy = l2_evict_first_policy();
-        WideIter jc, jp, ja, jb;
-        jc.start(a.segs, a.n_segs, team);
-        jp = ja = jb = jc;
-        uint32_t ph_out = 0, ph_free = 0;
-        auto issue_a = [&]() {  // IQ column tile of the next step to produce (A is free)
-            if (ja.nb == 0) return;
-            if (ja.blk == 0) tensormap_acquire(&wa.seg_maps[ja.seg]);  // first use of this segment's map
-            mbar_expect_tx(FULL_A, K1W_TILE_BYTES);
-            tma_load_tile_3d(A, &wa.seg_maps[ja.seg], 2 * c0, 0, ja.blk, FULL_A, policy);
-            ja.next(a.segs, a.n_segs, n_teams);
-        };
-        auto issue_b = [&]() {  // row tile of the next step to consume, once all sixteen column tiles are published
-            if (jb.nb == 0) return;
-            const int ob = a.segs[jb.seg].block_out + jb.blk;
-            int spins = 0;
-            while (ld_acquire_gpu(&wa.ready[ob]) < K1W_TEAM) {
-                ++spins;
-                if (spins > K1W_MAX_SPIN || ((spins & 1023) == 0 && ld_acquire_gpu(wa.err) != 0)) {  // give up; once one wait failed, all do
-                    atomicExch(wa.err, 1);
-                    break;
-                }
-                __nanosleep(32);
+        // ================================ DMA warps ================================
+        // Warp 8 (lane 0) moves the tiles this CTA PRODUCES: it stores the outgoing tile, refills A as soon as the store has
+        // read it, and publishes the step once the store has completed.  Warp 9 (lane 0) fetches the tiles this CTA
+        // CONSUMES: it waits until B has been read, until all sixteen producers have published the next step, and requests
+        // the row tile.  They are two threads because each chain is long and serial (measured on B200, SM cycles: tile read
+        // out of A 2200, release of the counter 1500; acquire poll of the counter 1900, tile landing 1800): one thread
+        // running both requested the row tile 6000 cycles after the produce phase ended, exactly when it was needed.
+        if (tid == 256) {
+            tensormap_acquire(wa.tmp_map);
+            const uint64_t policy = l2_evict_first_policy();
+            WideIter jp, ja;
+            jp.start(a.segs, a.n_segs, team);
+            ja = jp;
+            uint32_t ph_out = 0;
+            auto issue_a = [&]() {  // IQ column tile of the next step to produce (A is free)
+                if (ja.nb == 0) return;
+                if (ja.blk == 0) tensormap_acquire(&wa.seg_maps[ja.seg]);  // first use of this segment's map
+                mbar_expect_tx(FULL_A, K1W_TILE_BYTES);
+                tma_load_tile_3d(A, &wa.seg_maps[ja.seg], 2 * c0, 0, ja.blk, FULL_A, policy);
+                ja.next(a.segs, a.n_segs, n_teams);
+            };
+            issue_a();
+            while (jp.nb != 0) {  // the compute warps finished producing step jp
+                mbar_wait(OUT_RDY, ph_out);
+                ph_out ^= 1u;
+                K1W_TR(jp.step, 10);
+                fence_proxy_async_all();  // consumers' discards of the slot's old lines (generic proxy) before this async-proxy write
+                tma_store_tile_3d(wa.tmp_map, 2 * c0, 0, team * R + jp.step % R, A);
+                bulk_commit();
+                bulk_wait_read();  // the tile has been read out of A ...
+                K1W_TR(jp.step, 11);
+                issue_a();         // ... which takes the next column tile at once
+                bulk_wait_all();   // the store has completed: publish the step
+                K1W_TR(jp.step, 12);
+                red_release_gpu_add(&wa.ready[a.segs[jp.seg].block_out + jp.blk], 1);
+                K1W_TR(jp.step, 13);
+                jp.next(a.segs, a.n_segs, n_teams);
             }
-            fence_proxy_async_all();  // the acquire above orders the async-proxy read below after the producers' stores
-            mbar_expect_tx(FULL_B, K1W_TILE_BYTES);
-            tma_load_1d(wd_smem + K1W_OFF_B, wa.tmp + ((size_t)(team * R + jb.step % R) * N + (size_t)r0 * 256), K1W_TILE_BYTES, FULL_B);
-            jb.next(a.segs, a.n_segs, n_teams);
-        };
-        auto store_and_publish = [&]() {  // the compute warps finished producing step jp
-            mbar_wait(OUT_RDY, ph_out);
-            ph_out ^= 1u;
-            fence_proxy_async_all();  // consumers' discards of the slot's old lines (generic proxy) before this async-proxy write
-            tma_store_tile_3d(wa.tmp_map, 2 * c0, 0, team * R + jp.step % R, A);
-            bulk_commit();
-            bulk_wait_read();  // the tile has been read out of A ...
-            issue_a();         // ... which takes the next column tile at once
-            bulk_wait_all();   // the store has completed: publish the step
-            red_release_gpu_add(&wa.ready[a.segs[jp.seg].block_out + jp.blk], 1);
-            jp.next(a.segs, a.n_segs, n_teams);
-        };
-        issue_a();
-        for (int d = 0; d + 1 < D; d++) {  // prologue: D - 1 steps are produced before anything is consumed
-            if (jp.nb == 0) break;
-            store_and_publish();
-        }
-        issue_b();
-        while (jc.nb != 0) {
-            if (jp.nb != 0) store_and_publish();
-            mbar_wait(B_FREE, ph_free);
-            ph_free ^= 1u;
-            issue_b();
-            jc.next(a.segs, a.n_segs, n_teams);
+        } else if (tid == 288) {
+            WideIter jb;
+            jb.start(a.segs, a.n_segs, team);
+            uint32_t ph_free = 0;
+            bool first = true;
+            while (jb.nb != 0) {  // row tile of the next step to consume, once all sixteen column tiles are published
+                if (!first) {     // B has been read into registers
+                    mbar_wait(B_FREE, ph_free);
+                    ph_free ^= 1u;
+                    K1W_TR(jb.step - 1, 14);
+                }
+                first = false;
+                const int ob = a.segs[jb.seg].block_out + jb.blk;
+                int spins = 0;
+                while (ld_acquire_gpu(&wa.ready[ob]) < K1W_TEAM) {
+                    ++spins;
+                    if (spins > K1W_MAX_SPIN || ((spins & 1023) == 0 && ld_acquire_gpu(wa.err) != 0)) {  // give up; once one wait failed, all do
+                        atomicExch(wa.err, 1);
+                        break;
+                    }
+                    __nanosleep(64);
+                }
+                fence_proxy_async_all();  // the acquire above orders the async-proxy read below after the producers' stores
+                K1W_TR(jb.step, 15);
+                mbar_expect_tx(FULL_B, K1W_TILE_BYTES);
+                tma_load_1d(wd_smem + K1W_OFF_B, wa.tmp + ((size_t)(team * R + jb.step % R) * N + (size_t)r0 * 256), K1W_TILE_BYTES, FULL_B);
+                jb.next(a.segs, a.n_segs, n_teams);
+            }
         }
         return;
     }
@@ -253,8 +283,10 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
 
     // ---------------- produce: column tile of step ip -> outgoing tile in A ----------------
     auto produce = [&]() {
+        if (tid == 0) K1W_TR(ip.step, 0);
         mbar_wait(FULL_A, phase_a);
         phase_a ^= 1u;
+        if (tid == 0) K1W_TR(ip.step, 1);
         float2 v[16];
 #pragma unroll
         for (int q = 0; q < 16; q++) {
@@ -269,6 +301,7 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
             }
         }
         compute_sync();  // the tile is in registers: A can take the outgoing tile; S is free (consume's plane reads are done)
+        if (tid == 0) K1W_TR(ip.step, 2);
         {
             HwTwiddle t;
             load_hw_twiddle(t, hlp);
@@ -281,6 +314,7 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
         }
         fence_proxy_async();  // generic-proxy writes of the tile before the async-proxy (TMA) read
         mbar_arrive(OUT_RDY);
+        if (tid == 0) K1W_TR(ip.step, 3);
         ip.next(a.segs, a.n_segs, n_teams);
     };
 
@@ -290,7 +324,7 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
     }
 
     float cum[16];
-    int e = 0, ws = 1, n_win = 9, L = 0, nf_p = 0, nf_lo = 0, nf_hi = 0, nf_rot = 0;
+    int e = 0, ws = 1, n_win = 9, L = 0, nf_p = 0, nf_lo = 0, nf_hi = 0, nf_rot = 0, seg_block_out = 0;
     // S belongs to the warps in private slices of 2 * K1W_PITCH_P complex slots (no barrier separates one warp's produce
     // transposes from another warp's consume transposes): produce puts its two columns at pitch K1W_PITCH_P, consume at
     // pitch HW_PITCH inside the same slice.  The |X|^2 / dB planes of row j start at word plane_of(j) of S, inside the
@@ -302,8 +336,10 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
     while (ic.nb != 0) {
         // produce step ic + D - 1 first: its store then has the whole consume phase to complete and be published
         if (ip.nb != 0) produce();
-        const Segment sg = a.segs[ic.seg];
+        if (tid == 0) K1W_TR(ic.step, 20);
         if (ic.blk == 0) {  // a new segment: window geometry, listeners, cumulation registers
+            const Segment sg = a.segs[ic.seg];
+            seg_block_out = sg.block_out;
             const WorkParams wp = a.works[sg.work];
             e = wp.edge_width;
             ws = nf_window_size(N, e);
@@ -332,11 +368,13 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
                 cum[p] = sg.state_in >= 0 ? a.cum_state[(size_t)sg.state_in * N + kk] : 0.f;
             }
         }
-        const int ob = sg.block_out + ic.blk;
+        const int ob = seg_block_out + ic.blk;
 
         // ---------------- consume: row tile of step ic ----------------
+        if (tid == 0) K1W_TR(ic.step, 4);
         mbar_wait(FULL_B, phase_b);
         phase_b ^= 1u;
+        if (tid == 0) K1W_TR(ic.step, 5);
         float2 v[16];
 #pragma unroll
         for (int q = 0; q < 16; q++) {
@@ -369,7 +407,9 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
             prow[k2s] = psd;
             if (need_db) prow[256 + k2s] = db;  // only the taps (and the parity store) read the dB plane
         }
+        if (tid == 0) K1W_TR(ic.step, 6);
         compute_sync();
+        if (tid == 0) K1W_TR(ic.step, 7);
         const float *Sf = reinterpret_cast<const float *>(S);  // row j of the tile: Sf[plane_of(j) + (0 | 256) + k2s]
         if (a.dbg_psd) {  // parity / scope only: half-warp = 16 consecutive bins
 #pragma unroll
@@ -386,15 +426,18 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
         if (warp < 5) {
             const int w = 2 * warp + (lane >> 4);
             float s1, s2;
-            nf_row_share<K1W_NFMAX>(Sf + plane_of(lane & 15) + nf_p, nf_lo, nf_hi, nf_rot, s1, s2);
+            nf_row_share<K1W_NF_M>(Sf, plane_of(lane & 15) + nf_p, nf_lo, nf_hi, nf_rot, max(ws >> 8, 2), s1, s2);
+            if (tid == 0) K1W_TR(ic.step, 16);
             double d1 = (double)s1, d2 = (double)s2;
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) {
                 d1 += __shfl_xor_sync(0xffffffffu, d1, o);
                 d2 += __shfl_xor_sync(0xffffffffu, d2, o);
             }
+            if (tid == 0) K1W_TR(ic.step, 17);
             if ((lane & 15) == 0) wa.nf_part[((size_t)ob * K1W_TEAM + rank) * 10 + w] = make_double2(d1, d2);
         }
+        if (tid == 0) K1W_TR(ic.step, 18);
         if (tid < n_win) {  // x_to = psd[e + (w+1)*ws] (dsp/fft.go:238-243) if this CTA owns that bin
             const int kk = e + (tid + 1) * ws;
             const int k1 = kk & (N1 - 1);
@@ -406,7 +449,9 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
             const int k1 = kk & (N1 - 1);
             if (k1 >= r0 && k1 < r0 + 16) a.taps[(size_t)ob * a.tap_stride + l] = Sf[plane_of(k1 - r0) + 256 + (kk >> 8)];
         }
-        if (ic.blk == sg.n_blocks - 1) {  // end of the segment: flush or save the cumulation
+        if (tid == 0) K1W_TR(ic.step, 19);
+        if (ic.blk == ic.nb - 1) {  // end of the segment: flush or save the cumulation
+            const Segment sg = a.segs[ic.seg];
             float *dst = (sg.flush_idx >= 0) ? a.flush_cum + (size_t)sg.flush_idx * N : a.cum_state + (size_t)sg.state_out * N;
 #pragma unroll
             for (int p = 0; p < 16; p++) dst[(r0 + f) + N1 * ((hl + 16 * OutIdx<16>::of(p) + 128) & 255)] = cum[p];
@@ -415,6 +460,8 @@ __global__ void __launch_bounds__(K1W_THREADS, 2) k1_wide_kernel(const WideArgs 
         // barrier (after the column-tile reads, before the transform) already orders that, and the warps without
         // window-sum work start reading the next column tile meanwhile; only a consume that follows directly needs one.
         if (ip.nb == 0) compute_sync();
+        if (tid == 0) K1W_TR(ic.step, 8);
+        if (tid == 255) K1W_TR(ic.step, 9);
         ic.next(a.segs, a.n_segs, n_teams);
     }
 }

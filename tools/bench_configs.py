@@ -36,7 +36,7 @@ CASES = [
     ("cfg3 768 kS/s N=8192 L=200, 64 streams (r1 two-kernel large-block path)", 8192, 768000, 200, 64, 100, {"SDR_K1_MID8K": "0"}),
     ("cfg5 24.576 MS/s N=65536 peak scan, 64 streams", 65536, 24576000, 0, 64, 100),
     ("cfg5 24.576 MS/s N=65536 peak scan, 72 streams, lookahead 4", 65536, 24576000, 0, 72, 100, {"SDR_K1_WIDE_LOOKAHEAD": "4"}),
-    ("cfg5 24.576 MS/s N=65536 peak scan, 72 streams, ring 5", 65536, 24576000, 0, 72, 100, {"SDR_K1_WIDE_RING": "5"}),
+    ("cfg5 24.576 MS/s N=65536 peak scan, 72 streams, ring 8", 65536, 24576000, 0, 72, 100, {"SDR_K1_WIDE_RING": "8"}),
     ("cfg5 24.576 MS/s N=65536 peak scan, 72 streams, no discard", 65536, 24576000, 0, 72, 100, {"SDR_K1_WIDE_DISCARD": "0"}),
     ("cfg5 24.576 MS/s N=65536 peak scan, 72 streams (4 whole rounds of 18 teams)", 65536, 24576000, 0, 72, 100),
     ("cfg5 24.576 MS/s N=65536 peak scan, 64 streams (r1 two-kernel path)", 65536, 24576000, 0, 64, 100, {"SDR_K1_WIDE": "0"}),
