@@ -1363,6 +1363,7 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     size_t iq_off = 0;  // floats into d_iq
     std::vector<StreamInfo> new_state(n_works);
     int max_work_blocks = 1;
+    bool any_debounce = false;  // a work with a real debouncer (SetSignalDebounce >= 2): k2_debounce_kernel runs too
     bool warp_ok = (N == 512);        // ... and for k1_warp_kernel
     const float *pend_src = nullptr;  // pending coalesced H2D copy
     float *pend_dst = nullptr;
@@ -1414,6 +1415,7 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
         pw.n_listeners = wk.n_listeners;
         pw.do_peaks = (flags & SDR_NO_PEAKS) ? 0 : 1;
         pw.debounce = wk.signal_debounce;
+        if (wk.signal_debounce >= 2) any_debounce = true;
         pw.lflags_off = wk.listener_flags ? lb_off : -1;
         pw.pad = 0;
         lb_off += wk.n_listeners;
@@ -1563,6 +1565,7 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     NvtxRange nvtx_k2("K2 post (thresholds, keys, peaks) + D2H");
     K2Args a2;
     a2.works = reinterpret_cast<const PostWork *>(s.d_desc + dl.post);
+    a2.n_works = n_works;
     a2.rolling = e->d_rolling;
     a2.psd_floor = s.d_psd_floor;
     a2.variance = s.d_variance;
@@ -1583,7 +1586,7 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     if (e->s_post != e->s_compute) CK(e, cudaStreamWaitEvent(e->s_post, s.ev_km, 0));
     CK(e, cudaEventRecord(s.ev_k2s, e->s_post));
     int k2_launches = 2;
-    k2_thresholds_kernel<<<n_works, K2_THREADS, 0, e->s_post>>>(a2);
+    k2_thresholds_kernel<<<(n_works + K2_WARPS - 1) / K2_WARPS, K2_THREADS, 0, e->s_post>>>(a2);
     CK(e, cudaGetLastError());
     // keys and peaks both depend on the thresholds only: the peak scan goes to a side stream so that the two small,
     // latency-bound grids share the GPU instead of running back to back
@@ -1594,16 +1597,22 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
         k2_peaks_kernel<<<n_flushes, K2_THREADS, 0, e->s_aux>>>(a2);
         CK(e, cudaGetLastError());
         CK(e, cudaEventRecord(s.ev_peaks, e->s_aux));
-        k2_launches = 3;
+        k2_launches++;
     }
-    k2_keys_kernel<<<dim3((max_work_blocks + K2_KEY_ROWS - 1) / K2_KEY_ROWS, n_works), K2_THREADS, 0, e->s_post>>>(a2);
+    k2_keys_kernel<<<dim3((max_work_blocks + K2_KEY_ROWS - 1) / K2_KEY_ROWS, (n_works + K2_WARPS - 1) / K2_WARPS), K2_THREADS, 0,
+                     e->s_post>>>(a2);
     CK(e, cudaGetLastError());
+    if (any_debounce) {
+        k2_debounce_kernel<<<n_works, K2_THREADS, 0, e->s_post>>>(a2);
+        CK(e, cudaGetLastError());
+        k2_launches++;
+    }
     if (do_peaks && e->s_aux) {
         CK(e, cudaStreamWaitEvent(e->s_post, s.ev_peaks, 0));
     } else if (do_peaks) {
         k2_peaks_kernel<<<n_flushes, K2_THREADS, 0, e->s_post>>>(a2);
         CK(e, cudaGetLastError());
-        k2_launches = 3;
+        k2_launches++;
     }
     CK(e, cudaEventRecord(s.ev_k1, e->s_post));
     CK(e, cudaEventRecord(e->ev_post, e->s_post));

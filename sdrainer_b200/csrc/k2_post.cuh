@@ -49,6 +49,7 @@ struct PostWork {
 
 struct K2Args {
     const PostWork *works;
+    int n_works;
     RollingState *rolling;      // [max_streams]
     const float *psd_floor;     // [blocks]
     const double *variance;     // [blocks]
@@ -69,8 +70,9 @@ struct K2Args {
 };
 
 // dsp.PSDValueIndB (dsp/fft.go:83-85) + dBmShift as a float32 add (rx/receiver.go:383-384)
-__device__ __forceinline__ float psd_value_in_db_shifted(float psd_value, double n2) {
-    const float db = (float)(10.0 * log10(20.0 * (double)psd_value / n2));
+// inv_n2 = 1 / N^2: N is a power of two, so the product equals the reference's quotient bit for bit (no float64 divide)
+__device__ __forceinline__ float psd_value_in_db_shifted(float psd_value, double inv_n2) {
+    const float db = (float)(10.0 * log10(20.0 * (double)psd_value * inv_n2));
     return __fadd_rn(db, (float)SDR_DBM_SHIFT);
 }
 
@@ -195,94 +197,208 @@ __device__ void find_peaks_block(const float *__restrict__ cum, int n, float cum
 }
 
 // K2 is three launches so that every stage has its own parallelism (a launch with few streams but many blocks -- 64
-// receivers, 21 s each -- must not collapse onto a handful of CTAs):
-//   k2_thresholds_kernel  one CTA per work: the two rolling means (inherently sequential per stream) and the thresholds
-//   k2_keys_kernel        one CTA per (work, 64 blocks): value > threshold for every listener, packed by warp ballot
+// receivers, 21 s each -- must not collapse onto a handful of CTAs, and one with thousands of short works -- 7 104
+// streams of 100 blocks at N = 512 -- must not pay a CTA per work):
+//   k2_thresholds_kernel  one WARP per work: the two rolling means (inherently sequential per stream) and the thresholds
+//   k2_keys_kernel        one WARP per (work, 64 blocks): value > threshold for every listener, bit-packed
+//   k2_debounce_kernel    (only when a work has a real debouncer) one CTA per such work, sequential over its blocks
 //   k2_peaks_kernel       one CTA per flush: dsp.FindPeaks
+constexpr int K2_WARPS = K2_THREADS / 32;
+constexpr int K2_WCHUNK = 128;  // blocks staged in shared memory per pass of a warp (four per lane)
 
+// dsp.RollingMean.Put (dsp/dsp.go:257-268) is sum = fl(fl(sum - oldest) + new) per block, float32, in block order: only
+// that two-operation chain is sequential.  The value that falls out of the 60-deep ring at step i is known up front (the
+// ring's content for i < 60, the input of step i - 60 afterwards), so the lanes stage inputs and outgoing values in
+// parallel and lanes 0 / 1 walk the two chains (noise floor / deviation) over plain arrays.
 __global__ void __launch_bounds__(K2_THREADS) k2_thresholds_kernel(const K2Args a) {
-    __shared__ float s_floor[K2_CHUNK];
-    __shared__ float s_dev[K2_CHUNK];
-    __shared__ RollingState s_roll;
-    const PostWork w = a.works[blockIdx.x];
-    const int tid = threadIdx.x;
-    const double n2 = (double)a.n * (double)a.n;
+    __shared__ float s_in_all[K2_WARPS][2][K2_WCHUNK];   // inputs of the two means
+    __shared__ float s_run_all[K2_WARPS][2][K2_WCHUNK];  // outgoing ring values, then the running sums
+    __shared__ RollingState s_roll_all[K2_WARPS];
+    const int wq = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wi = blockIdx.x * K2_WARPS + wq;
+    if (wi >= a.n_works) return;  // warp-uniform; nothing below synchronises across warps
+    float (*s_in)[K2_WCHUNK] = s_in_all[wq];
+    float (*s_run)[K2_WCHUNK] = s_run_all[wq];
+    RollingState &s_roll = s_roll_all[wq];
+    const PostWork w = a.works[wi];
+    const double n2 = 1.0 / ((double)a.n * (double)a.n);  // exact: N is a power of two
+    constexpr int RW = (int)(sizeof(RollingState) / 4), RPL = (RW + 31) / 32;
 
-    {  // all threads copy the stream's rolling state (124 words) instead of one thread walking it
+    {  // the lanes copy the stream's rolling state (124 words), all loads in flight at once
         const uint32_t *src = reinterpret_cast<const uint32_t *>(a.rolling + w.stream);
         uint32_t *dst = reinterpret_cast<uint32_t *>(&s_roll);
-        for (int i = tid; i < (int)(sizeof(RollingState) / 4); i += K2_THREADS) dst[i] = src[i];
+        uint32_t r[RPL];
+#pragma unroll
+        for (int k = 0; k < RPL; k++) r[k] = (lane + 32 * k < RW) ? src[lane + 32 * k] : 0u;
+#pragma unroll
+        for (int k = 0; k < RPL; k++)
+            if (lane + 32 * k < RW) dst[lane + 32 * k] = r[k];
     }
     // flushes of this work (rx/receiver.go:409-425): which block closed each window
-    for (int f = tid; f < w.n_flushes; f += K2_THREADS) {
+    for (int f = lane; f < w.n_flushes; f += 32) {
         a.flush_block[w.flush_out + f] = w.block_out + w.first_flush_block + f * SDR_CUMULATION_SIZE;
         if (!w.do_peaks) a.flush_n_peaks[w.flush_out + f] = 0;
     }
-    __syncthreads();
+    __syncwarp();
 
-    for (int c0 = 0; c0 < w.n_blocks; c0 += K2_CHUNK) {
-        const int cn = min(K2_CHUNK, w.n_blocks - c0);
-        // phase A (parallel): inputs of the two rolling means (rx/receiver.go:383-384)
-        for (int i = tid; i < cn; i += K2_THREADS) {
-            const int b = w.block_out + c0 + i;
-            const float psd_noise_floor = a.psd_floor[b];
-            const double var = a.variance[b];
-            // T(float64(PSDValueIndB(T(math.Sqrt(var)), N) + dBmShift) * 0.25)
-            const float dev_db = psd_value_in_db_shifted((float)sqrt(var), n2);
-            s_dev[i] = (float)((double)dev_db * 0.25);
-            s_floor[i] = psd_value_in_db_shifted(psd_noise_floor, n2);
-        }
-        __syncthreads();
-        // phase B (sequential, float32, block order): dsp.RollingMean.Put (dsp/dsp.go:257-268)
-        if (tid == 0) {
-            float fs = s_roll.floor_sum, ds = s_roll.dev_sum;
-            int next = s_roll.next;
-            for (int i = 0; i < cn; i++) {
-                fs = __fsub_rn(fs, s_roll.floor_values[next]);
-                s_roll.floor_values[next] = s_floor[i];
-                fs = __fadd_rn(fs, s_floor[i]);
-                ds = __fsub_rn(ds, s_roll.dev_values[next]);
-                s_roll.dev_values[next] = s_dev[i];
-                ds = __fadd_rn(ds, s_dev[i]);
-                next = (next + 1 == SDR_NOISE_WINDOW) ? 0 : next + 1;
-                s_floor[i] = fs;
-                s_dev[i] = ds;
+    for (int c0 = 0; c0 < w.n_blocks; c0 += K2_WCHUNK) {
+        const int cn = min(K2_WCHUNK, w.n_blocks - c0);
+        // phase A (parallel): inputs of the two rolling means (rx/receiver.go:383-384); every lane's loads first
+        {
+            float pf[K2_WCHUNK / 32];
+            double vr[K2_WCHUNK / 32];
+#pragma unroll
+            for (int k = 0; k < K2_WCHUNK / 32; k++) {
+                const int i = lane + 32 * k;
+                pf[k] = i < cn ? a.psd_floor[w.block_out + c0 + i] : 1.f;
+                vr[k] = i < cn ? a.variance[w.block_out + c0 + i] : 1.0;
             }
-            s_roll.floor_sum = fs;
-            s_roll.dev_sum = ds;
-            s_roll.next = next;
+#pragma unroll
+            for (int k = 0; k < K2_WCHUNK / 32; k++) {
+                const int i = lane + 32 * k;
+                if (i < cn) {
+                    // T(float64(PSDValueIndB(T(math.Sqrt(var)), N) + dBmShift) * 0.25)
+                    const float dev_db = psd_value_in_db_shifted((float)sqrt(vr[k]), n2);
+                    s_in[1][i] = (float)((double)dev_db * 0.25);
+                    s_in[0][i] = psd_value_in_db_shifted(pf[k], n2);
+                }
+            }
         }
-        __syncthreads();
-        // phase C (parallel): means, thresholds (rx/receiver.go:384-385,394)
-        for (int i = tid; i < cn; i += K2_THREADS) {
+        __syncwarp();
+        // the value each step pushes out of the ring
+        const int next0 = s_roll.next;
+        for (int i = lane; i < cn; i += 32) {
+            int p = next0 + i;
+            if (p >= SDR_NOISE_WINDOW) p -= SDR_NOISE_WINDOW;
+            if (p >= SDR_NOISE_WINDOW) p -= SDR_NOISE_WINDOW;  // i < 128, next0 < 60: at most two wraps below index 60
+            s_run[0][i] = i < SDR_NOISE_WINDOW ? s_roll.floor_values[p] : s_in[0][i - SDR_NOISE_WINDOW];
+            s_run[1][i] = i < SDR_NOISE_WINDOW ? s_roll.dev_values[p] : s_in[1][i - SDR_NOISE_WINDOW];
+        }
+        __syncwarp();
+        // phase B (sequential, float32, block order): lane 0 the noise floor, lane 1 the deviation
+        if (lane < 2) {
+            float sum = lane == 0 ? s_roll.floor_sum : s_roll.dev_sum;
+            const float *in = s_in[lane];
+            float *run = s_run[lane];
+#pragma unroll 4
+            for (int i = 0; i < cn; i++) {
+                sum = __fadd_rn(__fsub_rn(sum, run[i]), in[i]);
+                run[i] = sum;
+            }
+            if (lane == 0) s_roll.floor_sum = sum;
+            else s_roll.dev_sum = sum;
+        }
+        __syncwarp();
+        // phase C (parallel): means, thresholds (rx/receiver.go:384-385,394); the ring takes the chunk's last 60 inputs
+        for (int i = lane; i < cn; i += 32) {
             const int b = w.block_out + c0 + i;
-            const float noise_floor = __fdiv_rn(s_floor[i], (float)SDR_NOISE_WINDOW);
-            const float noise_dev = __fdiv_rn(s_dev[i], (float)SDR_NOISE_WINDOW);
+            const float noise_floor = __fdiv_rn(s_run[0][i], (float)SDR_NOISE_WINDOW);
+            const float noise_dev = __fdiv_rn(s_run[1][i], (float)SDR_NOISE_WINDOW);
             float4 th;
             th.x = noise_floor;
             th.y = noise_dev;
             th.z = __fadd_rn(w.peak_threshold, noise_floor);
             th.w = __fadd_rn(noise_floor, noise_dev);  // the listeners' threshold (rx/receiver.go:394)
             reinterpret_cast<float4 *>(a.thresholds)[b] = th;
+            if (i >= cn - SDR_NOISE_WINDOW) {
+                const int p = (next0 + i) % SDR_NOISE_WINDOW;
+                s_roll.floor_values[p] = s_in[0][i];
+                s_roll.dev_values[p] = s_in[1][i];
+            }
         }
-        __syncthreads();
+        if (lane == 0) s_roll.next = (next0 + cn) % SDR_NOISE_WINDOW;
+        __syncwarp();
     }
     {
         uint32_t *dst = reinterpret_cast<uint32_t *>(a.rolling + w.stream);
         const uint32_t *src = reinterpret_cast<const uint32_t *>(&s_roll);
-        for (int i = tid; i < (int)(sizeof(RollingState) / 4); i += K2_THREADS) dst[i] = src[i];
+        for (int i = lane; i < RW; i += 32) dst[i] = src[i];
     }
 }
 
-constexpr int K2_KEY_ROWS = 64;  // blocks per CTA of the key kernel
+constexpr int K2_KEY_ROWS = 64;  // blocks per warp of the key kernel
 
-// Key states (cw/spectral.go:48-54): state := value > threshold, the listener's BoolDebouncer (dsp/dsp.go:164-182), one
-// warp ballot packs 32 listener positions of a block into a word.  grid = (ceil(max blocks of a work / 64), works).
-// Pass-through debouncers (threshold < 2, the reference's default) are stateless: every (block, 32 listeners) word is
-// independent.  A real debouncer is sequential per listener: CTA 0 of the work walks all its blocks in order, a warp
-// per 32 positions, the state carried per (stream, position) across submits.
+// Key states (cw/spectral.go:48-54): state := value > threshold, the listener's BoolDebouncer (dsp/dsp.go:164-182), 32
+// listener positions of a block packed into a word.  Pass-through debouncers (threshold < 2, the reference's default) are
+// stateless, every (block, 32 listeners) word is independent: k2_keys_kernel, grid = (ceil(max blocks of a work / 64),
+// ceil(works / 4)), one warp per (work, 64 blocks).  A real debouncer is sequential per listener: k2_debounce_kernel.
 __global__ void __launch_bounds__(K2_THREADS) k2_keys_kernel(const K2Args a) {
-    const PostWork w = a.works[blockIdx.y];
+    // The warp's 64 rows are one contiguous run of floats: every lane takes whole float4s (tap_stride is a multiple of
+    // four, so a float4 never straddles a row), eight of them in flight at once, compares four listeners per load and
+    // writes their raw key bytes as one 32-bit store; the packed words are put together through shared memory.
+    __shared__ float s_thr_all[K2_WARPS][K2_KEY_ROWS];
+    __shared__ uint8_t s_act_all[K2_WARPS][64];                   // per float4 of a row: which of its four positions are active
+    __shared__ uint8_t s_nib_all[K2_WARPS][K2_KEY_ROWS][64 + 4];  // four key bits per float4 of a row
+    const int wq = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wi = blockIdx.y * K2_WARPS + wq;
+    if (wi >= a.n_works) return;  // warp-uniform; nothing below synchronises across warps
+    const PostWork w = a.works[wi];
+    if (w.debounce >= 2) return;  // k2_debounce_kernel
+    const int row0 = blockIdx.x * K2_KEY_ROWS;
+    const int nrow = min(K2_KEY_ROWS, w.n_blocks - row0);
+    if (nrow <= 0) return;
+    float *s_thr = s_thr_all[wq];
+    uint8_t *s_act = s_act_all[wq];
+    uint8_t (*s_nib)[64 + 4] = s_nib_all[wq];
+    const int L = w.n_listeners;
+    const float *__restrict__ taps = a.taps + (size_t)w.block_out * a.tap_stride;
+    const float *__restrict__ thr = a.thresholds + (size_t)w.block_out * 4 + 3;  // listen threshold of block i at thr[4 i]
+    uint8_t *__restrict__ keys = a.keys ? a.keys + (size_t)w.block_out * a.tap_stride : nullptr;
+    uint32_t *__restrict__ kbits = a.key_bits + (size_t)w.block_out * a.key_words;
+    const int q4 = a.tap_stride >> 2;
+    for (int i = lane; i < nrow; i += 32) s_thr[i] = thr[(size_t)(row0 + i) * 4];
+    for (int c4 = lane; c4 < q4; c4 += 32) {
+        unsigned m = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int l = 4 * c4 + j;
+            if (l < L && (w.lflags_off < 0 || (a.lflags[w.lflags_off + l] & SDR_LISTENER_ACTIVE))) m |= 1u << j;
+        }
+        s_act[c4] = (uint8_t)m;
+    }
+    __syncwarp();
+    const unsigned inv_q4 = ((1u << 20) + q4 - 1) / q4;  // e / q4 == (e * inv_q4) >> 20 for e < 4096, q4 <= 64
+    const float4 *t4 = reinterpret_cast<const float4 *>(taps + (size_t)row0 * a.tap_stride);
+    uchar4 *k4 = keys ? reinterpret_cast<uchar4 *>(keys + (size_t)row0 * a.tap_stride) : nullptr;
+    const int total = nrow * q4;
+    for (int e0 = lane; e0 < total; e0 += 8 * 32) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int e = e0 + u * 32;
+            v[u] = e < total ? t4[e] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int e = e0 + u * 32;
+            if (e < total) {
+                const int row = (int)(((unsigned)e * inv_q4) >> 20), c4 = e - row * q4;
+                const float t = s_thr[row];
+                const unsigned nib = ((v[u].x > t ? 1u : 0u) | (v[u].y > t ? 2u : 0u) | (v[u].z > t ? 4u : 0u) | (v[u].w > t ? 8u : 0u)) & s_act[c4];
+                // bits 0..3 -> bytes 0..3 (one raw key byte per position)
+                if (k4) reinterpret_cast<uint32_t *>(k4)[e] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+                s_nib[row][c4] = (uint8_t)nib;
+            }
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < nrow * a.key_words; i += 32) {
+        const int row = i / a.key_words, lg = i - row * a.key_words;
+        uint32_t word = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int c4 = lg * 8 + j;
+            if (c4 < q4) word |= (uint32_t)s_nib[row][c4] << (4 * j);
+        }
+        kbits[(size_t)(row0 + row) * a.key_words + lg] = word;
+    }
+}
+
+// A real debouncer (SetSignalDebounce >= 2): one CTA per work walks all its blocks in order, a warp per 32 listener
+// positions, the state carried per (stream, position) across submits.  Works with a pass-through debouncer return at once.
+__global__ void __launch_bounds__(K2_THREADS) k2_debounce_kernel(const K2Args a) {
+    const PostWork w = a.works[blockIdx.x];
+    if (w.debounce < 2) return;
     const int tid = threadIdx.x, wq = tid >> 5, lane = tid & 31;
     constexpr int NWQ = K2_THREADS / 32;
     const int L = w.n_listeners;
@@ -290,58 +406,6 @@ __global__ void __launch_bounds__(K2_THREADS) k2_keys_kernel(const K2Args a) {
     const float *__restrict__ thr = a.thresholds + (size_t)w.block_out * 4 + 3;  // listen threshold of block i at thr[4 i]
     uint8_t *__restrict__ keys = a.keys ? a.keys + (size_t)w.block_out * a.tap_stride : nullptr;
     uint32_t *__restrict__ kbits = a.key_bits + (size_t)w.block_out * a.key_words;
-    if (w.debounce < 2) {
-        // The CTA's 64 rows are one contiguous run of floats: every thread takes whole float4s (tap_stride is a multiple of
-        // four, so a float4 never straddles a row), all of them in flight at once, compares four listeners per load and
-        // writes their raw key bytes as one 32-bit store; the packed words are put together through shared memory.
-        __shared__ float s_thr[K2_KEY_ROWS];
-        __shared__ uint8_t s_act[256];                    // per listener: position active
-        __shared__ uint8_t s_nib[K2_KEY_ROWS][64 + 4];    // four key bits per float4 of a row
-        const int row0 = blockIdx.x * K2_KEY_ROWS;
-        const int nrow = min(K2_KEY_ROWS, w.n_blocks - row0);
-        if (nrow <= 0) return;
-        const int q4 = a.tap_stride >> 2;
-        for (int i = tid; i < nrow; i += K2_THREADS) s_thr[i] = thr[(size_t)(row0 + i) * 4];
-        for (int l = tid; l < a.tap_stride; l += K2_THREADS)
-            s_act[l] = (l < L && (w.lflags_off < 0 || (a.lflags[w.lflags_off + l] & SDR_LISTENER_ACTIVE))) ? 1 : 0;
-        __syncthreads();
-        const float4 *t4 = reinterpret_cast<const float4 *>(taps + (size_t)row0 * a.tap_stride);
-        uchar4 *k4 = keys ? reinterpret_cast<uchar4 *>(keys + (size_t)row0 * a.tap_stride) : nullptr;
-        const int total = nrow * q4;
-        for (int e0 = tid; e0 < total; e0 += 8 * K2_THREADS) {
-            float4 v[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int e = e0 + u * K2_THREADS;
-                v[u] = e < total ? t4[e] : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int e = e0 + u * K2_THREADS;
-                if (e < total) {
-                    const int row = e / q4, c4 = e - row * q4, l = 4 * c4;
-                    const float t = s_thr[row];
-                    const unsigned b0 = (s_act[l] && v[u].x > t) ? 1u : 0u, b1 = (s_act[l + 1] && v[u].y > t) ? 1u : 0u;
-                    const unsigned b2 = (s_act[l + 2] && v[u].z > t) ? 1u : 0u, b3 = (s_act[l + 3] && v[u].w > t) ? 1u : 0u;
-                    if (k4) k4[e] = make_uchar4((unsigned char)b0, (unsigned char)b1, (unsigned char)b2, (unsigned char)b3);
-                    s_nib[row][c4] = (uint8_t)(b0 | (b1 << 1) | (b2 << 2) | (b3 << 3));
-                }
-            }
-        }
-        __syncthreads();
-        for (int i = tid; i < nrow * a.key_words; i += K2_THREADS) {
-            const int row = i / a.key_words, lg = i - row * a.key_words;
-            uint32_t word = 0;
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int c4 = lg * 8 + j;
-                if (c4 < q4) word |= (uint32_t)s_nib[row][c4] << (4 * j);
-            }
-            kbits[(size_t)(row0 + row) * a.key_words + lg] = word;
-        }
-        return;
-    }
-    if (blockIdx.x != 0) return;
     for (int lg = wq; lg < a.key_words; lg += NWQ) {
         const int l = lg * 32 + lane;
         const uint8_t lf = (l < L) ? (w.lflags_off >= 0 ? a.lflags[w.lflags_off + l] : (uint8_t)SDR_LISTENER_ACTIVE) : (uint8_t)0;

@@ -32,6 +32,8 @@ CASES = [
     ("cfg3 768 kS/s N=8192 L=200 (k1_mid8k, one 512-thread group)", 8192, 768000, 200, 444, 100, {"SDR_K1_MID8K_GROUPS": "0"}),
     ("cfg3 768 kS/s N=8192 L=200 (k1_mid8k, 1 stage)", 8192, 768000, 200, 444, 100, {"SDR_K1_MID8K_STAGES": "1"}),
     ("cfg3 768 kS/s N=8192 L=200 (r1 k1_mid<32>)", 8192, 768000, 200, 512, 100, {"SDR_K1_MID8K": "0"}),
+    ("cfg3-like N=8192 L=0 (no listeners)", 8192, 768000, 0, 444, 100),
+    ("cfg3-like N=8192 L=50", 8192, 768000, 50, 444, 100),
     ("cfg3 768 kS/s N=8192 L=200, 64 streams", 8192, 768000, 200, 64, 100),
     ("cfg3 768 kS/s N=8192 L=200, 64 streams (r1 two-kernel large-block path)", 8192, 768000, 200, 64, 100, {"SDR_K1_MID8K": "0"}),
     ("cfg5 24.576 MS/s N=65536 peak scan, 64 streams", 65536, 24576000, 0, 64, 100),
