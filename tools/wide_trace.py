@@ -1,8 +1,14 @@
 #!/usr/bin/env python
 """Phase timing of k1_wide_kernel from a measurement build (-DSDR_K1W_TRACE) run with SDR_K1_WIDE_TRACE=<file>.
 
-The file holds [32 CTAs][512 steps][32] clock64 stamps of the last launch (k1_wide.cuh, K1W_TR).  Prints, per traced
-CTA group, the median number of SM cycles between consecutive stamps in steady state.
+The file holds [32 CTAs][512 steps][32] clock64 stamps of the last launch (k1_wide.cuh, K1W_TR).  Prints the median
+number of SM cycles between consecutive stamps in steady state (every stamp itself costs about 120 cycles).
+
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -DSDR_K1W_TRACE -Xcompiler -fPIC -shared \
+       -o sdrainer_b200/libsdrgpu_trace.so sdrainer_b200/csrc/engine.cu sdrainer_b200/csrc/goertzel.cu
+  SDRGPU_LIB=$PWD/sdrainer_b200/libsdrgpu_trace.so SDR_K1_WIDE_TRACE=gpurun_out/wide_trace.bin \
+       python tools/bench_configs.py --steps 5 --only "(4 whole rounds"       # add SDR_K1_WIDE_TEAMS=9 for one CTA per SM
+  python tools/wide_trace.py gpurun_out/wide_trace.bin
 """
 import sys
 
