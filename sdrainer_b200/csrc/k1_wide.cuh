@@ -143,12 +143,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the eight compute warps
 __device__ __forceinline__ void discard_l2_line(const void *p) { asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory"); }
 
-// Warps 0-7 compute; warp 8 (one lane) is the DMA warp: it owns every wait on another CTA, every TMA issue and every
-// publication, so that the compute warps only ever wait on shared-memory mbarriers.
-//   FULL_A   tx barrier: the IQ column tile has landed in A            (DMA -> compute)
-//   FULL_B   tx barrier: the row tile of the intermediate has landed in B (DMA -> compute)
-//   OUT_RDY  256 arrivals: the outgoing tile is complete in A           (compute -> DMA: store it)
-//   B_FREE   256 arrivals: B has been read into registers               (compute -> DMA: refill it)
+// Warps 0-7 compute; warps 8 and 9 (one lane each) are the DMA warps: they own every wait on another CTA, every TMA issue
+// and every publication, so that the compute warps only ever wait on shared-memory mbarriers.
+//   FULL_A   tx barrier: the IQ column tile has landed in A            (warp 8 -> compute)
+//   FULL_B   tx barrier: the row tile of the intermediate has landed in B (warp 9 -> compute)
+//   OUT_RDY  256 arrivals: the outgoing tile is complete in A           (compute -> warp 8: store it)
+//   B_FREE   256 arrivals: B has been read into registers               (compute -> warp 9: refill it)
+// SDR_K1WIDE_MINB / SDR_K1W_MAXNREG: measurement builds (one CTA per SM with more registers).
 #ifndef SDR_K1WIDE_MINB
 #define SDR_K1WIDE_MINB 2
 #endif
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(K1W_THREADS, SDR_K1WIDE_MINB) k1_wide_kernel(c
         ip.next(a.segs, a.n_segs, n_teams);
     };
 
-    for (int d = 0; d + 1 < D; d++) {  // prologue (mirrors the DMA warp's)
+    for (int d = 0; d + 1 < D; d++) {  // prologue: D - 1 steps are produced before anything is consumed
         if (ip.nb == 0) break;
         produce();
     }
@@ -385,7 +386,7 @@ __global__ void __launch_bounds__(K1W_THREADS, SDR_K1WIDE_MINB) k1_wide_kernel(c
         // letting their eviction write 8 N bytes per block back to HBM (one 128-byte line per thread)
         if (wa.discard)
             discard_l2_line(reinterpret_cast<const unsigned char *>(wa.tmp + ((size_t)(team * R + ic.step % R) * N + (size_t)r0 * 256)) + tid * 128);
-        mbar_arrive(B_FREE);  // B is in registers: the DMA warp refills it
+        mbar_arrive(B_FREE);  // B is in registers: warp 9 refills it
         float2 *col = S + col_of(f);
         {
             HwTwiddle t;
