@@ -1566,6 +1566,7 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     K2Args a2;
     a2.works = reinterpret_cast<const PostWork *>(s.d_desc + dl.post);
     a2.n_works = n_works;
+    a2.n_blocks = s.n_blocks;
     a2.rolling = e->d_rolling;
     a2.psd_floor = s.d_psd_floor;
     a2.variance = s.d_variance;
@@ -1586,7 +1587,14 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     if (e->s_post != e->s_compute) CK(e, cudaStreamWaitEvent(e->s_post, s.ev_km, 0));
     CK(e, cudaEventRecord(s.ev_k2s, e->s_post));
     int k2_launches = 2;
-    k2_thresholds_kernel<<<(n_works + K2_WARPS - 1) / K2_WARPS, K2_THREADS, 0, e->s_post>>>(a2);
+    if (max_work_blocks > K2_SHORT_WORK) {  // long works: the float64 dB conversions run block-parallel in front of the chains
+        k2_db_kernel<<<(s.n_blocks + K2_THREADS - 1) / K2_THREADS, K2_THREADS, 0, e->s_post>>>(a2);
+        CK(e, cudaGetLastError());
+        k2_thresholds_kernel<true><<<(n_works + K2_WARPS - 1) / K2_WARPS, K2_THREADS, 0, e->s_post>>>(a2);
+        k2_launches++;
+    } else {
+        k2_thresholds_kernel<false><<<(n_works + K2_WARPS - 1) / K2_WARPS, K2_THREADS, 0, e->s_post>>>(a2);
+    }
     CK(e, cudaGetLastError());
     // keys and peaks both depend on the thresholds only: the peak scan goes to a side stream so that the two small,
     // latency-bound grids share the GPU instead of running back to back

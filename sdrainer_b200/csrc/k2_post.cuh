@@ -50,6 +50,7 @@ struct PostWork {
 struct K2Args {
     const PostWork *works;
     int n_works;
+    int n_blocks;               // blocks of the batch
     RollingState *rolling;      // [max_streams]
     const float *psd_floor;     // [blocks]
     const double *variance;     // [blocks]
@@ -204,12 +205,30 @@ __device__ void find_peaks_block(const float *__restrict__ cum, int n, float cum
 //   k2_debounce_kernel    (only when a work has a real debouncer) one CTA per such work, sequential over its blocks
 //   k2_peaks_kernel       one CTA per flush: dsp.FindPeaks
 constexpr int K2_WARPS = K2_THREADS / 32;
-constexpr int K2_WCHUNK = 128;  // blocks staged in shared memory per pass of a warp (four per lane)
+constexpr int K2_WCHUNK = 512;  // blocks staged in shared memory per pass of a warp
+constexpr int K2_SHORT_WORK = 128;  // launches whose works are all this short convert their noise scalars inside the chain kernel
+
+// Inputs of the two rolling means for every block of the batch (rx/receiver.go:383-384), one thread per block, written to
+// thresholds[b].xy.  Used when a launch has long works (64 receivers x 2000 blocks): the float64 log10 of 2000 blocks
+// would otherwise sit in front of one warp's sequential chain, 6 us per 128 blocks.
+__global__ void __launch_bounds__(K2_THREADS) k2_db_kernel(const K2Args a) {
+    const int b = blockIdx.x * K2_THREADS + threadIdx.x;
+    if (b >= a.n_blocks) return;
+    const double inv_n2 = 1.0 / ((double)a.n * (double)a.n);  // exact: N is a power of two
+    const float dev_db = psd_value_in_db_shifted((float)sqrt(a.variance[b]), inv_n2);
+    float4 t;
+    t.x = psd_value_in_db_shifted(a.psd_floor[b], inv_n2);
+    t.y = (float)((double)dev_db * 0.25);  // T(float64(PSDValueIndB(T(math.Sqrt(var)), N) + dBmShift) * 0.25)
+    t.z = t.w = 0.f;
+    reinterpret_cast<float4 *>(a.thresholds)[b] = t;
+}
 
 // dsp.RollingMean.Put (dsp/dsp.go:257-268) is sum = fl(fl(sum - oldest) + new) per block, float32, in block order: only
 // that two-operation chain is sequential.  The value that falls out of the 60-deep ring at step i is known up front (the
 // ring's content for i < 60, the input of step i - 60 afterwards), so the lanes stage inputs and outgoing values in
 // parallel and lanes 0 / 1 walk the two chains (noise floor / deviation) over plain arrays.
+// PRE: the inputs were staged by k2_db_kernel in thresholds[b].xy
+template <bool PRE>
 __global__ void __launch_bounds__(K2_THREADS) k2_thresholds_kernel(const K2Args a) {
     __shared__ float s_in_all[K2_WARPS][2][K2_WCHUNK];   // inputs of the two means
     __shared__ float s_run_all[K2_WARPS][2][K2_WCHUNK];  // outgoing ring values, then the running sums
@@ -243,19 +262,35 @@ __global__ void __launch_bounds__(K2_THREADS) k2_thresholds_kernel(const K2Args 
 
     for (int c0 = 0; c0 < w.n_blocks; c0 += K2_WCHUNK) {
         const int cn = min(K2_WCHUNK, w.n_blocks - c0);
-        // phase A (parallel): inputs of the two rolling means (rx/receiver.go:383-384); every lane's loads first
-        {
-            float pf[K2_WCHUNK / 32];
-            double vr[K2_WCHUNK / 32];
+        // phase A (parallel): inputs of the two rolling means (rx/receiver.go:383-384)
+        if (PRE) {  // every load of the pass in flight at once (sixteen float4 per lane)
+            float4 t[K2_WCHUNK / 32];
 #pragma unroll
             for (int k = 0; k < K2_WCHUNK / 32; k++) {
                 const int i = lane + 32 * k;
-                pf[k] = i < cn ? a.psd_floor[w.block_out + c0 + i] : 1.f;
-                vr[k] = i < cn ? a.variance[w.block_out + c0 + i] : 1.0;
+                t[k] = i < cn ? reinterpret_cast<const float4 *>(a.thresholds)[w.block_out + c0 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int k = 0; k < K2_WCHUNK / 32; k++) {
                 const int i = lane + 32 * k;
+                if (i < cn) {
+                    s_in[0][i] = t[k].x;
+                    s_in[1][i] = t[k].y;
+                }
+            }
+        }
+        for (int i0 = 0; !PRE && i0 < cn; i0 += 128) {  // four blocks per lane and pass, the loads first
+            float pf[4];
+            double vr[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int i = i0 + lane + 32 * k;
+                pf[k] = i < cn ? a.psd_floor[w.block_out + c0 + i] : 1.f;
+                vr[k] = i < cn ? a.variance[w.block_out + c0 + i] : 1.0;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int i = i0 + lane + 32 * k;
                 if (i < cn) {
                     // T(float64(PSDValueIndB(T(math.Sqrt(var)), N) + dBmShift) * 0.25)
                     const float dev_db = psd_value_in_db_shifted((float)sqrt(vr[k]), n2);
@@ -270,7 +305,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2_thresholds_kernel(const K2Args 
         for (int i = lane; i < cn; i += 32) {
             int p = next0 + i;
             if (p >= SDR_NOISE_WINDOW) p -= SDR_NOISE_WINDOW;
-            if (p >= SDR_NOISE_WINDOW) p -= SDR_NOISE_WINDOW;  // i < 128, next0 < 60: at most two wraps below index 60
+            if (p >= SDR_NOISE_WINDOW) p -= SDR_NOISE_WINDOW;  // only used for i < 60 (next0 < 60: one wrap)
             s_run[0][i] = i < SDR_NOISE_WINDOW ? s_roll.floor_values[p] : s_in[0][i - SDR_NOISE_WINDOW];
             s_run[1][i] = i < SDR_NOISE_WINDOW ? s_roll.dev_values[p] : s_in[1][i - SDR_NOISE_WINDOW];
         }
@@ -280,10 +315,35 @@ __global__ void __launch_bounds__(K2_THREADS) k2_thresholds_kernel(const K2Args 
             float sum = lane == 0 ? s_roll.floor_sum : s_roll.dev_sum;
             const float *in = s_in[lane];
             float *run = s_run[lane];
-#pragma unroll 4
-            for (int i = 0; i < cn; i++) {
-                sum = __fadd_rn(__fsub_rn(sum, run[i]), in[i]);
-                run[i] = sum;
+            // eight steps per pass through registers, the next pass's operands loaded before this pass's results are
+            // stored: the chain then costs its two dependent float32 operations per step, not a shared-memory round trip
+            // (the arrays hold K2_WCHUNK entries, reading past cn is harmless)
+            float o[8], x[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                o[u] = run[u];
+                x[u] = in[u];
+            }
+            for (int i0 = 0; i0 < cn; i0 += 8) {
+                float o2[8], x2[8];
+                const int j0 = (i0 + 8 < K2_WCHUNK) ? i0 + 8 : i0;
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    o2[u] = run[j0 + u];
+                    x2[u] = in[j0 + u];
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    if (i0 + u < cn) {  // the last pass may be partial
+                        sum = __fadd_rn(__fsub_rn(sum, o[u]), x[u]);
+                        run[i0 + u] = sum;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    o[u] = o2[u];
+                    x[u] = x2[u];
+                }
             }
             if (lane == 0) s_roll.floor_sum = sum;
             else s_roll.dev_sum = sum;

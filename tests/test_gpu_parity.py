@@ -203,7 +203,7 @@ def test_device_pointer_input_and_no_d2h(capi):
         s = eng.open_stream(192000)
         t = eng.submit([dict(stream=s, iq=d.data_ptr(), n_blocks=200, listener_bins=bins)], capi.WANT_FLUSH_CUM)
         dev = eng.collect(t)
-        assert eng.launch_count() == 4  # K1, k2_thresholds, k2_keys, k2_peaks
+        assert eng.launch_count() == 5  # K1, k2_db (a work longer than 128 blocks), k2_thresholds, k2_keys, k2_peaks
     for name in ("psd_noise_floor", "noise_variance", "thresholds", "flush_cum"):
         assert np.array_equal(getattr(host, name), getattr(dev, name), equal_nan=True), name
     for name in ("taps", "keys"):

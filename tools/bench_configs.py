@@ -25,6 +25,7 @@ CASES = [
     ("cfg1 48 kS/s N=512 L=5", 512, 48000, 5, 4 * 148 * 12, 100),
     ("N=1024 L=25", 1024, 96000, 25, 2 * 148 * 12, 100),
     ("cfg2/cfg4 192 kS/s N=2048 L=50", 2048, 192000, 50, 148 * 12, 100),
+    ("cfg4 literal N=2048 L=50, 64 streams x 2000 blocks", 2048, 192000, 50, 64, 2000),
     ("N=4096 L=100", 4096, 384000, 100, 148 * 4, 100),
     # >= 2 GiB of blocks per batch like the other shapes; 512 streams also give the fused N = 8192
     # kernel (k1_mid.cuh) its >= 2 segments per SM, below that the engine takes the block-parallel two-kernel path
