@@ -545,8 +545,10 @@ def run_e2e(args, capi, torch, iq, bins_all, local_rank, world, dist, device):
 
     steps = max(2, min(args.steps, args.e2e_steps))
 
-    def timed(prepared, flags):
-        for _ in range(2):
+    warm = max(3, args.warmup)  # untimed steps per leg; the first leg also wakes the PCIe link and the pinned pages up
+
+    def timed(prepared, flags, warm_steps):
+        for _ in range(warm_steps):
             t = eng.submit_prepared(prepared, flags)
             eng.collect_raw(t)
             eng.release(t)
@@ -578,11 +580,11 @@ def run_e2e(args, capi, torch, iq, bins_all, local_rank, world, dist, device):
     base_d2h = n_blocks * (4 + 8 + 16 + 4 * kw) + n_flush * (4 + 4 + 128 * 28)
     # headline: the key-state design -- the Go loop's l.Listen(value, threshold) (rx/listener.go:142) is replaced by the
     # device's debounced key bits, so neither the float32 taps nor the raw key bytes travel
-    dt = timed(eng.prepare(works), capi.NO_TAPS | capi.NO_RAW_KEYS)
+    dt = timed(eng.prepare(works), capi.NO_TAPS | capi.NO_RAW_KEYS, 2 * warm)
     # the same loop with the taps and raw keys copied back (what a host-side Listen() would need)
-    dt_taps = timed(eng.prepare(works), 0)
+    dt_taps = timed(eng.prepare(works), 0, warm)
     # KiwiSDR wire bytes in: half the H2D volume, bit-exact with the float path (tests/test_gpu_kiwi.py)
-    dt_i16 = timed(eng.prepare(works16), capi.NO_TAPS | capi.NO_RAW_KEYS)
+    dt_i16 = timed(eng.prepare(works16), capi.NO_TAPS | capi.NO_RAW_KEYS, warm)
     eng.free_pinned(pinned)
     eng.free_pinned(pinned16)
     eng.close()
@@ -590,7 +592,7 @@ def run_e2e(args, capi, torch, iq, bins_all, local_rank, world, dist, device):
     rate = lambda d: world * n_blocks * N * steps / d / 1e6  # noqa: E731
     h2d_gbs = nbytes * steps / dt / 1e9
     return {"value": rate(dt), "unit": "Msamples/s", "h2d_bytes_per_step": int(nbytes),
-            "d2h_bytes_per_step": int(base_d2h), "steps": steps, "ms_per_step": 1e3 * dt / steps,
+            "d2h_bytes_per_step": int(base_d2h), "steps": steps, "warmup": 2 * warm, "ms_per_step": 1e3 * dt / steps,
             "h2d_gbs_per_gpu": h2d_gbs, "h2d_ceiling_gbs": ceiling, "frac_of_ceiling": h2d_gbs / ceiling,
             "ceiling_note": "bare cudaMemcpyAsync of the same pinned batch on all ranks at once, GB/s per GPU of the slowest rank",
             "with_taps": {"value": rate(dt_taps), "d2h_bytes_per_step": int(base_d2h + n_blocks * (4 * ts + ts))},
@@ -756,7 +758,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=12 * SM_COUNT,
                     help="streams per GPU (x100 blocks each per step); 12*148 = 3 full waves of 4 resident CTAs per SM")
-    ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true")
