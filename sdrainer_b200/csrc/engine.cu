@@ -30,6 +30,7 @@
 #include "k2_post.cuh"
 #include "k1_large.cuh"
 #include "k1_mid.cuh"
+#include "k1_mid4k.cuh"
 #include "k1_mid8k.cuh"
 #include "k1_warp.cuh"
 #include "k1_wide.cuh"
@@ -145,6 +146,8 @@ struct sdr_engine {
     float2 *d_tw_mid = nullptr, *d_tw256m = nullptr;
     bool k1_mid = false;
     int k1m_grid_cap = 0;
+    bool k1_mid4k = false;    // N = 4096: TMA-staged k1_mid4k_kernel instead of k1_mid_kernel<16> (SDR_K1_MID4K=0)
+    int k1m4_grid_cap = 0;
     // N = 8192: TMA-staged 512-thread kernel (k1_mid8k.cuh), one CTA per SM.  SDR_K1_MID8K=0 disables it (the launch then
     // falls back to k1_mid_kernel<32> / the two-kernel path), =force takes it for every launch, whatever the segment count
     int k1_mid8k = 0;  // 0 off, 1 when the launch has enough segments, 2 always
@@ -521,6 +524,20 @@ const void *k1m_fn(int n, bool dbg, bool win) { return n == 4096 ? k1m_fn<16>(db
 int k1m_smem(int n) { return n == 4096 ? K1MidGeom<16>::SMEM_BYTES : K1MidGeom<32>::SMEM_BYTES; }
 int k1m_threads(int) { return 256; }
 
+const void *k1m4_fn(bool dbg, bool win) {
+    if (dbg) return win ? (const void *)k1_mid4k_kernel<2, true, true> : (const void *)k1_mid4k_kernel<2, true, false>;
+    return win ? (const void *)k1_mid4k_kernel<2, false, true> : (const void *)k1_mid4k_kernel<2, false, false>;
+}
+int k1m4_grid_cap_for(int sm_count) {  // 0: the kernel cannot run here
+    int occ = 0;
+    for (int v = 0; v < 4; v++) {
+        const void *fn = k1m4_fn((v & 1) != 0, (v & 2) != 0);
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, K1Mid4kGeom<2>::SMEM_BYTES) != cudaSuccess) return 0;
+        if (v == 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 256, K1Mid4kGeom<2>::SMEM_BYTES) != cudaSuccess) return 0;
+    }
+    return occ * sm_count;
+}
+
 int k1m_grid_cap_for(int n, bool win, int sm_count) {
     int occ = 0;
     for (int dbg = 0; dbg < 2; dbg++) {
@@ -581,6 +598,20 @@ cudaError_t launch_k1_mid8k(const sdr_engine *e, const K1Args &a, const Mid8kNf 
     return cudaGetLastError();
 }
 
+cudaError_t launch_k1_mid4k(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st) {
+    // two CTAs per SM walk the segment list with stride grid: whole rounds, no straggler
+    int grid = a.n_segs;
+    if (grid > e->k1m4_grid_cap) {
+        const int rounds = (grid + e->k1m4_grid_cap - 1) / e->k1m4_grid_cap;
+        grid = (a.n_segs + rounds - 1) / rounds;
+    }
+    if (grid < 1) grid = 1;
+    K1Args args = a;
+    const float2 *tws = e->d_tw_mid, *tw256 = e->d_tw256m;
+    void *params[] = {&args, &tws, &tw256};
+    return cudaLaunchKernel(k1m4_fn(dbg, a.window != nullptr), dim3(grid), dim3(256), params, K1Mid4kGeom<2>::SMEM_BYTES, st);
+}
+
 cudaError_t launch_k1_mid(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st) {
     int grid = a.n_segs;
     if (grid > e->k1m_grid_cap) {
@@ -596,6 +627,7 @@ cudaError_t launch_k1_mid(const sdr_engine *e, const K1Args &a, bool dbg, cudaSt
 
 // warp_ok: N = 512 and every work has noise windows of at least K1WarpGeom::MIN_WS bins
 cudaError_t launch_k1(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st, bool i16 = false, bool warp_ok = true) {
+    if (e->k1_mid4k && e->N == 4096 && !i16) return launch_k1_mid4k(e, a, dbg, st);
     if (e->k1_mid && e->N == 4096 && !i16) return launch_k1_mid(e, a, dbg, st);
     if (e->k1_warp && warp_ok) return launch_k1_warp(e, a, dbg, st, i16);
     switch (e->N) {
@@ -1100,6 +1132,14 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
         const char *v = getenv("SDR_K1_MID");
         e->k1_mid = !(v && v[0] == '0');
         if (e->k1_mid) e->k1m_grid_cap = k1m_grid_cap_for(e->N, e->d_window != nullptr, e->sm_count);
+        if (e->N == 4096) {
+            const char *v4 = getenv("SDR_K1_MID4K");
+            if (!(v4 && v4[0] == '0')) {
+                e->k1m4_grid_cap = k1m4_grid_cap_for(e->sm_count);
+                e->k1_mid4k = e->k1m4_grid_cap > 0;
+                cudaGetLastError();
+            }
+        }
         if (e->N == 8192) {
             const char *v8 = getenv("SDR_K1_MID8K");
             e->k1_mid8k = (v8 && v8[0] == '0') ? 0 : (v8 && v8[0] == 'f') ? 2 : 1;
@@ -1511,7 +1551,8 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     nvtx_k1.emplace("K1 spectral (FFT, |X|^2, dB, noise floor, taps, cumulation)");
     if (!e->large) {
         CK(e, launch_k1(e, a1, dbg, e->s_compute, i16, warp_ok));
-        e->last_kernel = (e->k1_mid && e->N == 4096 && !i16) ? "k1_mid_kernel<16>" : (e->k1_warp && warp_ok) ? "k1_warp_kernel"
+        e->last_kernel = (e->k1_mid4k && e->N == 4096 && !i16) ? "k1_mid4k_kernel"
+                         : (e->k1_mid && e->N == 4096 && !i16) ? "k1_mid_kernel<16>" : (e->k1_warp && warp_ok) ? "k1_warp_kernel"
                          : e->N == 512 ? "k1_spectral_kernel<512>" : e->N == 1024 ? "k1_spectral_kernel<1024>"
                          : e->N == 2048 ? "k1_spectral_kernel<2048>" : "k1_spectral_kernel<4096>";
     } else if (e->N == 8192 && block_off <= e->round_blocks && (e->k1_mid8k == 2 || (e->k1_mid8k == 1 && n_segs >= e->sm_count / 3))) {

@@ -1,5 +1,6 @@
-"""The fused single-pass kernel for N = 4096 / 8192 (csrc/k1_mid.cuh) against the oracle and against the kernels it
-replaces (three-pass K1 at 4096, the two-kernel large-block path at 8192; selected with SDR_K1_MID=0)."""
+"""The fused single-pass kernels for N = 4096 / 8192 (csrc/k1_mid4k.cuh, k1_mid.cuh) against the oracle and against the
+kernels they replace (k1_mid<16> and the three-pass K1 at 4096, the two-kernel large-block path at 8192; selected with
+SDR_K1_MID4K=0 / SDR_K1_MID=0)."""
 import numpy as np
 import pytest
 
@@ -58,20 +59,28 @@ def _agree(a, b, n_listen):
         assert np.abs(a.taps[:, :n_listen][strong] - b.taps[:, :n_listen][strong]).max() < 1e-3
 
 
-def test_mid_4096_agrees_with_three_pass(capi, monkeypatch):
+def test_mid_4096_kernels_agree(capi, monkeypatch):
+    """N = 4096 has three spectral kernels: the TMA-staged k1_mid4k_kernel (default), round 1's k1_mid_kernel<16>
+    (SDR_K1_MID4K=0) and the three-pass kernel (also SDR_K1_MID=0)"""
     n, fs, nb = 4096, 384000, 120
     rng = np.random.default_rng(77)
     specs = [synth.StreamSpec(sample_rate=fs, block_size=n, n_blocks=nb, seed=70 + i,
                               tones=synth.make_tones(rng, 10, n, 70)) for i in range(4)]
     iqs = [synth.generate(sp) for sp in specs]
-    res = []
-    for mid in ("1", "0"):
-        monkeypatch.setenv("SDR_K1_MID", mid)
+    res, names = [], []
+    for env in ({}, {"SDR_K1_MID4K": "0"}, {"SDR_K1_MID4K": "0", "SDR_K1_MID": "0"}):
+        for k in ("SDR_K1_MID4K", "SDR_K1_MID"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
         with capi.Engine(n, max_streams=4, max_listeners=16, max_blocks_per_batch=4 * nb, max_peaks_per_flush=n // 2 + 1) as eng:
             ss = [eng.open_stream(fs) for _ in specs]
             works = [dict(stream=s, iq=x, listener_bins=[t.bin for t in sp.tones]) for s, x, sp in zip(ss, iqs, specs)]
             res.append(eng.collect(eng.submit(works, capi.WANT_FLUSH_CUM)))
+            names.append(eng.last_kernel())
+    assert names == ["k1_mid4k_kernel", "k1_mid_kernel<16>", "k1_spectral_kernel<4096>"]
     _agree(res[0], res[1], 10)
+    _agree(res[0], res[2], 10)
 
 
 def test_mid_8192_many_streams_agrees_with_two_kernel_path_and_oracle(capi, oracle, monkeypatch):

@@ -27,6 +27,7 @@ CASES = [
     ("cfg2/cfg4 192 kS/s N=2048 L=50", 2048, 192000, 50, 148 * 12, 100),
     ("cfg4 literal N=2048 L=50, 64 streams x 2000 blocks", 2048, 192000, 50, 64, 2000),
     ("N=4096 L=100", 4096, 384000, 100, 148 * 4, 100),
+    ("N=4096 L=100 (r1 k1_mid<16>)", 4096, 384000, 100, 148 * 4, 100, {"SDR_K1_MID4K": "0"}),
     # >= 2 GiB of blocks per batch like the other shapes; 512 streams also give the fused N = 8192
     # kernel (k1_mid.cuh) its >= 2 segments per SM, below that the engine takes the block-parallel two-kernel path
     ("cfg3 768 kS/s N=8192 L=200 (k1_mid8k: TMA ring, 512 threads)", 8192, 768000, 200, 444, 100),
