@@ -119,3 +119,37 @@ def test_wide_many_segments_few_teams_ragged_bit_identity(capi, monkeypatch, loo
     for k in names:
         for i in range(ns):
             assert np.array_equal(outs[0][k][i], outs[1][k][i], equal_nan=True), (k, i)
+
+
+@pytest.mark.parametrize("n,env,edge", [
+    (65536, {"SDR_K1_WIDE": "force"}, 0), (65536, {"SDR_K1_WIDE": "force"}, 1000), (65536, {"SDR_K1_WIDE": "force"}, 10000),
+    (65536, {"SDR_K1_WIDE": "force"}, 30100),   # 533-bin windows: two whole positions per row
+    (65536, {"SDR_K1_WIDE": "force"}, 31000),   # 353-bin windows: one or two positions per row (clamped body)
+    (65536, {"SDR_K1_WIDE": "force"}, 32700),   # 13-bin windows: at most one position per row
+    (8192, {"SDR_K1_MID8K": "force"}, 0), (8192, {"SDR_K1_MID8K": "force"}, 1000), (8192, {"SDR_K1_MID8K": "force"}, 3500),
+    (8192, {"SDR_K1_MID8K": "force"}, 4000),    # 19-bin windows
+    (4096, {}, 1500), (4096, {}, 1950), (4096, {}, 2003),  # k1_mid4k: 109-, 19- and 9-bin windows
+])
+def test_noise_window_geometry_over_edge_widths(capi, oracle, monkeypatch, n, env, edge):
+    """The single-pass kernels split every noise window into per-row shares read from a common start position, the upper
+    half-warp rotated by one element (k1_large.cuh: nf_row_share); the geometry depends on the edge width.  Noise floor and
+    variance against the oracle from the widest to the narrowest windows that do not take the exact replay (>= 9 bins)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    fs = {65536: 24576000, 8192: 768000, 4096: 384000}[n]
+    nb = 6 if n == 65536 else 12
+    ws = (n - 2 * edge) // 10
+    assert ws >= 9
+    rng = np.random.default_rng(n + edge)
+    tones = synth.make_tones(rng, max(2, min(12, (n - 2 * edge - 26) // 14)), n, edge + 8, keyed=False)
+    iq = synth.generate(synth.StreamSpec(sample_rate=fs, block_size=n, n_blocks=nb, seed=n + edge, tones=tones))
+    bins = sorted({min(max(t.bin, edge + 5), n - edge - 6) for t in tones})[:6]
+    with capi.Engine(n, max_streams=1, max_listeners=8, max_blocks_per_batch=nb, max_peaks_per_flush=256) as eng:
+        sid = eng.open_stream(fs)
+        res = eng.collect(eng.submit([dict(stream=sid, iq=iq, edge_width=edge, listener_bins=bins)]))
+        kernel = eng.last_kernel()
+    assert kernel == {65536: "k1_wide_kernel", 8192: "k1_mid8k2_kernel", 4096: "k1_mid4k_kernel"}[n]
+    r = oracle.process_stream(iq, n, edge_width=edge, peak_threshold=15.0, listener_bins=bins, sample_rate=fs)
+    pu.check_scalars(res.psd_noise_floor, r.noise[:, 0], what=f"psdNoiseFloor, {ws}-bin windows")
+    # narrow windows: the fp32 error of the few bins of a window does not average out (1.1e-4 measured with 17 bins)
+    pu.check_scalars(res.noise_variance, r.noise[:, 1], rel=1e-4 if ws >= 100 else 5e-4, what=f"noise variance, {ws}-bin windows")
