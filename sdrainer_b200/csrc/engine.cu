@@ -128,7 +128,7 @@ struct sdr_engine {
     // large-block path (N >= 8192): four-step split N = n1 * n2
     bool large = false;
     LargeGeom lg{};
-    float2 *d_tw_sub1 = nullptr, *d_tw_sub2 = nullptr, *d_tw_n = nullptr;
+    float2 *d_tw_sub1 = nullptr, *d_tw_sub2 = nullptr;  // W_N1^m, W_N2^m
     float2 *d_tw_step = nullptr;  // [k1][c] = W_N^(c k1): step-1 twiddles of the register-resident kernels
     int round_blocks = 0;         // register-resident large path: blocks per L2-resident round (SDR_LARGE_ROUND_MB)
     // N = 65536: single-pass persistent kernel (k1_wide.cuh): teams of 16 CTAs, the four-step intermediate in an
@@ -268,23 +268,6 @@ cudaError_t launch_k1_n(const sdr_engine *e, const K1Args &a, bool dbg, cudaStre
     return cudaLaunchKernel(k1_fn<N>(dbg, win, e->k1_tw2r, i16), dim3(grid), dim3(Gm::CTA_THREADS), params, Gm::SMEM_BYTES, st);
 }
 
-template <int L, int STEP>
-cudaError_t launch_sub_fft(const SubFftArgs &sa, int n_ffts, int n_blocks, cudaStream_t st) {
-    const size_t smem = (size_t)2 * SUBFFT_F * (L + 1) * sizeof(float2);
-    sub_fft_kernel<L, STEP><<<dim3(n_ffts / SUBFFT_F, n_blocks), SUBFFT_F * L / 4, smem, st>>>(sa);
-    return cudaGetLastError();
-}
-
-template <int STEP>
-cudaError_t launch_sub_fft_len(int len, const SubFftArgs &sa, int n_ffts, int n_blocks, cudaStream_t st) {
-    switch (len) {
-        case 64: return launch_sub_fft<64, STEP>(sa, n_ffts, n_blocks, st);
-        case 128: return launch_sub_fft<128, STEP>(sa, n_ffts, n_blocks, st);
-        case 256: return launch_sub_fft<256, STEP>(sa, n_ffts, n_blocks, st);
-    }
-    return cudaErrorInvalidValue;
-}
-
 // register-resident large path (k1_large.cuh): per round of consecutive blocks step 1, step 2 + epilogue, cumulation;
 // once per batch the noise-floor finish
 struct LargeRound {
@@ -306,6 +289,7 @@ cudaError_t launch_large_fast(const sdr_engine *e, const K1Args &a, const LargeF
     fa.spectrum = dbg ? a.dbg_spectrum : nullptr;
     fa.psd = dbg ? a.dbg_psd : nullptr;
     fa.tw256 = e->d_tw_sub2;
+    fa.tw_n1 = e->d_tw_sub1;
     fa.tw_step = e->d_tw_step;
     fa.window = e->d_window;
     fa.segs = a.segs;
@@ -326,6 +310,8 @@ cudaError_t launch_large_fast(const sdr_engine *e, const K1Args &a, const LargeF
     for (const LargeRound &r : rounds) {
         fa.blk0 = r.blk0;
         if (e->lg.n1 == 256) fast_cols256_kernel<<<dim3(e->lg.n2 / 16, r.n_blocks), 256, smem, st>>>(fa);
+        else if (e->lg.n1 == 128) fast_cols64_kernel<true><<<dim3(e->lg.n2 / 128, r.n_blocks), 256, 0, st>>>(fa);
+        else if (e->lg.n1 == 64) fast_cols64_kernel<false><<<dim3(e->lg.n2 / 256, r.n_blocks), 256, 0, st>>>(fa);
         else fast_cols32_kernel<<<dim3(e->lg.n2 / 256, r.n_blocks), 256, 0, st>>>(fa);
         cudaError_t rc = cudaGetLastError();
         if (rc != cudaSuccess) return rc;
@@ -436,55 +422,6 @@ cudaError_t launch_k1_wide(const sdr_engine *e, const K1Args &a, const LargeFast
     fin.n_cta = K1W_TEAM;
     fin.n = 65536;
     large_nf_finish_kernel<<<(n_blocks + 3) / 4, 128, 0, st>>>(fin);
-    return cudaGetLastError();
-}
-
-// large-block path: step 1, step 2, noise floor + taps, cumulation (k1_large.cuh)
-cudaError_t launch_large(const sdr_engine *e, const K1Args &a, float2 *d_tmp, const int *d_block_seg, int n_blocks, int n_segs,
-                         cudaStream_t st) {
-    const int N = e->N;
-    SubFftArgs sa{};
-    sa.in = d_tmp;
-    sa.tmp = d_tmp;
-    sa.spectrum = a.dbg_spectrum;
-    sa.psd = a.dbg_psd;
-    sa.tw_n = e->d_tw_n;
-    sa.window = e->d_window;
-    sa.segs = a.segs;
-    sa.block_seg = d_block_seg;
-    sa.n = N;
-    sa.n1 = e->lg.n1;
-    sa.n2 = e->lg.n2;
-    sa.db_offset = (float)(10.0 * log10(20.0 / ((double)N * (double)N)));
-    cudaError_t rc;
-    sa.tw_sub = e->d_tw_sub1;
-    rc = launch_sub_fft_len<1>(e->lg.n1, sa, e->lg.n2, n_blocks, st);
-    if (rc != cudaSuccess) return rc;
-    sa.tw_sub = e->d_tw_sub2;
-    rc = launch_sub_fft_len<2>(e->lg.n2, sa, e->lg.n1, n_blocks, st);
-    if (rc != cudaSuccess) return rc;
-    LargePostArgs pa{};
-    pa.psd = a.dbg_psd;
-    pa.spectrum = a.dbg_spectrum;
-    pa.segs = a.segs;
-    pa.block_seg = d_block_seg;
-    pa.works = a.works;
-    pa.listener_bins = a.listener_bins;
-    pa.psd_floor = a.psd_floor;
-    pa.variance = a.variance;
-    pa.taps = a.taps;
-    pa.tap_stride = a.tap_stride;
-    pa.n = N;
-    large_post_kernel<<<n_blocks, 128, 0, st>>>(pa);
-    rc = cudaGetLastError();
-    if (rc != cudaSuccess) return rc;
-    LargeCumArgs ca{};
-    ca.spectrum = a.dbg_spectrum;
-    ca.segs = a.segs;
-    ca.cum_state = a.cum_state;
-    ca.flush_cum = a.flush_cum;
-    ca.n = N;
-    large_cum_kernel<<<dim3(N / 256, n_segs), 256, 0, st>>>(ca);
     return cudaGetLastError();
 }
 
@@ -826,10 +763,6 @@ int alloc_slot(sdr_engine *e, Slot &s) {
             }
             CK(e, cudaMemcpy(s.d_wide_map, &m, sizeof(m), cudaMemcpyHostToDevice));
         }
-    } else if (e->large) {  // Stockham path: materialises spectrum / psd / the four-step intermediate of the batch
-        CK(e, cudaMalloc((void **)&s.d_tmp, MB * N * sizeof(float2)));
-        CK(e, cudaMalloc((void **)&s.d_spectrum, MB * N * sizeof(float)));
-        CK(e, cudaMalloc((void **)&s.d_psd, MB * N * sizeof(float)));
     }
     CK(e, cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
     CK(e, cudaEventCreateWithFlags(&s.ev_desc, cudaEventDisableTiming));
@@ -1035,7 +968,6 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
         };
         CKC(table(e->lg.n1, &e->d_tw_sub1));
         CKC(table(e->lg.n2, &e->d_tw_sub2));
-        CKC(table(e->N, &e->d_tw_n));
         if (large_fast_geom(e->lg.n1, e->lg.n2)) {
             const int n1 = e->lg.n1, n2 = e->lg.n2;
             std::vector<float2> t((size_t)n1 * n2);
@@ -1203,7 +1135,6 @@ void sdr_engine_destroy(sdr_engine *e) {
     cudaFree(e->d_tw256m);
     cudaFree(e->d_tw_sub1);
     cudaFree(e->d_tw_sub2);
-    cudaFree(e->d_tw_n);
     cudaFree(e->d_window);
     cudaFree(e->d_cum_state);
     cudaFree(e->d_rolling);
@@ -1589,11 +1520,11 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
         const LargeFastBufs lb{s.d_tmp, s.d_spec_round, s.d_nf_part, s.d_xto, s.d_nf_edge};
         CK(e, launch_large_fast(e, a1, lb, reinterpret_cast<const int *>(s.d_desc + dl.block_seg), rounds, block_off, dbg, e->s_compute,
                                 &k1_launches));
-        e->last_kernel = e->lg.n1 == 256 ? "fast_cols256_kernel + fast_rows256_kernel" : "fast_cols32_kernel + fast_rows256_kernel";
+        e->last_kernel = e->lg.n1 == 256 ? "fast_cols256_kernel + fast_rows256_kernel"
+                         : e->lg.n1 == 32 ? "fast_cols32_kernel + fast_rows256_kernel" : "fast_cols64_kernel + fast_rows256_kernel";
     } else {
-        CK(e, launch_large(e, a1, s.d_tmp, reinterpret_cast<const int *>(s.d_desc + dl.block_seg), block_off, n_segs, e->s_compute));
-        e->last_kernel = "sub_fft_kernel (Stockham four-step)";
-        k1_launches = 4;
+        e->err = "internal: no spectral kernel for this block size";
+        return SDR_EINVAL;
     }
     if (n_exact > 0) {
         nf_exact_kernel<<<n_exact, 128, 0, e->s_compute>>>(reinterpret_cast<const ExactNf *>(s.d_desc + dl.exact), s.d_psd, N,
@@ -1893,15 +1824,12 @@ int sdr_dsp_iq_to_spectrum_and_psd(sdr_engine *e, const float *iq, int n_blocks,
         for (int b = 0; b < n_blocks; b++) bs[b] = b;
         CK(e, cudaMemcpyAsync(d_block_seg, bs.data(), sizeof(int) * (size_t)n_blocks, cudaMemcpyHostToDevice, e->s_compute));
         CK(e, cudaStreamSynchronize(e->s_compute));  // bs is a stack-lifetime buffer
-        if (e->round_blocks > 0) {  // one round: the scratch holds the whole call
+        {  // one round: the scratch holds the whole call
             const LargeFastBufs lb{d_tmp, d_spec_round, d_nf_part, d_xto, d_nf_edge};
             const std::vector<LargeRound> rounds{LargeRound{0, n_blocks, 0, n_blocks}};
             int nl = 0;
             CK(e, launch_large_fast(e, a, lb, d_block_seg, rounds, n_blocks, true, e->s_compute, &nl));
             e->launches += nl;
-        } else {
-            CK(e, launch_large(e, a, d_tmp, d_block_seg, n_blocks, n_blocks, e->s_compute));
-            e->launches += 4;
         }
     }
     CK(e, cudaMemcpyAsync(spectrum, d_spec, out_bytes, cudaMemcpyDeviceToHost, e->s_compute));

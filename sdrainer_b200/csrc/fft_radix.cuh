@@ -200,4 +200,49 @@ __device__ __forceinline__ void dft32(float2 (&v)[32]) {
     for (int ka = 0; ka < 4; ka++) dft8(*reinterpret_cast<float2(*)[8]>(&v[8 * ka]));
 }
 
+// ---- 64-point transform (step 1 of the N = 16384 / 32768 large path) ----
+template <>
+struct OutIdx<64> {  // position p = 8*j + q holds X[OutIdx<8>(j) + 8*OutIdx<8>(q)]
+    __host__ __device__ static constexpr int of(int p) { return OutIdx<8>::of(p >> 3) + 8 * OutIdx<8>::of(p & 7); }
+};
+template <int J, int B>
+__device__ __forceinline__ void dft64_twiddle_one(float2 (&w)[64]) {
+    w[8 * J + B] = mul_w64<B * OutIdx<8>::of(J)>(w[8 * J + B]);  // W64^(b ka), ka = OutIdx<8>(j)
+}
+template <int J>
+__device__ __forceinline__ void dft64_twiddle_row(float2 (&w)[64]) {
+    dft64_twiddle_one<J, 1>(w);
+    dft64_twiddle_one<J, 2>(w);
+    dft64_twiddle_one<J, 3>(w);
+    dft64_twiddle_one<J, 4>(w);
+    dft64_twiddle_one<J, 5>(w);
+    dft64_twiddle_one<J, 6>(w);
+    dft64_twiddle_one<J, 7>(w);
+}
+// 64-point forward DFT in registers: n = 8a + b; DFT8 over a, twiddle W64^(b ka), DFT8 over b.
+// Natural order in; v[p] = X[OutIdx<64>::of(p)] out.
+__device__ __forceinline__ void dft64(float2 (&v)[64]) {
+    float2 w[64];
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        float2 t[8];
+#pragma unroll
+        for (int a = 0; a < 8; a++) t[a] = v[b + 8 * a];
+        dft8(t);
+#pragma unroll
+        for (int j = 0; j < 8; j++) w[8 * j + b] = t[j];  // slot j holds ka = OutIdx<8>(j)
+    }
+    dft64_twiddle_row<1>(w);
+    dft64_twiddle_row<2>(w);
+    dft64_twiddle_row<3>(w);
+    dft64_twiddle_row<4>(w);
+    dft64_twiddle_row<5>(w);
+    dft64_twiddle_row<6>(w);
+    dft64_twiddle_row<7>(w);
+#pragma unroll
+    for (int j = 0; j < 8; j++) dft8(*reinterpret_cast<float2(*)[8]>(&w[8 * j]));
+#pragma unroll
+    for (int p = 0; p < 64; p++) v[p] = w[p];
+}
+
 }  // namespace sdr

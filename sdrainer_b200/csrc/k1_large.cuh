@@ -1,18 +1,17 @@
-// k1_large.cuh -- large-block path (N = 8192 .. 65536: BASELINE configs 3 and 5).
+// k1_large.cuh -- large-block path (N = 8192 .. 65536: BASELINE configs 3 and 5) as TWO launches per round.
 //
-// One block no longer fits a CTA's registers/shared memory, so the transform is the classic four-step
-// N = N1 x N2 split executed as two launches whose intermediate stays L2-resident (126 MB L2):
-//   step 1  sub_fft_kernel<STEP1>: N2 column FFTs of length N1 (x[r*N2 + c], r = 0..N1-1), multiplied by
-//           W_N^(c*k1), written to tmp[k1*N2 + c]
-//   step 2  sub_fft_kernel<STEP2>: N1 row FFTs of length N2 over tmp[k1*N2 + .]; X[k1 + N1*k2] goes through the
-//           same |X|^2 / dB projection as K1 (dsp/fft.go:32-36,71-85, rx/receiver.go:376-378) and is stored
-//           fftshifted (dsp/fft.go:54-57) as psd[] and spectrum[]
-//   post    large_post_kernel: dsp.FindNoiseFloor (shared device functions with K1) + listener taps per block
-//   cum     large_cum_kernel : float32 cumulation in block order (rx/receiver.go:404-407), flush / state save
-// Sub-FFTs (64/128/256 points) run entirely in shared memory: radix-4 Stockham autosort passes (+ one radix-2
-// pass for odd log2), fp32 table twiddles rounded from fp64, packed f32x2 arithmetic as in fft_radix.cuh.
-// This path trades HBM/L2 traffic (~6x the fused path) for generality; the configs that use it are peak-scan
-// workloads far below the GPU's capacity.  The fused single-pass kernel (k1_spectral.cuh) stays the hot path.
+// One block no longer fits a CTA's registers/shared memory, so the transform is the classic four-step N = N1 x 256
+// split (N1 = 32 | 64 | 128 | 256) whose intermediate stays L2-resident where it can (126 MB L2):
+//   step 1  fast_cols{32,64,256}_kernel: the 256 column transforms of length N1 (x[r*256 + c], r < N1) in registers,
+//           multiplied by W_N^(c*k1), written to tmp[k1*256 + c]
+//   step 2  fast_rows256_kernel: N1 row transforms of 256 points (a half-warp each) over tmp[k1*256 + .]; X[k1 + N1*k2]
+//           goes through the same |X|^2 / dB projection as K1 (dsp/fft.go:32-36,71-85, rx/receiver.go:376-378), the
+//           CTA's share of the ten noise-window sums, x_to and the taps are fused in; the dB spectrum goes to one buffer
+//   cum     large_round_cum_kernel: float32 cumulation in block order (rx/receiver.go:404-407), flush / state save
+//           (or fast_rows256_seg_kernel: rows + cumulation in one segment-sequential kernel when there are enough segments)
+//   finish  large_nf_finish_kernel: adds the per-CTA window sums and runs dsp.FindNoiseFloor's selection
+// This is the block-parallel path: launches with few segments (a single wideband stream) and N = 16384 / 32768 use it;
+// the single-pass kernels (k1_mid8k.cuh, k1_wide.cuh) take N = 8192 / 65536 when a launch has enough segments.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -22,149 +21,21 @@
 namespace sdr {
 
 struct LargeGeom {
-    int n, n1, n2;  // N = n1 * n2; (32 | 256) x 256 run the register-resident kernels, the rest the Stockham kernels
+    int n, n1, n2;  // N = n1 * n2; (32 | 64 | 128 | 256) x 256 run the register-resident kernels
 };
-__host__ __device__ inline bool large_fast_geom(int n1, int n2) { return n2 == 256 && (n1 == 32 || n1 == 256); }
+__host__ __device__ inline bool large_fast_geom(int n1, int n2) { return n2 == 256 && (n1 == 32 || n1 == 64 || n1 == 128 || n1 == 256); }
 __host__ __device__ inline bool large_geom(int n, LargeGeom *g) {
     g->n = n;
     switch (n) {
         case 8192: g->n1 = 32; g->n2 = 256; return true;
-        case 16384: g->n1 = 128; g->n2 = 128; return true;
-        case 32768: g->n1 = 256; g->n2 = 128; return true;
+        case 16384: g->n1 = 64; g->n2 = 256; return true;
+        case 32768: g->n1 = 128; g->n2 = 256; return true;
         case 65536: g->n1 = 256; g->n2 = 256; return true;
     }
     return false;
 }
 
-constexpr int SUBFFT_F = 8;  // sub-FFTs per CTA
-
-struct SubFftArgs {
-    const float2 *in;      // step 1: IQ blocks [blocks][N]; step 2: tmp [blocks][N]
-    float2 *tmp;           // step 1 output
-    float *spectrum;       // step 2 outputs [blocks][N]
-    float *psd;
-    const float2 *tw_sub;  // W_L^m, m < L (L = this step's sub-FFT length)
-    const float2 *tw_n;    // W_N^m, m < N (step 1 only)
-    const float *window;   // [N] or nullptr (step 1 only)
-    const Segment *segs;   // step 1 reads IQ through the segment table (blocks of a batch are not contiguous)
-    const int *block_seg;  // [blocks] segment of each block
-    int n, n1, n2;
-    float db_offset;       // 10*log10(20/N^2)
-};
-
-// In-shared-memory Stockham FFT of F sub-FFTs of length L held in buf[0]; result in the returned buffer.
-// Threads: F * L/4; thread (f, i) does the radix-4 butterfly i of sub-FFT f in every pass.
-template <int L>
-__device__ __forceinline__ float2 *stockham(float2 *b0, float2 *b1, const float2 *__restrict__ tw, int f, int i) {
-    constexpr int LP = L + 1;  // row pitch (complex)
-    float2 *x = b0 + f * LP, *y = b1 + f * LP;
-    constexpr int T4 = L / 4;
-    int p = 1;
-#pragma unroll
-    for (int pass = 0; pass < 4; pass++) {
-        if (p * 4 > L) break;
-        const int k = i & (p - 1);
-        const int j = ((i - k) << 2) + k;
-        // W_{4p}^(k*m) = W_L^(k*m*L/(4p))
-        const int tstep = k * (L / (4 * p));
-        float2 u0 = x[i], u1 = x[i + T4], u2 = x[i + 2 * T4], u3 = x[i + 3 * T4];
-        if (p > 1) {
-            u1 = cmul(u1, tw[tstep]);
-            u2 = cmul(u2, tw[2 * tstep]);
-            u3 = cmul(u3, tw[3 * tstep]);
-        }
-        dft4(u0, u1, u2, u3);  // natural order: X0..X3
-        y[j] = u0;
-        y[j + p] = u1;
-        y[j + 2 * p] = u2;
-        y[j + 3 * p] = u3;
-        __syncthreads();
-        float2 *t = x;
-        x = y;
-        y = t;
-        p *= 4;
-    }
-    if (p < L) {  // one radix-2 pass (L = 128): p == L/2, thread i handles butterflies i and i + L/4
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int ii = i + h * T4;  // 0 .. L/2-1
-            const int k = ii & (p - 1);
-            const int j = ((ii - k) << 1) + k;
-            const float2 u0 = x[ii];
-            const float2 u1 = cmul(x[ii + L / 2], tw[k * (L / (2 * p))]);
-            y[j] = cadd(u0, u1);
-            y[j + p] = csub(u0, u1);
-        }
-        __syncthreads();
-        float2 *t = x;
-        x = y;
-        y = t;
-    }
-    return x - f * LP;  // base of the buffer that holds the results
-}
-
-// STEP 1: grid (N2 / F, blocks); STEP 2: grid (N1 / F, blocks).  L = sub-FFT length of this step.
-template <int L, int STEP>
-__global__ void __launch_bounds__(SUBFFT_F *L / 4) sub_fft_kernel(const SubFftArgs a) {
-    extern __shared__ __align__(16) unsigned char sub_smem[];
-    constexpr int F = SUBFFT_F, LP = L + 1, NT = F * L / 4;
-    float2 *b0 = reinterpret_cast<float2 *>(sub_smem);
-    float2 *b1 = b0 + F * LP;
-    const int tid = threadIdx.x;
-    const int blk = blockIdx.y;
-    const int f0 = blockIdx.x * F;
-    const int N = a.n, N1 = a.n1, N2 = a.n2;
-    if (STEP == 1) {
-        // element (f, r) = x[r*N2 + f0 + f]: consecutive threads read consecutive columns
-        const Segment sg = a.segs[a.block_seg[blk]];
-        const float2 *src = reinterpret_cast<const float2 *>(sg.iq) + (size_t)(blk - sg.block_out) * N;
-#pragma unroll 4
-        for (int idx = tid; idx < F * L; idx += NT) {
-            const int f = idx % F, r = idx / F;
-            float2 v = __ldg(&src[(size_t)r * N2 + f0 + f]);
-            if (a.window) {
-                const float w = __ldg(&a.window[r * N2 + f0 + f]);
-                v = __fmul2_rn(v, make_float2(w, w));
-            }
-            b0[f * LP + r] = v;
-        }
-    } else {
-        const float2 *src = a.in + (size_t)blk * N;
-#pragma unroll 4
-        for (int idx = tid; idx < F * L; idx += NT) {
-            const int f = idx / L, c = idx % L;
-            b0[f * LP + c] = src[(size_t)(f0 + f) * N2 + c];
-        }
-    }
-    __syncthreads();
-    const int f = tid / (L / 4), i = tid % (L / 4);
-    const float2 *res = stockham<L>(b0, b1, a.tw_sub, f, i);
-    if (STEP == 1) {
-        // A_c[k1] * W_N^(c*k1) -> tmp[k1*N2 + c]; consecutive threads write consecutive columns
-        float2 *dst = a.tmp + (size_t)blk * N;
-        for (int idx = tid; idx < F * L; idx += NT) {
-            const int ff = idx % F, k1 = idx / F;
-            const int c = f0 + ff;
-            const float2 w = __ldg(&a.tw_n[(int)(((long long)c * k1) & (N - 1))]);
-            dst[(size_t)k1 * N2 + c] = cmul(res[ff * LP + k1], w);
-        }
-    } else {
-        // X[k1 + N1*k2]: |X|^2, dB + 120, fftshift
-        for (int idx = tid; idx < F * L; idx += NT) {
-            const int ff = idx % F, k2 = idx / F;
-            const int k = (f0 + ff) + N1 * k2;
-            const int kk = (k + N / 2) & (N - 1);
-            const float2 v = res[ff * LP + k2];
-            const float2 sq = __fmul2_rn(v, v);
-            const float psd = sq.x + sq.y;
-            const float t = fmaf(3.01029995663981195f, fast_log2(psd), a.db_offset);
-            a.psd[(size_t)blk * N + kk] = psd;
-            a.spectrum[(size_t)blk * N + kk] = __fadd_rn(t, 120.0f);
-        }
-    }
-}
-
-// ---- register-resident sub-FFTs for the two BASELINE shapes (N = 8192 = 32 x 256, N = 65536 = 256 x 256) ----------
+// ---- register-resident sub-transforms (N = N1 x 256) ---------------------------------------------------------------
 // A 256-point transform is run by a HALF-WARP: lane hl keeps 16 points, radix-16 over n1 (x[16 n1 + hl]), twiddle
 // W256^(hl k1), one 16x16 transpose through the FFT's own shared-memory column (pitch 17, conflict-free, __syncwarp
 // only), radix-16 over n2.  Lane hl ends with X[hl + 16*OutIdx<16>(p)] in register p.  Same packed-f32x2 butterflies
@@ -295,6 +166,7 @@ struct FastStepArgs {
     float *spec_round;      // [round blocks][N] dB spectrum of the round (cumulation input)
     float *spectrum, *psd;  // [blocks][N] or nullptr (parity / scope)
     const float2 *tw256;    // W_256^m
+    const float2 *tw_n1;    // W_N1^m (the N1 = 128 column kernel's parity twiddle)
     const float2 *tw_step;  // [k1][c] = W_N^(c k1), k1 < N1, c < N2 (step 1)
     const float *window;
     const Segment *segs;    // all segments of the batch
@@ -383,6 +255,52 @@ __global__ void __launch_bounds__(256) fast_cols32_kernel(const FastStepArgs a) 
         const int k1 = OutIdx<32>::of(p);
         float2 x = v[p];
         if (k1 > 0) x = cmul(x, __ldg(&a.tw_step[(size_t)k1 * N2 + c]));
+        dst[(size_t)k1 * N2] = x;
+    }
+}
+
+// step 1, N1 = 64 (SPLIT = false: one thread per column, grid (N2 / 256, blocks), 256 threads) and N1 = 128 (SPLIT = true:
+// the 128-point column transform split by output parity between two threads, decimation in frequency as in k1_mid8k:
+// thread (c, h) forms u[m] = x[m] + (-1)^h x[m + 64], multiplies by W128^m when h = 1 (h is warp-uniform), runs the
+// 64-point transform and owns the outputs k1 = 2j + h; grid (N2 / 128, blocks), 256 threads).  The whole transform in
+// registers: 64 complex values per thread, one CTA per SM -- these block sizes (16384 / 32768) are no BASELINE shape, the
+// kernel exists so that they take the register-resident two-kernel path instead of the generic Stockham one.
+template <bool SPLIT>
+__global__ void __launch_bounds__(256, 1) fast_cols64_kernel(const FastStepArgs a) {
+    const int c = SPLIT ? blockIdx.x * 128 + (threadIdx.x & 127) : blockIdx.x * 256 + threadIdx.x;
+    const int h = SPLIT ? threadIdx.x >> 7 : 0;
+    const int blk = a.blk0 + blockIdx.y;
+    const int N = a.n, N2 = a.n2;
+    const Segment sg = a.segs[a.block_seg[blk]];
+    const float2 *src = reinterpret_cast<const float2 *>(sg.iq) + (size_t)(blk - sg.block_out) * N + c;
+    float2 v[64];
+#pragma unroll
+    for (int q = 0; q < 64; q++) {
+        const int r = (q & 7) * 8 + (q >> 3);  // issue order = consumption order of the first layer
+        float2 x0 = __ldg(&src[(size_t)r * N2]);
+        if (a.window) {
+            const float w = __ldg(&a.window[r * N2 + c]);
+            x0 = __fmul2_rn(x0, make_float2(w, w));
+        }
+        if (SPLIT) {
+            float2 x1 = __ldg(&src[(size_t)(r + 64) * N2]);
+            if (a.window) {
+                const float w = __ldg(&a.window[(r + 64) * N2 + c]);
+                x1 = __fmul2_rn(x1, make_float2(w, w));
+            }
+            const float2 sgn = h ? make_float2(-1.f, -1.f) : make_float2(1.f, 1.f);
+            x0 = __ffma2_rn(x1, sgn, x0);  // x0 + (-1)^h x1, exact
+            if (h && r > 0) x0 = cmul(x0, __ldg(&a.tw_n1[r]));
+        }
+        v[r] = x0;
+    }
+    dft64(v);
+    float2 *dst = a.tmp + (size_t)blockIdx.y * N + c;
+#pragma unroll
+    for (int p = 0; p < 64; p++) {
+        const int k1 = SPLIT ? 2 * OutIdx<64>::of(p) + h : OutIdx<64>::of(p);
+        float2 x = v[p];
+        if (SPLIT || OutIdx<64>::of(p) > 0) x = cmul(x, __ldg(&a.tw_step[(size_t)k1 * N2 + c]));
         dst[(size_t)k1 * N2] = x;
     }
 }
@@ -597,57 +515,6 @@ __global__ void __launch_bounds__(256) large_round_cum_kernel(const RoundCumArgs
     float cum = sg.state_in >= 0 ? a.cum_state[(size_t)sg.state_in * a.n + bin] : 0.f;
     const float *sp = a.spec_round + (size_t)(sg.block_out - a.blk0) * a.n + bin;
     for (int b = 0; b < sg.n_blocks; b++) cum = __fadd_rn(cum, sp[(size_t)b * a.n]);
-    float *dst = (sg.flush_idx >= 0) ? a.flush_cum + (size_t)sg.flush_idx * a.n : a.cum_state + (size_t)sg.state_out * a.n;
-    dst[bin] = cum;
-}
-
-struct LargePostArgs {
-    const float *psd, *spectrum;  // [blocks][N]
-    const Segment *segs;
-    const int *block_seg;
-    const WorkParams *works;
-    const int *listener_bins;
-    float *psd_floor;
-    double *variance;
-    float *taps;
-    int tap_stride;
-    int n;
-};
-
-// one CTA (128 threads) per block: dsp.FindNoiseFloor + listener taps
-__global__ void __launch_bounds__(128) large_post_kernel(const LargePostArgs a) {
-    __shared__ double wsum[32];
-    const int blk = blockIdx.x;
-    const WorkParams wp = a.works[a.segs[a.block_seg[blk]].work];
-    const float *psd = a.psd + (size_t)blk * a.n;
-    const int e = wp.edge_width;
-    const int ws = nf_window_size(a.n, e), n_win = nf_window_count(a.n, e);
-    nf_window_sums<128>(psd, wsum, wsum + 16, e, ws, n_win, threadIdx.x);
-    for (int l = threadIdx.x; l < wp.n_listeners; l += 128)
-        a.taps[(size_t)blk * a.tap_stride + l] = a.spectrum[(size_t)blk * a.n + a.listener_bins[wp.listener_off + l]];
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        const bool real = lane < n_win;
-        nf_select_variance(real ? wsum[lane] : 0.0, real ? wsum[16 + lane] : 0.0,
-                           real ? (double)psd[e + (lane + 1) * ws] : 0.0, ws, n_win, lane, &a.psd_floor[blk], &a.variance[blk]);
-    }
-}
-
-struct LargeCumArgs {
-    const float *spectrum;
-    const Segment *segs;
-    float *cum_state;
-    float *flush_cum;
-    int n;
-};
-
-// grid (N / 256, segments): thread = bin, blocks added in order (sequential float32, rx/receiver.go:404-407)
-__global__ void __launch_bounds__(256) large_cum_kernel(const LargeCumArgs a) {
-    const Segment sg = a.segs[blockIdx.y];
-    const int bin = blockIdx.x * 256 + threadIdx.x;
-    float cum = sg.state_in >= 0 ? a.cum_state[(size_t)sg.state_in * a.n + bin] : 0.f;
-    for (int b = 0; b < sg.n_blocks; b++) cum = __fadd_rn(cum, a.spectrum[(size_t)(sg.block_out + b) * a.n + bin]);
     float *dst = (sg.flush_idx >= 0) ? a.flush_cum + (size_t)sg.flush_idx * a.n : a.cum_state + (size_t)sg.state_out * a.n;
     dst[bin] = cum;
 }

@@ -376,8 +376,9 @@ def test_receiver_with_device_debounce_matches_oracle(capi, oracle, host, deboun
 
 @pytest.mark.parametrize("n", [16384, 32768])
 def test_stockham_block_sizes_against_the_oracle(capi, oracle, n):
-    """N = 16384 / 32768 (the shared-memory Stockham four-step kernels): noise floor, thresholds, key states, cumulation
-    and peak list against the oracle; tolerances from profiles/r2_error_table.md"""
+    """N = 16384 / 32768 (64 x 256 and 128 x 256: fast_cols64_kernel + fast_rows256_kernel; round 1 ran them through the
+    shared-memory Stockham four-step kernels): noise floor, thresholds, key states, cumulation and peak list against the
+    oracle; tolerances from profiles/r2_error_table.md"""
     import test_gpu_parity as tp
     fs = 48000 * n // 512
     rng = np.random.default_rng(n)

@@ -38,8 +38,8 @@ CASES = [
     ("cfg3-like N=8192 L=50", 8192, 768000, 50, 444, 100),
     ("cfg3 768 kS/s N=8192 L=200, 64 streams", 8192, 768000, 200, 64, 100),
     ("cfg3 768 kS/s N=8192 L=200, 64 streams (r1 two-kernel large-block path)", 8192, 768000, 200, 64, 100, {"SDR_K1_MID8K": "0"}),
-    ("N=16384 L=100 (Stockham four-step)", 16384, 1536000, 100, 222, 100),
-    ("N=32768 L=100 (Stockham four-step)", 32768, 3072000, 100, 111, 100),
+    ("N=16384 L=100 (64 x 256)", 16384, 1536000, 100, 222, 100),
+    ("N=32768 L=100 (128 x 256)", 32768, 3072000, 100, 111, 100),
     ("cfg5 24.576 MS/s N=65536 peak scan, 64 streams", 65536, 24576000, 0, 64, 100),
     ("cfg5 24.576 MS/s N=65536 peak scan, 72 streams, lookahead 4", 65536, 24576000, 0, 72, 100, {"SDR_K1_WIDE_LOOKAHEAD": "4"}),
     ("cfg5 24.576 MS/s N=65536 peak scan, 72 streams, ring 8", 65536, 24576000, 0, 72, 100, {"SDR_K1_WIDE_RING": "8"}),
