@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsdrgpu.so")
 SOURCES = ["engine.cu", "goertzel.cu"]
-HEADERS = ["fft_radix.cuh", "k1_spectral.cuh", "k1_large.cuh", "k1_mid.cuh", "k1_mid4k.cuh", "k1_mid8k.cuh", "k1_warp.cuh", "k1_wide.cuh", "k2_post.cuh", "k3_goertzel.cuh"]
+HEADERS = ["fft_radix.cuh", "k1_spectral.cuh", "k1_large.cuh", "k1_mid4k.cuh", "k1_mid8k.cuh", "k1_warp.cuh", "k1_wide.cuh", "k2_post.cuh", "k3_goertzel.cuh"]
 
 
 def nvcc_path() -> str:

@@ -29,7 +29,6 @@
 #include "k1_spectral.cuh"
 #include "k2_post.cuh"
 #include "k1_large.cuh"
-#include "k1_mid.cuh"
 #include "k1_mid4k.cuh"
 #include "k1_mid8k.cuh"
 #include "k1_warp.cuh"
@@ -142,14 +141,12 @@ struct sdr_engine {
     float2 *d_tw512 = nullptr, *d_tw256w = nullptr;
     bool k1_warp = false;
     int k1w_grid_cap = 0;
-    // N = 4096 / 8192: fused single-pass kernel (k1_mid.cuh), SDR_K1_MID=0 disables it
+    // N = 4096 / 8192: step twiddles [k1][c] = W_N^(c k1) and W_256^m of the fused single-pass kernels
     float2 *d_tw_mid = nullptr, *d_tw256m = nullptr;
-    bool k1_mid = false;
-    int k1m_grid_cap = 0;
-    bool k1_mid4k = false;    // N = 4096: TMA-staged k1_mid4k_kernel instead of k1_mid_kernel<16> (SDR_K1_MID4K=0)
+    bool k1_mid4k = false;    // N = 4096: TMA-staged k1_mid4k_kernel (SDR_K1_MID4K=0: the three-pass kernel)
     int k1m4_grid_cap = 0;
     // N = 8192: TMA-staged 512-thread kernel (k1_mid8k.cuh), one CTA per SM.  SDR_K1_MID8K=0 disables it (the launch then
-    // falls back to k1_mid_kernel<32> / the two-kernel path), =force takes it for every launch, whatever the segment count
+    // takes the two-kernel path), =force takes it for every launch, whatever the segment count
     int k1_mid8k = 0;  // 0 off, 1 when the launch has enough segments, 2 always
     int k1m8_stages = 2;
     bool k1m8_groups = true;  // two decoupled 256-thread groups (k1_mid8k2_kernel); SDR_K1_MID8K_GROUPS=0: one 512-thread group
@@ -452,15 +449,6 @@ cudaError_t launch_k1_warp(const sdr_engine *e, const K1Args &a, bool dbg, cudaS
                             K1WarpGeom::SMEM_BYTES, st);
 }
 
-template <int R1>
-const void *k1m_fn(bool dbg, bool win) {
-    if (dbg) return win ? (const void *)k1_mid_kernel<R1, true, true> : (const void *)k1_mid_kernel<R1, true, false>;
-    return win ? (const void *)k1_mid_kernel<R1, false, true> : (const void *)k1_mid_kernel<R1, false, false>;
-}
-const void *k1m_fn(int n, bool dbg, bool win) { return n == 4096 ? k1m_fn<16>(dbg, win) : k1m_fn<32>(dbg, win); }
-int k1m_smem(int n) { return n == 4096 ? K1MidGeom<16>::SMEM_BYTES : K1MidGeom<32>::SMEM_BYTES; }
-int k1m_threads(int) { return 256; }
-
 const void *k1m4_fn(bool dbg, bool win) {
     if (dbg) return win ? (const void *)k1_mid4k_kernel<2, true, true> : (const void *)k1_mid4k_kernel<2, true, false>;
     return win ? (const void *)k1_mid4k_kernel<2, false, true> : (const void *)k1_mid4k_kernel<2, false, false>;
@@ -472,17 +460,6 @@ int k1m4_grid_cap_for(int sm_count) {  // 0: the kernel cannot run here
         if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, K1Mid4kGeom<2>::SMEM_BYTES) != cudaSuccess) return 0;
         if (v == 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 256, K1Mid4kGeom<2>::SMEM_BYTES) != cudaSuccess) return 0;
     }
-    return occ * sm_count;
-}
-
-int k1m_grid_cap_for(int n, bool win, int sm_count) {
-    int occ = 0;
-    for (int dbg = 0; dbg < 2; dbg++) {
-        const void *fn = k1m_fn(n, dbg != 0, win);
-        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k1m_smem(n));
-        if (!dbg) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, k1m_threads(n), k1m_smem(n));
-    }
-    if (occ < 1) occ = 1;
     return occ * sm_count;
 }
 
@@ -549,23 +526,9 @@ cudaError_t launch_k1_mid4k(const sdr_engine *e, const K1Args &a, bool dbg, cuda
     return cudaLaunchKernel(k1m4_fn(dbg, a.window != nullptr), dim3(grid), dim3(256), params, K1Mid4kGeom<2>::SMEM_BYTES, st);
 }
 
-cudaError_t launch_k1_mid(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st) {
-    int grid = a.n_segs;
-    if (grid > e->k1m_grid_cap) {
-        const int rounds = (grid + e->k1m_grid_cap - 1) / e->k1m_grid_cap;
-        grid = (a.n_segs + rounds - 1) / rounds;
-    }
-    if (grid < 1) grid = 1;
-    K1Args args = a;
-    const float2 *tws = e->d_tw_mid, *tw256 = e->d_tw256m;
-    void *params[] = {&args, &tws, &tw256};
-    return cudaLaunchKernel(k1m_fn(e->N, dbg, a.window != nullptr), dim3(grid), dim3(k1m_threads(e->N)), params, k1m_smem(e->N), st);
-}
-
 // warp_ok: N = 512 and every work has noise windows of at least K1WarpGeom::MIN_WS bins
 cudaError_t launch_k1(const sdr_engine *e, const K1Args &a, bool dbg, cudaStream_t st, bool i16 = false, bool warp_ok = true) {
     if (e->k1_mid4k && e->N == 4096 && !i16) return launch_k1_mid4k(e, a, dbg, st);
-    if (e->k1_mid && e->N == 4096 && !i16) return launch_k1_mid(e, a, dbg, st);
     if (e->k1_warp && warp_ok) return launch_k1_warp(e, a, dbg, st, i16);
     switch (e->N) {
         case 512: return launch_k1_n<512>(e, a, dbg, st, i16);
@@ -1061,9 +1024,6 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
         CKC(cudaMemcpy(e->d_tw_mid, t.data(), t.size() * sizeof(float2), cudaMemcpyHostToDevice));
         CKC(cudaMalloc((void **)&e->d_tw256m, t256.size() * sizeof(float2)));
         CKC(cudaMemcpy(e->d_tw256m, t256.data(), t256.size() * sizeof(float2), cudaMemcpyHostToDevice));
-        const char *v = getenv("SDR_K1_MID");
-        e->k1_mid = !(v && v[0] == '0');
-        if (e->k1_mid) e->k1m_grid_cap = k1m_grid_cap_for(e->N, e->d_window != nullptr, e->sm_count);
         if (e->N == 4096) {
             const char *v4 = getenv("SDR_K1_MID4K");
             if (!(v4 && v4[0] == '0')) {
@@ -1483,7 +1443,7 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     if (!e->large) {
         CK(e, launch_k1(e, a1, dbg, e->s_compute, i16, warp_ok));
         e->last_kernel = (e->k1_mid4k && e->N == 4096 && !i16) ? "k1_mid4k_kernel"
-                         : (e->k1_mid && e->N == 4096 && !i16) ? "k1_mid_kernel<16>" : (e->k1_warp && warp_ok) ? "k1_warp_kernel"
+                         : (e->k1_warp && warp_ok) ? "k1_warp_kernel"
                          : e->N == 512 ? "k1_spectral_kernel<512>" : e->N == 1024 ? "k1_spectral_kernel<1024>"
                          : e->N == 2048 ? "k1_spectral_kernel<2048>" : "k1_spectral_kernel<4096>";
     } else if (e->N == 8192 && block_off <= e->round_blocks && (e->k1_mid8k == 2 || (e->k1_mid8k == 1 && n_segs >= e->sm_count / 3))) {
@@ -1492,10 +1452,6 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
         const Mid8kNf nfb{s.d_nf_part, s.d_xto, s.d_nf_edge};
         CK(e, launch_k1_mid8k(e, a1, nfb, block_off, dbg, e->s_compute, &k1_launches));
         e->last_kernel = e->k1m8_groups ? "k1_mid8k2_kernel" : "k1_mid8k_kernel";
-    } else if (e->k1_mid && e->N == 8192 && block_off <= e->round_blocks && n_segs >= 2 * e->sm_count) {
-        // enough segments to fill the GPU with segment-sequential CTAs: fused single pass (k1_mid.cuh)
-        CK(e, launch_k1_mid(e, a1, dbg, e->s_compute));
-        e->last_kernel = "k1_mid_kernel<32>";
     } else if (use_wide) {
         // single pass over HBM: one team of 16 CTAs per segment, the intermediate in an L2-resident ring (k1_wide.cuh)
         const LargeFastBufs lb{s.d_tmp, s.d_spec_round, s.d_nf_part, s.d_xto, s.d_nf_edge};

@@ -4,8 +4,8 @@
 // Reference arithmetic: dsp/fft.go:23-85 (FFT, fftshift, |X|^2, dB + 120), dsp/fft.go:215-252 (FindNoiseFloor),
 // rx/receiver.go:393 (listener taps), rx/receiver.go:404-407 (cumulation, float32, block order).
 //
-// k1_mid_kernel<16> loads global -> registers directly (nothing in flight while it computes) and re-reads its step
-// twiddles from L1 per block: 43 % of the HBM roofline.  Here a CTA of 256 threads owns a segment (<= 100 consecutive
+// Round 1's kernel for this size loaded global -> registers directly (nothing in flight while it computed) and re-read its
+// step twiddles from L1 per block: 43 % of the HBM roofline.  Here a CTA of 256 threads owns a segment (<= 100 consecutive
 // blocks of one stream), two CTAs per SM:
 //   staging   thread 0 keeps NSTAGE whole blocks (32 KB each) in flight with cp.async.bulk (TMA, SASS UBLKCP) into a
 //             shared-memory ring guarded by mbarriers -- block b+1 lands while block b is transformed;

@@ -4,9 +4,9 @@
 // Reference arithmetic: dsp/fft.go:23-85 (FFT, fftshift, |X|^2, dB + 120), dsp/fft.go:215-252 (FindNoiseFloor),
 // rx/receiver.go:393 (listener taps), rx/receiver.go:404-407 (cumulation, float32, block order).
 //
-// Why a second kernel next to k1_mid_kernel<32>: that one loads global -> registers directly (nothing in flight while
-// it computes: 33 % of the HBM roofline, long-scoreboard bound, 16 warps per SM in two CTAs) and re-reads 31 step
-// twiddles per column from L1.  Here ONE CTA of 512 threads per SM owns a segment (<= 100 consecutive blocks of one
+// Round 1's kernel for this size (removed) loaded global -> registers directly (nothing in flight while it computed: 33 %
+// of the HBM roofline, long-scoreboard bound, 16 warps per SM in two CTAs) and re-read 31 step twiddles per column from
+// L1.  Here ONE CTA of 512 threads per SM owns a segment (<= 100 consecutive blocks of one
 // stream):
 //   staging   thread 0 keeps NSTAGE whole blocks (64 KB each) in flight with cp.async.bulk (TMA, SASS UBLKCP) into a
 //             shared-memory ring guarded by mbarriers -- block b+1 lands while block b is transformed;

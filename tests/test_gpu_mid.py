@@ -1,6 +1,6 @@
-"""The fused single-pass kernels for N = 4096 / 8192 (csrc/k1_mid4k.cuh, k1_mid.cuh) against the oracle and against the
-kernels they replace (k1_mid<16> and the three-pass K1 at 4096, the two-kernel large-block path at 8192; selected with
-SDR_K1_MID4K=0 / SDR_K1_MID=0)."""
+"""The fused single-pass kernels for N = 4096 / 8192 (csrc/k1_mid4k.cuh, k1_mid8k.cuh) against the oracle and against the
+kernels that serve the same sizes without them (the three-pass K1 at 4096, the two-kernel large-block path at 8192;
+selected with SDR_K1_MID4K=0 / SDR_K1_MID8K=0)."""
 import numpy as np
 import pytest
 
@@ -14,7 +14,7 @@ NAMES = ("psd_noise_floor", "noise_variance", "thresholds", "taps", "keys", "flu
 
 
 def test_mid_4096_batch_against_oracle(capi, oracle, monkeypatch):
-    monkeypatch.delenv("SDR_K1_MID", raising=False)
+    monkeypatch.delenv("SDR_K1_MID4K", raising=False)
     n, fs = 4096, 384000
     rng = np.random.default_rng(4096)
     tones = synth.make_tones(rng, 30, n, 70, wpm_range=(18.0, 28.0))
@@ -27,7 +27,7 @@ def test_mid_4096_batch_against_oracle(capi, oracle, monkeypatch):
 
 @pytest.mark.parametrize("edge", [0, 70, 300, 1000])
 def test_mid_4096_edge_widths_and_ragged_bit_identity(capi, oracle, monkeypatch, edge):
-    monkeypatch.delenv("SDR_K1_MID", raising=False)
+    monkeypatch.delenv("SDR_K1_MID4K", raising=False)
     n, fs = 4096, 384000
     spec = tp._spec(n, fs, 237, seed=edge + 5, k=6)
     iq = synth.generate(spec)
@@ -60,17 +60,16 @@ def _agree(a, b, n_listen):
 
 
 def test_mid_4096_kernels_agree(capi, monkeypatch):
-    """N = 4096 has three spectral kernels: the TMA-staged k1_mid4k_kernel (default), round 1's k1_mid_kernel<16>
-    (SDR_K1_MID4K=0) and the three-pass kernel (also SDR_K1_MID=0)"""
+    """N = 4096 has two spectral kernels: the TMA-staged k1_mid4k_kernel (default) and the three-pass kernel
+    (SDR_K1_MID4K=0)"""
     n, fs, nb = 4096, 384000, 120
     rng = np.random.default_rng(77)
     specs = [synth.StreamSpec(sample_rate=fs, block_size=n, n_blocks=nb, seed=70 + i,
                               tones=synth.make_tones(rng, 10, n, 70)) for i in range(4)]
     iqs = [synth.generate(sp) for sp in specs]
     res, names = [], []
-    for env in ({}, {"SDR_K1_MID4K": "0"}, {"SDR_K1_MID4K": "0", "SDR_K1_MID": "0"}):
-        for k in ("SDR_K1_MID4K", "SDR_K1_MID"):
-            monkeypatch.delenv(k, raising=False)
+    for env in ({}, {"SDR_K1_MID4K": "0"}):
+        monkeypatch.delenv("SDR_K1_MID4K", raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         with capi.Engine(n, max_streams=4, max_listeners=16, max_blocks_per_batch=4 * nb, max_peaks_per_flush=n // 2 + 1) as eng:
@@ -78,22 +77,24 @@ def test_mid_4096_kernels_agree(capi, monkeypatch):
             works = [dict(stream=s, iq=x, listener_bins=[t.bin for t in sp.tones]) for s, x, sp in zip(ss, iqs, specs)]
             res.append(eng.collect(eng.submit(works, capi.WANT_FLUSH_CUM)))
             names.append(eng.last_kernel())
-    assert names == ["k1_mid4k_kernel", "k1_mid_kernel<16>", "k1_spectral_kernel<4096>"]
+    assert names == ["k1_mid4k_kernel", "k1_spectral_kernel<4096>"]
     _agree(res[0], res[1], 10)
-    _agree(res[0], res[2], 10)
 
 
 def test_mid_8192_many_streams_agrees_with_two_kernel_path_and_oracle(capi, oracle, monkeypatch):
-    """the fused kernel takes N = 8192 launches with >= 2 segments per SM; 320 streams x 104 blocks cross a
-    cumulation boundary (two segments per stream, state rows ping-pong)"""
+    """k1_mid8k2_kernel takes N = 8192 launches with >= 49 segments, the two-kernel path the others (and all of them with
+    SDR_K1_MID8K=0); 320 streams x 104 blocks cross a cumulation boundary (two segments per stream, state rows ping-pong)"""
     n, fs, nb, ns = 8192, 768000, 104, 320
     rng = np.random.default_rng(8)
     base = [synth.generate(synth.StreamSpec(sample_rate=fs, block_size=n, n_blocks=nb, seed=800 + i,
                                             tones=synth.make_tones(rng, 8, n, 70))) for i in range(4)]
     binss = [np.sort(rng.choice(np.arange(80, n - 80), size=6, replace=False)).astype(np.int32) for _ in range(ns)]
-    res = []
+    res, names = [], []
     for mid in ("1", "0"):
-        monkeypatch.setenv("SDR_K1_MID", mid)
+        if mid == "1":
+            monkeypatch.delenv("SDR_K1_MID8K", raising=False)
+        else:
+            monkeypatch.setenv("SDR_K1_MID8K", "0")
         with capi.Engine(n, max_streams=ns, max_listeners=8, max_blocks_per_batch=ns * nb, max_peaks_per_flush=256) as eng:
             ss = [eng.open_stream(fs) for _ in range(ns)]
             works = [dict(stream=ss[i], iq=base[i % 4], listener_bins=binss[i]) for i in range(ns)]
@@ -101,6 +102,8 @@ def test_mid_8192_many_streams_agrees_with_two_kernel_path_and_oracle(capi, orac
             keep = {k: np.array(getattr(first, k)) for k in ("psd_noise_floor", "keys", "taps")}
             second = eng.collect(eng.submit([dict(w, iq=w["iq"][2 * n * 50:]) for w in works], capi.WANT_FLUSH_CUM))
             res.append((keep, second))
+            names.append(eng.last_kernel())
+    assert names == ["k1_mid8k2_kernel", "fast_cols32_kernel + fast_rows256_kernel"]
     (k1, s1), (k0, s0) = res
     assert np.abs(k1["psd_noise_floor"] - k0["psd_noise_floor"]).max() <= 3e-6 * np.abs(k0["psd_noise_floor"]).max()
     assert (k1["keys"] != k0["keys"]).sum() <= 6

@@ -27,13 +27,13 @@ CASES = [
     ("cfg2/cfg4 192 kS/s N=2048 L=50", 2048, 192000, 50, 148 * 12, 100),
     ("cfg4 literal N=2048 L=50, 64 streams x 2000 blocks", 2048, 192000, 50, 64, 2000),
     ("N=4096 L=100", 4096, 384000, 100, 148 * 4, 100),
-    ("N=4096 L=100 (r1 k1_mid<16>)", 4096, 384000, 100, 148 * 4, 100, {"SDR_K1_MID4K": "0"}),
-    # >= 2 GiB of blocks per batch like the other shapes; 512 streams also give the fused N = 8192
-    # kernel (k1_mid.cuh) its >= 2 segments per SM, below that the engine takes the block-parallel two-kernel path
+    ("N=4096 L=100 (three-pass kernel)", 4096, 384000, 100, 148 * 4, 100, {"SDR_K1_MID4K": "0"}),
+    # >= 2 GiB of blocks per batch like the other shapes; 444 streams = three segments per SM for the
+    # fused N = 8192 kernel (k1_mid8k.cuh); below 49 segments the engine takes the block-parallel two-kernel path
     ("cfg3 768 kS/s N=8192 L=200 (k1_mid8k: TMA ring, 512 threads)", 8192, 768000, 200, 444, 100),
     ("cfg3 768 kS/s N=8192 L=200 (k1_mid8k, one 512-thread group)", 8192, 768000, 200, 444, 100, {"SDR_K1_MID8K_GROUPS": "0"}),
     ("cfg3 768 kS/s N=8192 L=200 (k1_mid8k, 1 stage)", 8192, 768000, 200, 444, 100, {"SDR_K1_MID8K_STAGES": "1"}),
-    ("cfg3 768 kS/s N=8192 L=200 (r1 k1_mid<32>)", 8192, 768000, 200, 512, 100, {"SDR_K1_MID8K": "0"}),
+    ("cfg3 768 kS/s N=8192 L=200 (two-kernel path)", 8192, 768000, 200, 444, 100, {"SDR_K1_MID8K": "0"}),
     ("cfg3-like N=8192 L=0 (no listeners)", 8192, 768000, 0, 444, 100),
     ("cfg3-like N=8192 L=50", 8192, 768000, 50, 444, 100),
     ("cfg3 768 kS/s N=8192 L=200, 64 streams", 8192, 768000, 200, 64, 100),
