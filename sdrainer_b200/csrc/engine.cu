@@ -149,7 +149,6 @@ struct sdr_engine {
     // takes the two-kernel path), =force takes it for every launch, whatever the segment count
     int k1_mid8k = 0;  // 0 off, 1 when the launch has enough segments, 2 always
     int k1m8_stages = 2;
-    bool k1m8_groups = true;  // two decoupled 256-thread groups (k1_mid8k2_kernel); SDR_K1_MID8K_GROUPS=0: one 512-thread group
     float *d_window = nullptr;
     float *d_cum_state = nullptr;
     RollingState *d_rolling = nullptr;
@@ -463,14 +462,7 @@ int k1m4_grid_cap_for(int sm_count) {  // 0: the kernel cannot run here
     return occ * sm_count;
 }
 
-template <int NSTAGE>
-const void *k1m8_fn(bool dbg, bool win) {
-    if (dbg) return win ? (const void *)k1_mid8k_kernel<NSTAGE, true, true> : (const void *)k1_mid8k_kernel<NSTAGE, true, false>;
-    return win ? (const void *)k1_mid8k_kernel<NSTAGE, false, true> : (const void *)k1_mid8k_kernel<NSTAGE, false, false>;
-}
-const void *k1m8_fn(int stages, bool dbg, bool win) { return stages == 1 ? k1m8_fn<1>(dbg, win) : k1m8_fn<2>(dbg, win); }
 int k1m8_smem(int stages) { return stages == 1 ? K1Mid8kGeom<1>::SMEM_BYTES : K1Mid8kGeom<2>::SMEM_BYTES; }
-
 template <int NSTAGE>
 const void *k1m8g_fn(bool dbg, bool win) {
     if (dbg) return win ? (const void *)k1_mid8k2_kernel<NSTAGE, true, true> : (const void *)k1_mid8k2_kernel<NSTAGE, true, false>;
@@ -489,11 +481,6 @@ cudaError_t launch_k1_mid8k(const sdr_engine *e, const K1Args &a, const Mid8kNf 
     if (grid < 1) grid = 1;
     K1Args args = a;
     const float2 *tws = e->d_tw_mid, *tw256 = e->d_tw256m;
-    if (!e->k1m8_groups) {
-        void *params[] = {&args, &tws, &tw256};
-        *n_launches = 1;
-        return cudaLaunchKernel(k1m8_fn(e->k1m8_stages, dbg, a.window != nullptr), dim3(grid), dim3(512), params, k1m8_smem(e->k1m8_stages), st);
-    }
     Mid8kNf nfa = nfb;
     void *params[] = {&args, &tws, &tw256, &nfa};
     cudaError_t rc = cudaLaunchKernel(k1m8g_fn(e->k1m8_stages, dbg, a.window != nullptr), dim3(grid), dim3(512), params, k1m8_smem(e->k1m8_stages), st);
@@ -1037,12 +1024,8 @@ int sdr_engine_create(const sdr_engine_config *cfg, sdr_engine **out) {
             e->k1_mid8k = (v8 && v8[0] == '0') ? 0 : (v8 && v8[0] == 'f') ? 2 : 1;
             const char *st = getenv("SDR_K1_MID8K_STAGES");
             e->k1m8_stages = (st && st[0] == '1') ? 1 : 2;
-            const char *gv = getenv("SDR_K1_MID8K_GROUPS");
-            e->k1m8_groups = !(gv && gv[0] == '0');
             for (int dbgv = 0; dbgv < 2 && e->k1_mid8k; dbgv++)
-                if (cudaFuncSetAttribute(k1m8_fn(e->k1m8_stages, dbgv != 0, e->d_window != nullptr), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         k1m8_smem(e->k1m8_stages)) != cudaSuccess ||
-                    cudaFuncSetAttribute(k1m8g_fn(e->k1m8_stages, dbgv != 0, e->d_window != nullptr), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                if (cudaFuncSetAttribute(k1m8g_fn(e->k1m8_stages, dbgv != 0, e->d_window != nullptr), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          k1m8_smem(e->k1m8_stages)) != cudaSuccess)
                     e->k1_mid8k = 0;
             cudaGetLastError();
@@ -1451,7 +1434,7 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
         // two-kernel path (which does not serialise the blocks of a stream) is faster.
         const Mid8kNf nfb{s.d_nf_part, s.d_xto, s.d_nf_edge};
         CK(e, launch_k1_mid8k(e, a1, nfb, block_off, dbg, e->s_compute, &k1_launches));
-        e->last_kernel = e->k1m8_groups ? "k1_mid8k2_kernel" : "k1_mid8k_kernel";
+        e->last_kernel = "k1_mid8k2_kernel";
     } else if (use_wide) {
         // single pass over HBM: one team of 16 CTAs per segment, the intermediate in an L2-resident ring (k1_wide.cuh)
         const LargeFastBufs lb{s.d_tmp, s.d_spec_round, s.d_nf_part, s.d_xto, s.d_nf_edge};

@@ -19,10 +19,10 @@
 //             through the row's own storage; lane hl ends with X[k1 + 32 k2], k2 = hl + 16 q;
 //   epilogue  in registers: |X|^2, dB, cumulation (16 bins per thread, sequential float32 adds in block order);
 //             |X|^2 is parked in the dead row storage for the noise windows, x_to and the taps;
-//   noise     thread (window w, row k1) sums the <= 26 bins of window w that live in row k1 (contiguous floats, no
-//             index arithmetic), a float64 warp reduction over the 32 rows gives the window's (sum x, sum x^2);
-//             dsp.FindNoiseFloor's sequential selection runs batched, one lane per block, every 8 blocks.
-// Three CTA barriers per block; the next block's pass A (stage reads only) overlaps this block's noise phase.
+//   noise     thread (window w, row k1) sums the <= 26 bins of window w that live in row k1 (nf_row_share_tested, k1_large.cuh),
+//             a float64 half-warp reduction over a group's 16 rows gives its share of the window's (sum x, sum x^2);
+//             large_nf_finish_kernel adds the two groups' shares and runs dsp.FindNoiseFloor's selection.
+// Three group barriers per block; the next block's pass A (stage reads only) overlaps this block's noise phase.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -47,224 +47,10 @@ struct K1Mid8kGeom {
     static constexpr int SMEM_BYTES = OFF_BAR + NSTAGE * 8 + 64;
 };
 
-template <int NSTAGE, bool DEBUG_STORE, bool HAS_WINDOW>
-__global__ void __launch_bounds__(512, 1) k1_mid8k_kernel(const K1Args a, const float2 *__restrict__ tw_step,
-                                                           const float2 *__restrict__ tw256) {
-    using Gm = K1Mid8kGeom<NSTAGE>;
-    constexpr int N = Gm::N, NFB = Gm::NFB;
-    extern __shared__ __align__(128) unsigned char m8_smem[];
-    float2 *E = reinterpret_cast<float2 *>(m8_smem + Gm::OFF_E);      // [32][HW_PITCH]
-    float *Ef = reinterpret_cast<float *>(m8_smem + Gm::OFF_E);       // |X|^2 of bin kk at Ef[(kk & 31) * 2*HW_PITCH + (kk >> 5)]
-    float2 *TW = reinterpret_cast<float2 *>(m8_smem + Gm::OFF_TW);    // [15][16] W_256^(hl k)
-    double *NFS1 = reinterpret_cast<double *>(m8_smem + Gm::OFF_NF);  // [NFB][10]
-    double *NFS2 = NFS1 + NFB * 10;
-    float *NFX = reinterpret_cast<float *>(NFS2 + NFB * 10);
-    uint64_t *FULL = reinterpret_cast<uint64_t *>(m8_smem + Gm::OFF_BAR);
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int h = tid >> 8, c = tid & 255;      // pass A: column c, output parity h (warp-uniform)
-    const int f = tid >> 4, hl = tid & 15;      // pass B: row k1 = f, lane hl of its half-warp
-    const float db_offset = (float)(13.0102999566398120 - 20.0 * 13.0 * 0.30102999566398120);  // 10 log10(20) - 20 log10(N)
-    auto to_db = [&](float psd) -> float { return __fadd_rn(fmaf(3.01029995663981195f, fast_log2(psd), db_offset), 120.0f); };
-    auto psd_at = [&](int kk) -> float { return Ef[(kk & 31) * (2 * HW_PITCH) + (kk >> 5)]; };
-
-    const float2 sgn = h ? make_float2(-1.f, -1.f) : make_float2(1.f, 1.f);
-
-    // ---- one-time setup ----
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < NSTAGE; s++) mbar_init(&FULL[s], 1);
-        fence_mbar_init();
-    }
-    // per-lane layout [k - 1][hl] = W_256^(hl k): the sixteen lanes of a half-warp read sixteen consecutive words (both
-    // half-warps of a warp the same ones): one conflict-free wavefront per load instead of a strided table walk
-    if (tid < 240) TW[tid] = __ldg(&tw256[((tid & 15) * ((tid >> 4) + 1)) & 255]);
-    // step twiddles of this thread's sixteen outputs: register p of dft16 holds j = OutIdx<16>(p), k1 = 2j + h
-    float2 tws[16];
-#pragma unroll
-    for (int p = 0; p < 16; p++) tws[p] = __ldg(&tw_step[(2 * OutIdx<16>::of(p) + h) * 256 + c]);
-    __syncthreads();
-
-    // ---- producer iterator (thread 0 runs NSTAGE blocks ahead, across segment boundaries) ----
-    int pseg = blockIdx.x, pblk = 0, pn = 0;
-    if (pseg < a.n_segs) pn = __ldg(&a.segs[pseg].n_blocks);
-    uint32_t issued = 0;
-    auto issue_next = [&]() {
-        if (pseg >= a.n_segs) return;
-        const unsigned char *src = reinterpret_cast<const unsigned char *>(a.segs[pseg].iq) + (size_t)pblk * Gm::STAGE_BYTES;
-        const int s = issued % NSTAGE;
-        mbar_expect_tx(&FULL[s], Gm::STAGE_BYTES);
-        tma_load_1d(m8_smem + (size_t)s * Gm::STAGE_BYTES, src, Gm::STAGE_BYTES, &FULL[s]);
-        issued++;
-        if (++pblk == pn) {
-            pseg += gridDim.x;
-            pblk = 0;
-            if (pseg < a.n_segs) pn = a.segs[pseg].n_blocks;
-        }
-    };
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < NSTAGE; s++) issue_next();
-    }
-    uint32_t item = 0;
-
-    for (int seg = blockIdx.x; seg < a.n_segs; seg += gridDim.x) {
-        const Segment sg = a.segs[seg];
-        const WorkParams wp = a.works[sg.work];
-        const int L = wp.n_listeners;
-        const int *lbins = a.listener_bins + wp.listener_off;
-        const int e = wp.edge_width;
-        const int ws = nf_window_size(N, e), n_win = nf_window_count(N, e);
-        // noise floor: warp w < 10 owns window w, lane = row k1; the window's bins in that row are the positions
-        // [nf_p0, nf_p0 + nf_n) (bin kk = k1 + 32 p)
-        int nf_p0 = 0, nf_n = 0;
-        if (warp < 10) {
-            const int lo = e + warp * ws, hi = lo + ws, k1 = lane;
-            nf_p0 = lo < k1 ? 0 : (lo - k1 + 31) >> 5;
-            const int p1 = hi <= k1 ? 0 : min(256, (hi - k1 + 31) >> 5);
-            nf_n = max(p1 - nf_p0, 0);
-        }
-        int nf_fill = 0, nf_first = sg.block_out;
-
-        // cumulation registers: cum[p] is bin kk = f + 32*((hl + 16*OutIdx<16>(p) + 128) & 255)
-        float cum[16];
-#pragma unroll
-        for (int p = 0; p < 16; p++) {
-            const int kk = f + 32 * ((hl + 16 * OutIdx<16>::of(p) + 128) & 255);
-            cum[p] = sg.state_in >= 0 ? a.cum_state[(size_t)sg.state_in * N + kk] : 0.f;
-        }
-
-        for (int blk = 0; blk < sg.n_blocks; blk++, item++) {
-            const int s = item % NSTAGE;
-            const uint32_t parity = (item / NSTAGE) & 1u;
-            const float2 *IN = reinterpret_cast<const float2 *>(m8_smem + (size_t)s * Gm::STAGE_BYTES);
-            const int ob = sg.block_out + blk;
-            mbar_wait(&FULL[s], parity);
-
-            // ---------------- pass A: column c, outputs k1 = 2j + h ----------------
-            float2 v[16];
-#pragma unroll
-            for (int q = 0; q < 16; q++) {
-                const int m = (q & 3) * 4 + (q >> 2);  // issue order = consumption order of dft16's first layer
-                float2 x0 = IN[m * 256 + c], x1 = IN[(m + 16) * 256 + c];
-                if (HAS_WINDOW) {
-                    const float w0 = __ldg(&a.window[m * 256 + c]), w1 = __ldg(&a.window[(m + 16) * 256 + c]);
-                    x0 = __fmul2_rn(x0, make_float2(w0, w0));
-                    x1 = __fmul2_rn(x1, make_float2(w1, w1));
-                }
-                v[m] = __ffma2_rn(x1, sgn, x0);  // x0 + (-1)^h x1, exact
-            }
-            if (h) {  // warp-uniform: u[m] *= W32^m = W64^(2m)
-                v[1] = mul_w64<2>(v[1]);
-                v[2] = mul_w64<4>(v[2]);
-                v[3] = mul_w64<6>(v[3]);
-                v[4] = mul_w64<8>(v[4]);
-                v[5] = mul_w64<10>(v[5]);
-                v[6] = mul_w64<12>(v[6]);
-                v[7] = mul_w64<14>(v[7]);
-                v[8] = mul_w64<16>(v[8]);
-                v[9] = mul_w64<18>(v[9]);
-                v[10] = mul_w64<20>(v[10]);
-                v[11] = mul_w64<22>(v[11]);
-                v[12] = mul_w64<24>(v[12]);
-                v[13] = mul_w64<26>(v[13]);
-                v[14] = mul_w64<28>(v[14]);
-                v[15] = mul_w64<30>(v[15]);
-            }
-            dft16(v);
-#pragma unroll
-            for (int p = 0; p < 16; p++) v[p] = cmul(v[p], tws[p]);  // tws[0] = 1 when h = 0: one multiply kept for uniform code
-            // B0: every thread has consumed stage s (it can be refilled) and, for blk > 0, the previous block's
-            // noise-floor / tap reads of E are done (E can be overwritten)
-            __syncthreads();
-            if (tid == 0) {
-                fence_proxy_async();
-                issue_next();
-            }
-            if (nf_fill == NFB) {  // batched dsp.FindNoiseFloor selection (dsp/fft.go:217-251); NFS is rewritten after B2
-                if (warp == 15 && lane < NFB)
-                    nf_select_serial(NFS1 + lane * 10, NFS2 + lane * 10, NFX + lane * 10, 1, ws, n_win,
-                                     &a.psd_floor[nf_first + lane], &a.variance[nf_first + lane]);
-                nf_first += NFB;
-                nf_fill = 0;
-            }
-#pragma unroll
-            for (int p = 0; p < 16; p++) E[(2 * OutIdx<16>::of(p) + h) * HW_PITCH + c] = v[p];
-            __syncthreads();  // B1: E complete
-
-            // ---------------- pass B: half-warp f = row k1 ----------------
-            {
-                HwTwiddle t;
-#pragma unroll
-                for (int k = 1; k < 16; k++) t.w[k - 1] = TW[(k - 1) * 16 + hl];
-                float2 *col = E + f * HW_PITCH;
-#pragma unroll
-                for (int q = 0; q < 16; q++) {
-                    const int n1 = (q & 3) * 4 + (q >> 2);
-                    v[n1] = col[16 * n1 + hl];
-                }
-                fft256_halfwarp_regs(v, col, t, hl);
-                __syncwarp();  // transpose reads done: the row storage may take the |X|^2 values
-                float *prow = reinterpret_cast<float *>(col);
-#pragma unroll
-                for (int p = 0; p < 16; p++) {
-                    const int k2s = (hl + 16 * OutIdx<16>::of(p) + 128) & 255;  // fftshift (dsp/fft.go:54-57)
-                    const float psd = fmaf(v[p].x, v[p].x, v[p].y * v[p].y);    // dsp/fft.go:71-73
-                    const float db = to_db(psd);                                 // rx/receiver.go:376-378
-                    cum[p] = __fadd_rn(cum[p], db);                              // rx/receiver.go:404-406
-                    prow[k2s] = psd;
-                    if (DEBUG_STORE) {
-                        const int kk = f + 32 * k2s;
-                        a.dbg_spectrum[(size_t)ob * N + kk] = db;
-                        a.dbg_psd[(size_t)ob * N + kk] = psd;
-                    }
-                }
-            }
-            __syncthreads();  // B2: |X|^2 complete
-
-            // ---------------- dsp.FindNoiseFloor (dsp/fft.go:215-252): window sums ----------------
-            if (warp < 10) {
-                // float32 inside the <= 26-bin share of one row, float64 across the 32 rows of the window
-                // rows k1 and k1 + 16 share their banks (row pitch 2*273 words): the upper half-warp walks its share
-                // rotated by one element, so the two halves of the warp never meet in a bank
-                const float *pp = Ef + lane * (2 * HW_PITCH) + nf_p0;
-                const int rot = lane >> 4;
-                float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-#pragma unroll
-                for (int i = 0; i + 1 < Gm::NFMAX; i += 2) {
-                    const int j0 = (i + rot == Gm::NFMAX) ? 0 : i + rot, j1 = (i + 1 + rot == Gm::NFMAX) ? 0 : i + 1 + rot;
-                    const float x0 = (j0 < nf_n) ? pp[j0] : 0.f, x1 = (j1 < nf_n) ? pp[j1] : 0.f;
-                    s1a += x0;
-                    s2a = fmaf(x0, x0, s2a);
-                    s1b += x1;
-                    s2b = fmaf(x1, x1, s2b);
-                }
-                const double d1 = warp_sum((double)(s1a + s1b)), d2 = warp_sum((double)(s2a + s2b));
-                if (lane == 0 && warp < n_win) {
-                    NFS1[nf_fill * 10 + warp] = d1;
-                    NFS2[nf_fill * 10 + warp] = d2;
-                    NFX[nf_fill * 10 + warp] = psd_at(e + (warp + 1) * ws);  // x_to (dsp/fft.go:238-243)
-                }
-            } else {
-                // listener taps (rx/receiver.go:393): same dB function as the owner thread
-                for (int l = tid - 320; l < L; l += 192) a.taps[(size_t)ob * a.tap_stride + l] = to_db(psd_at(__ldg(&lbins[l])));
-            }
-            nf_fill++;
-        }
-        __syncthreads();  // the last block's window sums are in NFS; its reads of E are done
-        if (warp == 15 && lane < nf_fill)
-            nf_select_serial(NFS1 + lane * 10, NFS2 + lane * 10, NFX + lane * 10, 1, ws, n_win, &a.psd_floor[nf_first + lane],
-                             &a.variance[nf_first + lane]);
-
-        float *dst = (sg.flush_idx >= 0) ? a.flush_cum + (size_t)sg.flush_idx * N : a.cum_state + (size_t)sg.state_out * N;
-#pragma unroll
-        for (int p = 0; p < 16; p++) dst[f + 32 * ((hl + 16 * OutIdx<16>::of(p) + 128) & 255)] = cum[p];
-        __syncthreads();  // NFS is free for the next segment
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
-// k1_mid8k2_kernel: the same transform as two DECOUPLED groups of 256 threads.  Parity h of the column split owns the
+// k1_mid8k2_kernel: the transform above as two DECOUPLED groups of 256 threads (the first build ran the CTA as one
+// 512-thread group with three CTA-wide barriers per block and the selection inside the kernel: 42.6 % of the HBM roofline
+// against 44.4 % for this one on the same box, removed).  Parity h of the column split owns the
 // rows k1 = 2 fl + h in pass B as well, so group h (warps 8h .. 8h+7) never touches the other group's half of E: the
 // groups only share the TMA stages (both read every stage; the second one to finish a stage re-arms its copy) and run
 // out of phase like two CTAs would -- one group's barrier waits and shared-memory bursts are the other's compute time.

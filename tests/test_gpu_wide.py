@@ -153,3 +153,31 @@ def test_noise_window_geometry_over_edge_widths(capi, oracle, monkeypatch, n, en
     pu.check_scalars(res.psd_noise_floor, r.noise[:, 0], what=f"psdNoiseFloor, {ws}-bin windows")
     # narrow windows: the fp32 error of the few bins of a window does not average out (1.1e-4 measured with 17 bins)
     pu.check_scalars(res.noise_variance, r.noise[:, 1], rel=1e-4 if ws >= 100 else 5e-4, what=f"noise variance, {ws}-bin windows")
+
+
+@pytest.mark.parametrize("n,env,kernel", [
+    (512, {}, "k1_warp_kernel"), (2048, {}, "k1_spectral_kernel<2048>"), (4096, {}, "k1_mid4k_kernel"),
+    (8192, {"SDR_K1_MID8K": "force"}, "k1_mid8k2_kernel"), (8192, {"SDR_K1_MID8K": "0"}, "fast_cols32_kernel + fast_rows256_kernel"),
+    (16384, {}, "fast_cols64_kernel + fast_rows256_kernel"), (32768, {}, "fast_cols64_kernel + fast_rows256_kernel"),
+    (65536, {"SDR_K1_WIDE": "force"}, "k1_wide_kernel"), (65536, {"SDR_K1_WIDE": "0"}, "fast_cols256_kernel + fast_rows256_kernel"),
+])
+def test_window_table_through_every_spectral_kernel(capi, oracle, monkeypatch, n, env, kernel):
+    """The optional window table (an extension: the reference applies none) multiplies in float32 before the transform in
+    every spectral kernel of the submit path: noise floor against the oracle run with the same window"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    fs = 48000 * n // 512
+    nb = 8 if n >= 16384 else 24
+    rng = np.random.default_rng(n)
+    tones = synth.make_tones(rng, 8, n, 70, keyed=False)
+    iq = synth.generate(synth.StreamSpec(sample_rate=fs, block_size=n, n_blocks=nb, seed=n + 9, tones=tones))
+    win = (np.hanning(n) + 0.01).astype(np.float32)
+    bins = [t.bin for t in tones][:6]
+    with capi.Engine(n, window=win, max_streams=1, max_listeners=8, max_blocks_per_batch=nb, max_peaks_per_flush=256) as eng:
+        sid = eng.open_stream(fs)
+        res = eng.collect(eng.submit([dict(stream=sid, iq=iq, listener_bins=bins)]))
+        assert eng.last_kernel() == kernel
+    r = oracle.process_stream(iq, n, window=win, listener_bins=bins, sample_rate=fs)
+    pu.check_scalars(res.psd_noise_floor, r.noise[:, 0], what="psdNoiseFloor with a window")
+    strong = r.taps > r.thresholds[:, :1] + 15  # the listeners sit on the tones: well above the mean noise floor (dB)
+    assert strong.any() and np.abs(res.taps[:, :len(bins)][strong] - r.taps[strong]).max() < 2e-3

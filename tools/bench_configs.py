@@ -31,7 +31,6 @@ CASES = [
     # >= 2 GiB of blocks per batch like the other shapes; 444 streams = three segments per SM for the
     # fused N = 8192 kernel (k1_mid8k.cuh); below 49 segments the engine takes the block-parallel two-kernel path
     ("cfg3 768 kS/s N=8192 L=200 (k1_mid8k: TMA ring, 512 threads)", 8192, 768000, 200, 444, 100),
-    ("cfg3 768 kS/s N=8192 L=200 (k1_mid8k, one 512-thread group)", 8192, 768000, 200, 444, 100, {"SDR_K1_MID8K_GROUPS": "0"}),
     ("cfg3 768 kS/s N=8192 L=200 (k1_mid8k, 1 stage)", 8192, 768000, 200, 444, 100, {"SDR_K1_MID8K_STAGES": "1"}),
     ("cfg3 768 kS/s N=8192 L=200 (two-kernel path)", 8192, 768000, 200, 444, 100, {"SDR_K1_MID8K": "0"}),
     ("cfg3-like N=8192 L=0 (no listeners)", 8192, 768000, 0, 444, 100),
