@@ -1501,10 +1501,12 @@ int sdr_submit(sdr_engine *e, const sdr_work *works, int n_works, int flags, sdr
     if (max_work_blocks > K2_SHORT_WORK) {  // long works: the float64 dB conversions run block-parallel in front of the chains
         k2_db_kernel<<<(s.n_blocks + K2_THREADS - 1) / K2_THREADS, K2_THREADS, 0, e->s_post>>>(a2);
         CK(e, cudaGetLastError());
-        k2_thresholds_kernel<true><<<(n_works + K2_WARPS - 1) / K2_WARPS, K2_THREADS, 0, e->s_post>>>(a2);
+        // few long works: the whole CTA serves one work (the parallel phases around the chain run four times as wide)
+        if (n_works <= 4 * e->sm_count) k2_thresholds_kernel<true, K2_THREADS><<<n_works, K2_THREADS, 0, e->s_post>>>(a2);
+        else k2_thresholds_kernel<true, 32><<<(n_works + K2_WARPS - 1) / K2_WARPS, K2_THREADS, 0, e->s_post>>>(a2);
         k2_launches++;
     } else {
-        k2_thresholds_kernel<false><<<(n_works + K2_WARPS - 1) / K2_WARPS, K2_THREADS, 0, e->s_post>>>(a2);
+        k2_thresholds_kernel<false, 32><<<(n_works + K2_WARPS - 1) / K2_WARPS, K2_THREADS, 0, e->s_post>>>(a2);
     }
     CK(e, cudaGetLastError());
     // keys and peaks both depend on the thresholds only: the peak scan goes to a side stream so that the two small,

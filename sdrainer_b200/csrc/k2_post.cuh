@@ -228,69 +228,78 @@ __global__ void __launch_bounds__(K2_THREADS) k2_db_kernel(const K2Args a) {
 // ring's content for i < 60, the input of step i - 60 afterwards), so the lanes stage inputs and outgoing values in
 // parallel and lanes 0 / 1 walk the two chains (noise floor / deviation) over plain arrays.
 // PRE: the inputs were staged by k2_db_kernel in thresholds[b].xy
-template <bool PRE>
+// GROUP: threads per work -- a warp (many works), or the whole CTA when the launch has few, long works: the parallel
+// phases around the chain then run four times as wide (one stream x 4000 blocks: 83 -> 30 us)
+template <bool PRE, int GROUP>
 __global__ void __launch_bounds__(K2_THREADS) k2_thresholds_kernel(const K2Args a) {
-    __shared__ float s_in_all[K2_WARPS][2][K2_WCHUNK];   // inputs of the two means
-    __shared__ float s_run_all[K2_WARPS][2][K2_WCHUNK];  // outgoing ring values, then the running sums
-    __shared__ RollingState s_roll_all[K2_WARPS];
-    const int wq = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wi = blockIdx.x * K2_WARPS + wq;
-    if (wi >= a.n_works) return;  // warp-uniform; nothing below synchronises across warps
-    float (*s_in)[K2_WCHUNK] = s_in_all[wq];
-    float (*s_run)[K2_WCHUNK] = s_run_all[wq];
+    static_assert(GROUP == 32 || GROUP == K2_THREADS, "a warp or the CTA per work");
+    constexpr int NGRP = K2_THREADS / GROUP;
+    constexpr int CH = GROUP == 32 ? K2_WCHUNK : 4 * K2_WCHUNK;  // blocks per pass: the CTA form stages 2048 (32 KB)
+    __shared__ float s_in_all[NGRP][2][CH];   // inputs of the two means
+    __shared__ float s_run_all[NGRP][2][CH];  // outgoing ring values, then the running sums
+    __shared__ RollingState s_roll_all[NGRP];
+    const int wq = threadIdx.x / GROUP, lane = threadIdx.x % GROUP;  // lane: index within the work's thread group
+    const int wi = blockIdx.x * NGRP + wq;
+    if (wi >= a.n_works) return;  // uniform in the group; nothing below synchronises across groups
+    auto gsync = [&]() {
+        if (GROUP == 32) __syncwarp();
+        else __syncthreads();
+    };
+    float (*s_in)[CH] = s_in_all[wq];
+    float (*s_run)[CH] = s_run_all[wq];
     RollingState &s_roll = s_roll_all[wq];
     const PostWork w = a.works[wi];
     const double n2 = 1.0 / ((double)a.n * (double)a.n);  // exact: N is a power of two
-    constexpr int RW = (int)(sizeof(RollingState) / 4), RPL = (RW + 31) / 32;
+    constexpr int RW = (int)(sizeof(RollingState) / 4), RPL = (RW + GROUP - 1) / GROUP;
 
     {  // the lanes copy the stream's rolling state (124 words), all loads in flight at once
         const uint32_t *src = reinterpret_cast<const uint32_t *>(a.rolling + w.stream);
         uint32_t *dst = reinterpret_cast<uint32_t *>(&s_roll);
         uint32_t r[RPL];
 #pragma unroll
-        for (int k = 0; k < RPL; k++) r[k] = (lane + 32 * k < RW) ? src[lane + 32 * k] : 0u;
+        for (int k = 0; k < RPL; k++) r[k] = (lane + GROUP * k < RW) ? src[lane + GROUP * k] : 0u;
 #pragma unroll
         for (int k = 0; k < RPL; k++)
-            if (lane + 32 * k < RW) dst[lane + 32 * k] = r[k];
+            if (lane + GROUP * k < RW) dst[lane + GROUP * k] = r[k];
     }
     // flushes of this work (rx/receiver.go:409-425): which block closed each window
-    for (int f = lane; f < w.n_flushes; f += 32) {
+    for (int f = lane; f < w.n_flushes; f += GROUP) {
         a.flush_block[w.flush_out + f] = w.block_out + w.first_flush_block + f * SDR_CUMULATION_SIZE;
         if (!w.do_peaks) a.flush_n_peaks[w.flush_out + f] = 0;
     }
-    __syncwarp();
+    gsync();
 
-    for (int c0 = 0; c0 < w.n_blocks; c0 += K2_WCHUNK) {
-        const int cn = min(K2_WCHUNK, w.n_blocks - c0);
+    for (int c0 = 0; c0 < w.n_blocks; c0 += CH) {
+        const int cn = min(CH, w.n_blocks - c0);
         // phase A (parallel): inputs of the two rolling means (rx/receiver.go:383-384)
-        if (PRE) {  // every load of the pass in flight at once (sixteen float4 per lane)
-            float4 t[K2_WCHUNK / 32];
+        if (PRE) {  // every load of the pass in flight at once
+            float4 t[CH / GROUP];
 #pragma unroll
-            for (int k = 0; k < K2_WCHUNK / 32; k++) {
-                const int i = lane + 32 * k;
+            for (int k = 0; k < CH / GROUP; k++) {
+                const int i = lane + GROUP * k;
                 t[k] = i < cn ? reinterpret_cast<const float4 *>(a.thresholds)[w.block_out + c0 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
-            for (int k = 0; k < K2_WCHUNK / 32; k++) {
-                const int i = lane + 32 * k;
+            for (int k = 0; k < CH / GROUP; k++) {
+                const int i = lane + GROUP * k;
                 if (i < cn) {
                     s_in[0][i] = t[k].x;
                     s_in[1][i] = t[k].y;
                 }
             }
         }
-        for (int i0 = 0; !PRE && i0 < cn; i0 += 128) {  // four blocks per lane and pass, the loads first
+        for (int i0 = 0; !PRE && i0 < cn; i0 += 4 * GROUP) {  // four blocks per thread and pass, the loads first
             float pf[4];
             double vr[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const int i = i0 + lane + 32 * k;
+                const int i = i0 + lane + GROUP * k;
                 pf[k] = i < cn ? a.psd_floor[w.block_out + c0 + i] : 1.f;
                 vr[k] = i < cn ? a.variance[w.block_out + c0 + i] : 1.0;
             }
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const int i = i0 + lane + 32 * k;
+                const int i = i0 + lane + GROUP * k;
                 if (i < cn) {
                     // T(float64(PSDValueIndB(T(math.Sqrt(var)), N) + dBmShift) * 0.25)
                     const float dev_db = psd_value_in_db_shifted((float)sqrt(vr[k]), n2);
@@ -299,39 +308,36 @@ __global__ void __launch_bounds__(K2_THREADS) k2_thresholds_kernel(const K2Args 
                 }
             }
         }
-        __syncwarp();
+        gsync();
         // the value each step pushes out of the ring
         const int next0 = s_roll.next;
-        for (int i = lane; i < cn; i += 32) {
+        for (int i = lane; i < cn; i += GROUP) {
             int p = next0 + i;
             if (p >= SDR_NOISE_WINDOW) p -= SDR_NOISE_WINDOW;
             if (p >= SDR_NOISE_WINDOW) p -= SDR_NOISE_WINDOW;  // only used for i < 60 (next0 < 60: one wrap)
             s_run[0][i] = i < SDR_NOISE_WINDOW ? s_roll.floor_values[p] : s_in[0][i - SDR_NOISE_WINDOW];
             s_run[1][i] = i < SDR_NOISE_WINDOW ? s_roll.dev_values[p] : s_in[1][i - SDR_NOISE_WINDOW];
         }
-        __syncwarp();
+        gsync();
         // phase B (sequential, float32, block order): lane 0 the noise floor, lane 1 the deviation
         if (lane < 2) {
             float sum = lane == 0 ? s_roll.floor_sum : s_roll.dev_sum;
             const float *in = s_in[lane];
             float *run = s_run[lane];
-            // eight steps per pass through registers, the next pass's operands loaded before this pass's results are
-            // stored: the chain then costs its two dependent float32 operations per step, not a shared-memory round trip
-            // (the arrays hold K2_WCHUNK entries, reading past cn is harmless)
-            float o[8], x[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                o[u] = run[u];
-                x[u] = in[u];
-            }
-            for (int i0 = 0; i0 < cn; i0 += 8) {
-                float o2[8], x2[8];
-                const int j0 = (i0 + 8 < K2_WCHUNK) ? i0 + 8 : i0;
+            // Eight steps per pass through registers, two register sets in ping-pong: the operands of the pass after next
+            // are requested before a pass computes, so the chain costs its two dependent float32 operations per step and
+            // no shared-memory latency (a plain loop over the arrays: 64 cycles per step in store -> load ordering; one
+            // register set with copies: 22).  The arrays hold CH entries; reading past cn (inside them) is harmless.
+            float o0[8], x0[8], o1[8], x1[8];
+            auto load = [&](float (&o)[8], float (&x)[8], int i0) {
+                const int j0 = (i0 + 8 <= CH) ? i0 : 0;  // stay inside the arrays
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
-                    o2[u] = run[j0 + u];
-                    x2[u] = in[j0 + u];
+                    o[u] = run[j0 + u];
+                    x[u] = in[j0 + u];
                 }
+            };
+            auto pass = [&](const float (&o)[8], const float (&x)[8], int i0) {
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
                     if (i0 + u < cn) {  // the last pass may be partial
@@ -339,18 +345,20 @@ __global__ void __launch_bounds__(K2_THREADS) k2_thresholds_kernel(const K2Args 
                         run[i0 + u] = sum;
                     }
                 }
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    o[u] = o2[u];
-                    x[u] = x2[u];
-                }
+            };
+            load(o0, x0, 0);
+            for (int i0 = 0; i0 < cn; i0 += 16) {
+                load(o1, x1, i0 + 8);
+                pass(o0, x0, i0);
+                load(o0, x0, i0 + 16);
+                pass(o1, x1, i0 + 8);
             }
             if (lane == 0) s_roll.floor_sum = sum;
             else s_roll.dev_sum = sum;
         }
-        __syncwarp();
+        gsync();
         // phase C (parallel): means, thresholds (rx/receiver.go:384-385,394); the ring takes the chunk's last 60 inputs
-        for (int i = lane; i < cn; i += 32) {
+        for (int i = lane; i < cn; i += GROUP) {
             const int b = w.block_out + c0 + i;
             const float noise_floor = __fdiv_rn(s_run[0][i], (float)SDR_NOISE_WINDOW);
             const float noise_dev = __fdiv_rn(s_run[1][i], (float)SDR_NOISE_WINDOW);
@@ -367,12 +375,12 @@ __global__ void __launch_bounds__(K2_THREADS) k2_thresholds_kernel(const K2Args 
             }
         }
         if (lane == 0) s_roll.next = (next0 + cn) % SDR_NOISE_WINDOW;
-        __syncwarp();
+        gsync();
     }
     {
         uint32_t *dst = reinterpret_cast<uint32_t *>(a.rolling + w.stream);
         const uint32_t *src = reinterpret_cast<const uint32_t *>(&s_roll);
-        for (int i = lane; i < RW; i += 32) dst[i] = src[i];
+        for (int i = lane; i < RW; i += GROUP) dst[i] = src[i];
     }
 }
 

@@ -33,6 +33,7 @@ CASES = [
     ("cfg3 768 kS/s N=8192 L=200 (k1_mid8k: TMA ring, 512 threads)", 8192, 768000, 200, 444, 100),
     ("cfg3 768 kS/s N=8192 L=200 (k1_mid8k, 1 stage)", 8192, 768000, 200, 444, 100, {"SDR_K1_MID8K_STAGES": "1"}),
     ("cfg3 768 kS/s N=8192 L=200 (two-kernel path)", 8192, 768000, 200, 444, 100, {"SDR_K1_MID8K": "0"}),
+    ("cfg3 literal N=8192 L=200, 1 stream x 4000 blocks", 8192, 768000, 200, 1, 4000),
     ("cfg3-like N=8192 L=0 (no listeners)", 8192, 768000, 0, 444, 100),
     ("cfg3-like N=8192 L=50", 8192, 768000, 50, 444, 100),
     ("cfg3 768 kS/s N=8192 L=200, 64 streams", 8192, 768000, 200, 64, 100),
