@@ -135,9 +135,12 @@ struct K1Geom {
     static constexpr int TW2_BYTES = 15 * R3 * 8;
     static constexpr int TPW = (T / 10) / 3 * 3;  // noise floor: threads per window (multiple of 3: lanes 3w..3w+2 combine)
     static constexpr int NF_MAX = ((N / 10 + TPW - 1) / TPW) | 1;  // longest per-thread share of a noise window (edge 0)
+    static constexpr int PART_PITCH = TPW + 1;   // partial sums [window][PART_PITCH]: the windows one warp combines sit 8 banks apart
+    static constexpr int PART_SLOTS = T + 16;    // >= 10 * PART_PITCH
     static constexpr int NFB = 16;               // noise floor: blocks whose window sums are batched for selection
     static constexpr int NF_BYTES = NFB * 10 * (8 + 8 + 4);
-    static constexpr int MISC_BYTES = NF_BYTES + T * 8 /*chunk partials (s1,s2)*/ + LMAX * 4 + NSTAGE * 8 /*mbar*/ + 64;
+    static constexpr int MISC_BYTES = NF_BYTES + PART_SLOTS * 8 /*share partials (s1,s2)*/ + LMAX * 4 + NSTAGE * 8 /*mbar*/ + 64;
+    static_assert(10 * PART_PITCH + (T - 10 * TPW) <= PART_SLOTS, "partial sums fit");
     static constexpr int GROUP_BYTES = ((NSTAGE * STAGE_BYTES + E1_BYTES + TW2_BYTES + MISC_BYTES) + 127) / 128 * 128;
     static constexpr int G = (T >= 128) ? 1 : 128 / T;  // groups per CTA
     static constexpr int CTA_THREADS = G * T;
@@ -326,7 +329,7 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS, SDR_K1_MINB) k1_spectr
     double *NFS2 = NFS1 + Gm::NFB * 10;
     float *NFX = reinterpret_cast<float *>(NFS2 + Gm::NFB * 10);
     float2 *PART = reinterpret_cast<float2 *>(NFX + Gm::NFB * 10);
-    int *LB = reinterpret_cast<int *>(PART + T);
+    int *LB = reinterpret_cast<int *>(PART + Gm::PART_SLOTS);
     uint64_t *FULL = reinterpret_cast<uint64_t *>(LB + Gm::LMAX);
 
     const int group_id = blockIdx.x * G + g;
@@ -394,11 +397,12 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS, SDR_K1_MINB) k1_spectr
         const int n_win = nf_window_count(N, e);  // the 10th window only closes if a later bin exists
         // this thread's share of the window sums: TPW threads per window, <= nf_len contiguous bins each
         constexpr int TPW = Gm::TPW;
-        int nf_lo = 0, nf_len = 0, nf_part = t;  // nf_part: slot of this thread's partial sums in PART ([window][part])
+        // nf_part: slot of this thread's partial sums in PART ([window][PART_PITCH]); threads without a share write zeros behind it
+        int nf_lo = 0, nf_len = 0, nf_part = 10 * Gm::PART_PITCH + max(t - 10 * Gm::TPW, 0);
         if (t < 10 * TPW) {
             const int grp = t / TPW, part = t - grp * TPW;
             const int w = wp.nf_map[grp];
-            nf_part = w * TPW + part;
+            nf_part = w * Gm::PART_PITCH + part;
             // an ODD share length makes the lane stride odd: the strided reads below are bank-conflict free
             // within a window (lanes of neighbouring windows can still collide)
             const int per = ((ws + TPW - 1) / TPW) | 1;
@@ -441,7 +445,7 @@ __global__ void __launch_bounds__(K1Geom<N>::CTA_THREADS, SDR_K1_MINB) k1_spectr
         auto nf_phase2 = [&]() {
             float s1 = 0.f, s2 = 0.f;
             if (nf_owner) {
-                const float2 *pp = PART + nf_w * TPW + nf_j;
+                const float2 *pp = PART + nf_w * Gm::PART_PITCH + nf_j;
 #pragma unroll
                 for (int m = 0; m < TPW / 3; m++) {
                     const float2 pr = pp[3 * m];
