@@ -146,6 +146,47 @@ __device__ __forceinline__ void fft256_halfwarp_regs(float2 (&v)[16], float2 *co
     dft16(v);
 }
 
+// The same transform with the fifteen lane twiddles formed from four table values (w1, w2, w4, w8 = W256^(hl), ^(2 hl),
+// ^(4 hl), ^(8 hl)) by eleven products: 4 shared-memory reads per transform instead of 15, 22 more packed instructions.
+__device__ __forceinline__ void fft256_halfwarp_regs_p2(float2 (&v)[16], float2 *col, float2 w1, float2 w2, float2 w4, float2 w8, int hl) {
+    dft16(v);
+#define SDR_PK(k) (4 * ((k) & 3) + ((k) >> 2))  // register that holds frequency index k (OutIdx<16>)
+    v[SDR_PK(1)] = cmul(v[SDR_PK(1)], w1);
+    v[SDR_PK(2)] = cmul(v[SDR_PK(2)], w2);
+    v[SDR_PK(4)] = cmul(v[SDR_PK(4)], w4);
+    v[SDR_PK(8)] = cmul(v[SDR_PK(8)], w8);
+    {
+        const float2 w3 = cmul(w1, w2);
+        v[SDR_PK(3)] = cmul(v[SDR_PK(3)], w3);
+        v[SDR_PK(11)] = cmul(v[SDR_PK(11)], cmul(w3, w8));
+        const float2 w7 = cmul(w3, w4);
+        v[SDR_PK(7)] = cmul(v[SDR_PK(7)], w7);
+        v[SDR_PK(15)] = cmul(v[SDR_PK(15)], cmul(w7, w8));
+    }
+    {
+        const float2 w5 = cmul(w1, w4);
+        v[SDR_PK(5)] = cmul(v[SDR_PK(5)], w5);
+        v[SDR_PK(13)] = cmul(v[SDR_PK(13)], cmul(w5, w8));
+        const float2 w6 = cmul(w2, w4);
+        v[SDR_PK(6)] = cmul(v[SDR_PK(6)], w6);
+        v[SDR_PK(14)] = cmul(v[SDR_PK(14)], cmul(w6, w8));
+    }
+    v[SDR_PK(9)] = cmul(v[SDR_PK(9)], cmul(w1, w8));
+    v[SDR_PK(10)] = cmul(v[SDR_PK(10)], cmul(w2, w8));
+    v[SDR_PK(12)] = cmul(v[SDR_PK(12)], cmul(w4, w8));
+#undef SDR_PK
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < 16; p++) col[OutIdx<16>::of(p) * 17 + hl] = v[p];
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        const int n2 = (q & 3) * 4 + (q >> 2);
+        v[n2] = col[hl * 17 + n2];
+    }
+    dft16(v);
+}
+
 // The register-resident path runs in ROUNDS of consecutive blocks [blk0, blk0 + round blocks): the four-step
 // intermediate and the dB spectrum of a round are addressed relative to blk0 and sized to stay L2-resident, so HBM
 // sees the IQ once; everything a block contributes per block (noise-window partial sums, taps) is produced by the

@@ -175,16 +175,17 @@ __global__ void __launch_bounds__(256, 2) k1_mid4k_kernel(const K1Args a, const 
 
             // ---------------- pass B: half-warp f = row k1 ----------------
             {
-                HwTwiddle t;
-#pragma unroll
-                for (int k = 1; k < 16; k++) t.w[k - 1] = TW[(k - 1) * 16 + hl];
                 float2 *col = E + f * HW_PITCH;
+                // four table reads (W256^(hl), ^(2 hl), ^(4 hl), ^(8 hl)) and eleven products instead of fifteen reads: this kernel
+                // is bound by the shared-memory pipe and has registers to spare (47.7 -> 50.7 % of the HBM roofline; the
+                // same change costs k1_mid8k2, at its 128-register cap, 5 %; keeping the four resident across blocks: 50.4 %)
+                const float2 w1 = TW[hl], w2 = TW[16 + hl], w4 = TW[48 + hl], w8 = TW[112 + hl];
 #pragma unroll
                 for (int q = 0; q < 16; q++) {
                     const int n1 = (q & 3) * 4 + (q >> 2);
                     v[n1] = col[16 * n1 + hl];
                 }
-                fft256_halfwarp_regs(v, col, t, hl);
+                fft256_halfwarp_regs_p2(v, col, w1, w2, w4, w8, hl);
                 __syncwarp();  // transpose reads done: the row storage may take the |X|^2 values
                 float *prow = Ef + plane_of(f);
 #pragma unroll

@@ -5,7 +5,7 @@ tolerances the parity tests use.
 
 Classes (by the ORACLE's PSD of the bin, per block):  signal = >= block noise floor + 15 dB;  floor = >= the block's
 noise-floor mean;  deep = below it (fades / nulls next to strong carriers).
-Usage (GPU box):  python tools/error_table.py
+Usage (GPU box):  python tools/error_table.py [N ...]   (with sizes: only those rows are re-measured, the others are kept)
 """
 import json
 import os
@@ -73,7 +73,14 @@ def one(n):
 def main():
     O.lib()
     capi.lib()
-    rows = [one(n) for n in (512, 1024, 2048, 4096, 8192, 16384, 32768, 65536)]
+    sizes = [int(x) for x in sys.argv[1:]] or [512, 1024, 2048, 4096, 8192, 16384, 32768, 65536]
+    rows = [one(n) for n in sizes]
+    committed = os.path.join(ROOT, "profiles", "r2_error_table.json")
+    if sys.argv[1:] and os.path.exists(committed):  # partial run: replace the measured rows, keep the rest
+        with open(committed) as f:
+            keep = {r["block_size"]: r for r in json.load(f)}
+        keep.update({r["block_size"]: r for r in rows})
+        rows = [keep[n] for n in sorted(keep)]
     # under gpurun only gpurun_out/ travels back: write there when it exists, else straight into profiles/
     out_dir = os.path.join(ROOT, "gpurun_out") if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else os.path.join(ROOT, "profiles")
     os.makedirs(out_dir, exist_ok=True)
