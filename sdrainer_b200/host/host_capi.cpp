@@ -1,5 +1,6 @@
 // host_capi.cpp -- C entry points over sdrhost.hpp so that the pytest suite can drive the C++ host mirror
 // (the tests mirror cw/decode_test.go, dsp/dsp_test.go, dsp/fft_test.go, rx/peaks_test.go, rx/listener_test.go).
+#include <cstdio>
 #include <string>
 #include <vector>
 
@@ -270,7 +271,8 @@ int sdrh_rt_run(void *p, int n_streams, int n_batches, int ring_copy, double *ou
         out[7] = (double)st.chars;
         out[8] = (double)st.key_downs;
         return 0;
-    } catch (const std::exception &) {
+    } catch (const std::exception &ex) {
+        fprintf(stderr, "sdrh_rt_run: %s\n", ex.what());  // the engine's message (sdr_last_error) for the caller's log
         return -1;
     }
 }

@@ -234,7 +234,9 @@ class RealtimeHarness:
     def run(self, n_streams, n_batches, ring_copy=True):
         out = (C.c_double * 9)()
         if self.L.sdrh_rt_run(self.h, n_streams, n_batches, 1 if ring_copy else 0, out) != 0:
-            raise RuntimeError("realtime harness: run failed")
+            # free the harness while its engine is still alive: a later __del__ would close streams through a dangling handle
+            self.close()
+            raise RuntimeError("realtime harness: run failed (the engine's message is on stderr)")
         return dict(zip(self.FIELDS, [float(x) for x in out]))
 
     def close(self):
