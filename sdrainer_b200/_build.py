@@ -32,8 +32,13 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in _deps())
 
 
+LOADED = False  # set by capi.lib(): this process has dlopen'ed LIB
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+    # A loaded library cannot be swapped: rebuilding it in place would give every later dlopen (libsdrhost.so's
+    # dependency) a SECOND copy whose kernels never had their attributes set by the engine the first copy created.
+    if not force and (LOADED or not is_stale()):
         return LIB
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-Xcompiler", "-fPIC", "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]

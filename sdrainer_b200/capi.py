@@ -94,6 +94,7 @@ def lib():
         raise RuntimeError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(the CUDA hot path has no CPU fallback)")
     L = C.CDLL(path)
+    _build.LOADED = True
     L.sdr_version.restype = C.c_char_p
     L.sdr_device_count.restype = C.c_int
     L.sdr_engine_create.argtypes = [C.POINTER(EngineConfig), C.POINTER(C.c_void_p)]

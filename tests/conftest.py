@@ -40,8 +40,10 @@ def oracle():
 def capi():
     """The product library.  On a GPU box a missing/unloadable library is a hard failure."""
     from sdrainer_b200 import _build, capi as cap
-    if not os.path.exists(_build.LIB):
-        _build.build()
+    # both libraries are brought up to date BEFORE the first dlopen (no-ops when they are newer than their sources):
+    # a rebuild of libsdrgpu.so after it has been loaded would put a second copy of it behind libsdrhost.so
+    _build.build()
+    _build.build_host()
     cap.lib()
     return cap
 
