@@ -50,3 +50,15 @@ def test_sass_has_tma_bulk_copy(capi):
     assert "sm_100a" in sass
     assert "UBLKCP" in sass
     assert "SYNCS" in sass  # mbarrier
+
+
+def test_loaded_library_is_never_rebuilt_in_place(monkeypatch):
+    """A stale libsdrgpu.so that this process has already loaded must not be rebuilt (a rebuilt file is a second copy
+    for every later dlopen: the host mirror then launches kernels whose attributes no engine set -> invalid argument)"""
+    from sdrainer_b200 import _build, capi
+    capi.lib()
+    assert _build.LOADED
+    monkeypatch.setattr(_build, "is_stale", lambda: True)
+    calls = []
+    monkeypatch.setattr(_build.subprocess, "check_call", lambda *a, **k: calls.append(a))
+    assert _build.build() == _build.LIB and not calls
